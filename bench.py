@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py - ray-samples/sec of the NSFF render_rays forward on B200 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1], SURVEY.md §8d cfg 2): full NSFF - static + dynamic field, scene-flow warp
+to t+1 and t-1 with re-query of the dynamic MLP, joint alpha composite - on a synthetic 512x288 frame x 128
+samples per ray, inference (no_grad; perturb=0, noise_std=0, output_transient_flow=['fw','bw','disocc']).
+A "step" = one render_rays forward over one frame per GPU (weak scaling: N GPUs render N frames per step,
+rank r renders frame index r) followed by ONE all-gather of the packed per-ray pixels (rgb, depth, flows).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scaling weak|strong]
+
+`value`  : ray-samples/s with rays/ts already resident in HBM, CUDA-event timed, max over ranks.
+`e2e`    : same metric through the public API from pinned HOST buffers (H2D of rays+ts and D2H of the
+           gathered pixels inside the timed region).
+`--impl reference`: the reference's own CPU implementation of this path is Python that cannot travel to the
+GPU box, so this arm times its pinned restatement (oracle/nsff_oracle.py, torch CPU, all host threads) on a
+bounded ray sample of the same workload; rank 0 only.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+IMG_WH = (512, 288)
+N_SAMPLES = 128
+N_FRAMES = 30
+FLOP_PER_POINT_MAIN = 2 * (630_016 + 583_680)        # static + dynamic branch, all heads  
+FLOP_PER_POINT_WARP = 2 * 582_912                    # dynamic branch, one flow head
+FLOP_PER_POINT = FLOP_PER_POINT_MAIN + 2 * FLOP_PER_POINT_WARP   # 4,759,040
+RENDER_KW = dict(N_samples=N_SAMPLES, perturb=0, noise_std=0, N_importance=0, test_time=False,
+                 output_transient_flow=["fw", "bw", "disocc"])
+CPU_SAMPLE_RAYS = 2048
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return dict(tflops=float(d["bf16_tflops_sustained"]), hbm=float(d["hbm_gbs"]), source="measured")
+    return dict(tflops=1400.0, hbm=6650.0, source="fallback")   # B200_PROFILING.md fallback (sustained)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                     nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+            while not self._stop_evt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.05)
+        except Exception as e:  # NVML missing: report that instead of inventing clocks
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = statistics.median(self.samples) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def _cpu_setup(n_rays):
+    from parity_util import build_fields, synthetic_rays
+    _, _, specs, enc = build_fields(W=256, seed=0, n_frames=N_FRAMES, device=None)
+    rays, ts = synthetic_rays(IMG_WH[0] * IMG_WH[1], n_frames=N_FRAMES, seed=1, img_wh=IMG_WH, frame=8)
+    return specs, enc, rays[:n_rays].contiguous(), ts[:n_rays].contiguous()
+
+
+def _cpu_render(specs, enc, rays, ts):
+    from oracle import nsff_oracle as O
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        O.render_rays(specs, enc, rays, ts, N_FRAMES - 1, **RENDER_KW)
+    return time.perf_counter() - t0
+
+
+def pick_cpu_threads(specs, enc, rays, ts):
+    """torch's intra-op pool does not scale to every core for 256-wide GEMMs on a few thousand rows; use the
+    thread count that is fastest on a 256-ray probe (reported as `cores`)."""
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        _cpu_render(specs, enc, rays[:64], ts[:64])
+        t = _cpu_render(specs, enc, rays[:256], ts[:256])
+        if t < best_t:
+            best, best_t = c, t
+    torch.set_num_threads(best)
+    return best
+
+
+def cpu_port_throughput(n_rays, reps):
+    """ray-samples/s of the oracle (CPU restatement of the reference path) on `n_rays` rays of the workload."""
+    specs, enc, rays, ts = _cpu_setup(n_rays)
+    cores = pick_cpu_threads(specs, enc, rays, ts)
+    times = [_cpu_render(specs, enc, rays, ts) for _ in range(reps)]
+    return n_rays * N_SAMPLES / min(times), times, cores
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    n_rays = CPU_SAMPLE_RAYS
+    specs, enc, rays, ts = _cpu_setup(n_rays)
+    cores = pick_cpu_threads(specs, enc, rays, ts)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t = _cpu_render(specs, enc, rays, ts)
+        if i >= args.warmup:
+            times.append(t)
+    total = sum(times)
+    value = n_rays * N_SAMPLES * args.steps / total
+    sample = f"{n_rays} rays x {N_SAMPLES} samples of the 512x288 frame per step (first rows of frame 8)"
+    line = {"impl": "reference", "metric": "ray-samples/sec (render_rays fwd)", "value": value, "unit": "ray-samples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "cpu_baseline": {"value": value, "unit": "ray-samples/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "ray-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "full NSFF static+dynamic+flow-warp +-1, 512x288 frame x 128 samples/ray, inference "
+                        "(BASELINE.json configs[1])",
+            "rays_per_frame": IMG_WH[0] * IMG_WH[1], "samples_per_ray": N_SAMPLES,
+            "frames_per_step": world if args.scaling == "weak" else 1,
+            "parallelism": f"ray-sharded x{world}, 1 all-gather of per-ray pixels",
+            "l2": "per-step outputs (~3.5 GB/GPU) exceed the 126 MB L2; no explicit flush needed"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from nsff_pl_b200 import _cabi, parallel
+    from nsff_pl_b200.models import nerf as nerf_mod
+    from nsff_pl_b200.models.rendering import render_rays
+    from parity_util import build_fields, synthetic_rays
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (the nsff_pl_b200 path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+
+    models, emb, _, _ = build_fields(W=256, seed=0, n_frames=N_FRAMES, device=dev, precision=args.precision)
+    R_frame = IMG_WH[0] * IMG_WH[1]
+    if args.scaling == "weak":
+        frame = 8 + rank
+        rays_h, ts_h = synthetic_rays(R_frame, n_frames=N_FRAMES, seed=1, img_wh=IMG_WH, frame=frame % N_FRAMES)
+        units_per_step = R_frame * N_SAMPLES * world
+    else:
+        rays_f, ts_f = synthetic_rays(R_frame, n_frames=N_FRAMES, seed=1, img_wh=IMG_WH, frame=8)
+        lo, hi = parallel.shard_bounds(R_frame, rank, world)
+        rays_h, ts_h = rays_f[lo:hi].contiguous(), ts_f[lo:hi].contiguous()
+        units_per_step = R_frame * N_SAMPLES
+    R = rays_h.shape[0]
+    rays_pin, ts_pin = rays_h.pin_memory(), ts_h.pin_memory()
+    rays_d, ts_d = rays_h.to(dev), ts_h.to(dev)
+    n_gather = R * world
+    pix_host = torch.empty(n_gather, 10, dtype=torch.float32).pin_memory()
+
+    field_events = []
+
+    def step(rays, ts):
+        with torch.no_grad():
+            res = render_rays(models, emb, rays, ts, N_FRAMES - 1, **RENDER_KW)
+            pix = parallel.pack_pixels(res)
+            if world > 1:
+                full = torch.empty(n_gather, pix.shape[1], device=dev)
+                dist.all_gather_into_tensor(full, pix)
+                pix = full
+        return pix
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(args.warmup):
+        step(rays_d, ts_d)
+    # ---- device-resident timing (value) ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    nerf_mod.FIELD_EVENTS = field_events
+    n0 = _cabi.launch_count()
+    ms = timed(lambda: step(rays_d, ts_d), args.steps)
+    launches = _cabi.launch_count() - n0
+    nerf_mod.FIELD_EVENTS = None
+    clocks = sampler.stop()
+    value = units_per_step * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end timing from pinned host buffers (e2e) ----
+    def e2e_step():
+        r = rays_pin.to(dev, non_blocking=True)
+        t = ts_pin.to(dev, non_blocking=True)
+        pix = step(r, t)
+        pix_host.copy_(pix, non_blocking=True)
+        torch.cuda.current_stream().synchronize()     # the caller needs the pixels on the host
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_value = units_per_step * args.steps / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        peaks = measured_peaks()
+        torch.cuda.synchronize()
+        kern_ms = [a.elapsed_time(b) for a, b, _ in field_events]
+        flops = [f for _, _, f in field_events]
+        per_launch_ms = sum(kern_ms) / max(1, len(kern_ms))
+        achieved = (sum(flops) / (sum(kern_ms) * 1e-3)) / 1e12 if kern_ms else None
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "field_forward_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = json.load(fh).get("dram_bytes_per_launch")
+        roofline = {"bound": "tensor", "kernel": "nsff::tc::field_forward_kernel", "achieved": achieved,
+                    "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": None if achieved is None else achieved / peaks["tflops"],
+                    "traffic": traffic, "peak_source": f"{peaks['source']} bf16_tflops_sustained",
+                    "launches_timed": len(kern_ms), "avg_launch_ms": per_launch_ms,
+                    "kernel_share_of_step": (sum(kern_ms) / ms) if kern_ms else None,
+                    "algorithmic_flop_per_launch": (sum(flops) / len(flops)) if flops else None}
+        cpu = None
+        if not args.no_cpu_baseline and world >= 1:
+            v, times, cores = cpu_port_throughput(CPU_SAMPLE_RAYS, reps=2)
+            cpu = {"value": v, "unit": "ray-samples/s", "cores": cores, "kind": "port",
+                   "sample": f"{CPU_SAMPLE_RAYS} rays x {N_SAMPLES} samples of the same frame, best of 2 "
+                             f"({', '.join(f'{t:.1f}s' for t in times)})"}
+        line = {"metric": "ray-samples/sec (render_rays fwd)", "value": value, "unit": "ray-samples/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic", "config": workload_config(args, world),
+                "e2e": {"value": e2e_value, "unit": "ray-samples/s", "h2d_bytes_per_step": int(rays_pin.numel() * 4 + ts_pin.numel() * 8),
+                        "d2h_bytes_per_step": int(pix_host.numel() * 4), "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "tflops_whole_step": units_per_step * FLOP_PER_POINT / (ms / args.steps * 1e-3) / 1e12 / world}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

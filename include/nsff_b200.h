@@ -1,0 +1,230 @@
+/* nsff_b200.h - C ABI of the Blackwell-native NSFF volume-rendering hot path.
+ *
+ * Drop-in boundary for kwea123/nsff_pl's render_rays() path.  The reference
+ * is pure Python/PyTorch, so "the reference's FFI for this path" is the precedent it sets with
+ * its only native op: models/softsplat.py:208-301 (a CUDA-only autograd.Function over raw
+ * kernels, contiguous fp32 tensors, NotImplementedError on CPU tensors) and
+ * third_party/flow/alt_cuda_corr/correlation.cpp:18-54 (CHECK_CUDA / CHECK_CONTIGUOUS, raw
+ * pointers handed to launchers).  Each entry point below names the reference lines it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous row-major data unless marked "host";
+ *   - floats are fp32, time indices are int64 (torch.long), exactly what the reference passes;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing syncs;
+ *   - no allocation happens inside the library: callers own every buffer;
+ *   - return value: 0 on success, a negative NSFF_E* code otherwise (nsff_error_string()).
+ *   - no global state; the only long-lived object is the caller-owned "field pack" buffer.
+ *
+ * Shapes: R rays, S samples per ray, B = R*S points, points ordered (ray, sample).
+ */
+#ifndef NSFF_B200_H_
+#define NSFF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSFF_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define NSFF_API __attribute__((visibility("default")))
+#else
+#define NSFF_API
+#endif
+
+enum {
+  NSFF_OK = 0,
+  NSFF_EINVAL = -1,      /* bad shape / null pointer / misaligned buffer           */
+  NSFF_EUNSUPPORTED = -2,/* configuration this build has no kernel for             */
+  NSFF_ECUDA = -3,       /* a CUDA runtime call failed (see nsff_last_cuda_error)  */
+  NSFF_EARCH = -4        /* device is not sm_100 (tcgen05 path requested)          */
+};
+
+NSFF_API int nsff_abi_version(void);
+NSFF_API const char* nsff_error_string(int code);
+/* cudaGetErrorString of the last failing runtime call made by this library on this thread. */
+NSFF_API const char* nsff_last_cuda_error(void);
+/* Select the device subsequent launches target (the library carries its own CUDA runtime). */
+NSFF_API int nsff_set_device(int device);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches counter). */
+NSFF_API uint64_t nsff_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * a1  PosEmbedding.forward                                            models/nerf.py:17-30
+ *     out[n] = [x, sin(2^0 x), cos(2^0 x), ..., sin(2^(F-1) x), cos(2^(F-1) x)]   (n, 3+6F)
+ *     freqs: F device floats (the module's .freqs, so logscale=False also works).
+ */
+NSFF_API int nsff_pos_embedding(const float* x, int64_t n, const float* freqs, int n_freqs,
+                       float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a6  stratified depths + sample points                      models/rendering.py:314-324,332,359
+ *     zs = linspace(0,1,S) (optionally jittered: lower+(upper-lower)*perturb*u, u = `rand` (R,S));
+ *     xyz = o + d*z.  `rand` may be NULL iff perturb == 0.
+ */
+NSFF_API int nsff_sample_points(const float* rays /*(R,6)*/, int64_t R, int S, float perturb,
+                       const float* rand /*(R,S) or NULL*/, float* zs /*(R,S)*/,
+                       float* xyz /*(R,S,3)*/, void* stream);
+/*     xyz = o + d*z for caller-provided depths (the fine pass of the hierarchical mode, :359). */
+NSFF_API int nsff_points_from_depths(const float* rays, const float* zs, int64_t R, int S,
+                            float* xyz, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a3/a4/a5  NeRF.forward - static and dynamic 8x256 MLPs               models/nerf.py:118-213
+ *
+ * A "field pack" is the caller-owned device image of one NeRF module's parameters, laid out for
+ * the tcgen05 kernel (bf16, 128B-swizzled K-major tiles, one block per 64-wide K chunk) plus an
+ * fp32 bias table.  nsff_field_pack_bytes() sizes it, nsff_field_pack() fills it from the fp32
+ * nn.Parameters (state_dict names listed in SURVEY.md §8b); repack after every optimizer step.
+ */
+typedef struct {
+  int32_t W;               /* hidden width; the tcgen05 path requires 256                  */
+  int32_t D;               /* trunk depth; 8                                               */
+  int32_t skip;            /* index of the layer that re-reads the input; 4               */
+  int32_t in_xyz;          /* 63                                                           */
+  int32_t in_dir;          /* 27 (0 when use_viewdir is false)                             */
+  int32_t in_a;            /* 0 or 48                                                      */
+  int32_t in_t;            /* 0 or 48 (0 when the module has no transient branch)          */
+  int32_t use_viewdir;
+  int32_t has_transient;
+  int32_t has_flow;        /* fine model with output_flow                                  */
+  float   flow_scale;      /* 0.2                                                          */
+} nsff_field_desc;
+
+/* fp32 parameter pointers, reference names.  weight (out,in) row-major, bias (out).
+ * Unused entries (e.g. transient_* of a static-only module) are NULL. */
+typedef struct {
+  const float* static_w[8];   const float* static_b[8];    /* static_xyz_encoding_{1..8}.0        */
+  const float* static_final_w; const float* static_final_b;/* static_xyz_encoding_final           */
+  const float* static_dir_w;  const float* static_dir_b;   /* static_dir_encoding.0               */
+  const float* static_sigma_w; const float* static_sigma_b;/* static_sigma                        */
+  const float* static_rgb_w;  const float* static_rgb_b;   /* static_rgb.0                        */
+  const float* trans_w[8];    const float* trans_b[8];     /* transient_xyz_encoding_{1..8}.0     */
+  const float* trans_final_w; const float* trans_final_b;  /* transient_xyz_encoding_final        */
+  const float* trans_sigma_w; const float* trans_sigma_b;  /* transient_sigma                     */
+  const float* trans_rgb_w;   const float* trans_rgb_b;    /* transient_rgb.0                     */
+  const float* trans_fw_w;    const float* trans_fw_b;     /* transient_flow_fw.0                 */
+  const float* trans_bw_w;    const float* trans_bw_b;     /* transient_flow_bw.0                 */
+} nsff_field_params;
+
+NSFF_API int nsff_field_pack_bytes(const nsff_field_desc* desc /*host*/, size_t* bytes /*host*/);
+NSFF_API int nsff_field_pack(const nsff_field_desc* desc /*host*/, const nsff_field_params* params /*host*/,
+                    void* pack /*device, 128B aligned*/, size_t pack_bytes, void* stream);
+
+/* What one forward evaluates; mirrors the four call modes of nerf.py:129-141. */
+enum {
+  NSFF_OUT_STATIC      = 1,   /* static rgb(3) + raw sigma(1)                               */
+  NSFF_OUT_TRANSIENT   = 2,   /* transient rgb(3) + raw sigma(1)                            */
+  NSFF_OUT_FLOW_FW     = 4,   /* + flow_scale*tanh fw(3)                                    */
+  NSFF_OUT_FLOW_BW     = 8,   /* + flow_scale*tanh bw(3)                                    */
+  NSFF_OUT_SIGMA_ONLY  = 16   /* coarse@test: raw sigmas only (static [, transient])        */
+};
+
+/* Per-point inputs for the fused renderer entry (PE computed in-kernel; rendering.py:164-175,
+ * 113-120).  Point p belongs to ray p / S. */
+typedef struct {
+  const float*   xyz;        /* (B,3) sample points                                         */
+  const float*   offset;     /* (B,*) optional: points are xyz + offset[.., 0:3]; NULL = none */
+  int32_t        offset_ld;  /* row stride (floats) of `offset`                             */
+  float*         xyz_out;    /* (B,3) optional: where xyz+offset is written (xyzs_fw/bw)    */
+  const float*   dirs;       /* (R,3) view directions (rays_d or kwargs['view_dir'])        */
+  const float*   t_table;    /* (N_frames or R, in_t) time codes; NULL if no transient      */
+  const int64_t* t_index;    /* (R,) frame index per ray; NULL => row r of t_table is ray r */
+  int32_t        t_shift;    /* -1/0/+1: index = clamp(t_index + shift, 0, max_t)           */
+  int32_t        max_t;
+  const float*   a_table;    /* appearance codes, same addressing (a_index, no shift)       */
+  const int64_t* a_index;
+  const float*   zs;         /* (B,) depths; flow heads are zeroed where z > 0.95 (:126,187) */
+  int64_t        B;
+  int32_t        S;
+} nsff_points;
+
+/* Fused PE + MLP forward on tensor cores (tcgen05/TMEM, bf16 operands, fp32 accumulate).
+ * out: (B, C) fp32, C = 4*[static] + 4*[transient] + 3*[fw] + 3*[bw]  (or 1..2 in SIGMA_ONLY),
+ * column order as nerf.py:129-141. */
+NSFF_API int nsff_field_forward(const nsff_field_desc* desc /*host*/, const void* pack,
+                       const nsff_points* pts /*host*/, int out_mask, float* out, int32_t out_ld,
+                       void* stream);
+
+/* NeRF.forward drop-in on an already-embedded input x (B, in_xyz+in_dir+in_a+in_t) fp32
+ * (column split of nerf.py:142-160).  Same kernel, the prologue converts x instead of encoding. */
+NSFF_API int nsff_field_forward_embedded(const nsff_field_desc* desc /*host*/, const void* pack,
+                                const float* x, int32_t x_ld, int64_t B, int out_mask,
+                                float* out, int32_t out_ld, void* stream);
+
+/* fp32 verification path: the same math on CUDA cores straight from the fp32 parameters
+ * (no pack, no tensor cores); `scratch` must hold nsff_field_fp32_scratch_floats(...) floats. */
+NSFF_API size_t nsff_field_fp32_scratch_floats(const nsff_field_desc* desc /*host*/, int64_t B);
+NSFF_API int nsff_field_forward_fp32(const nsff_field_desc* desc /*host*/, const nsff_field_params* params /*host*/,
+                            const nsff_points* pts /*host, or NULL*/,
+                            const float* x_embedded /*(B_embedded, x_ld) or NULL*/, int32_t x_ld,
+                            int64_t B_embedded, int out_mask, float* out, int32_t out_ld, float* scratch,
+                            void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a8  eval-only camera visibility                rendering.py:190-200, ray_utils.py:127-181
+ *     vis[p] = number of cameras whose image contains the world-space projection of NDC point p.
+ *     w2c: (n_cams, 12) row-major 3x4 world-to-camera matrices (inverse of the c2w poses).
+ */
+NSFF_API int nsff_visibility(const float* xyz /*(B,3)*/, int64_t B, const float* K /*host: fx,fy,cx,cy*/,
+                    const float* w2c /*device (n_cams,12)*/, int n_cams, int H, int W,
+                    float* vis /*(B,)*/, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a9-a12  density->alpha, joint static+dynamic composite, warped composites, disocclusion
+ *         models/rendering.py:202-298 and 98-140.  NULL output pointers are skipped.
+ */
+typedef struct {
+  int64_t R; int32_t S;
+  /* inputs */
+  const float* zs;          /* (R,S)                                                       */
+  const float* xyz;         /* (R,S,3)  (needed only for xyz_fine)                          */
+  const float* raw;         /* (R,S,raw_ld) output of nsff_field_forward                    */
+  int32_t raw_ld;
+  int32_t has_static_rgb;   /* 0 in SIGMA_ONLY mode: raw = [sigma_s(, sigma_t)]             */
+  int32_t has_transient;
+  int32_t has_flow;         /* raw holds fw,bw flows at columns 8..13                       */
+  const float* noise_static;/* (R,S) N(0,1) draws or NULL; multiplied by noise_std          */
+  const float* noise_trans;
+  float noise_std;
+  const float* vis;         /* (R,S) camera-visibility counts or NULL (sigma_t := -10 at 0) */
+  /* warped passes (training only): raw_* = (R,S,7) [rgb, sigma, flow-back] at xyz+flow     */
+  const float* raw_fw; const float* raw_bw; int32_t raw_w_ld;
+  const float* xyz_fw; const float* xyz_bw;      /* (R,S,3) warped points                   */
+  const float* noise_fw; const float* noise_bw;  /* (R,S) or NULL                           */
+  /* per-sample outputs (R,S[,3]) */
+  float* static_sigmas; float* transient_sigmas;
+  float* static_weights; float* transient_weights; float* weights;
+  float* static_alphas; float* transient_alphas;
+  float* xyzs_fw_bw; float* xyzs_bw_fw;          /* (R,S,3)                                 */
+  float* disoccs_fw; float* disoccs_bw;          /* (R,S)                                   */
+  /* per-ray outputs */
+  float* depth; float* rgb; float* transient_alpha; float* transient_rgb;
+  float* static_only_rgb; float* static_only_depth;
+  float* xyz_fine; float* flow_fw; float* xyz_fw_ray; float* flow_bw; float* xyz_bw_ray;
+  float* rgb_fw; float* rgb_bw; float* disocc_fw; float* disocc_bw;
+} nsff_composite_args;
+
+NSFF_API int nsff_composite(const nsff_composite_args* args /*host*/, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a13  sample_pdf + merge                                   models/rendering.py:10-49, 335-348
+ *     sample_pdf(bins, weights, N_importance, det, eps): bins (R, n_weights+1), weights
+ *     (R, n_weights), each with its own row stride in floats (0 = one row shared by all rays, which
+ *     is how render_rays passes the un-jittered mid-points, :315,:336); u: (R,N) uniforms, or NULL
+ *     for det=True (u = linspace(0,1,N)).  out: (R,N) new depths.
+ */
+NSFF_API int nsff_sample_pdf(const float* bins, int64_t bins_row_stride, const float* weights,
+                    int64_t weights_row_stride, int64_t R, int n_weights, int n_importance,
+                    const float* u, float eps, float* out, void* stream);
+/*     out (R, total) = sort(cat(parts...)) along the last axis; up to 3 parts (:348).        */
+NSFF_API int nsff_merge_sorted(const float* a, int na, const float* b, int nb, const float* c, int nc,
+                      int64_t R, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSFF_B200_H_ */

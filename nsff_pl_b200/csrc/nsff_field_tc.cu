@@ -1,0 +1,744 @@
+// a3/a4/a5/a7/a10: fused positional-encoding + NeRF MLP forward on the 5th-gen tensor cores.
+//
+//   reference: models/nerf.py:118-213 (NeRF.forward, all call modes) fed by
+//              models/rendering.py:113-120,152-175 (PE(xyz) | PE(dir) | a | t input rows)
+//
+// One persistent CTA per SM walks 128-point tiles.  For each tile the whole layer program of the
+// requested heads (static trunk -> sigma head -> final -> dir layer -> rgb head, then the dynamic
+// trunk -> final -> rgb/sigma/flow heads) runs without the activations ever leaving the SM:
+//
+//   smem  A operand : 4 "hidden" chunks (128 rows x 64 bf16, 128B-swizzled, K-major) + 3 "extra"
+//                     chunks written once per tile by the prologue: PE(xyz) (63 -> 64 cols),
+//                     time code (48), PE(dir) (27 -> 32)
+//   smem  B operand : 3-stage ring of weight blocks (N x 64 bf16, same swizzle) streamed from the
+//                     L2-resident field pack with cp.async.bulk + mbarrier complete_tx
+//   TMEM            : two 128x256 fp32 accumulators, alternating per layer
+//   warps 0-7       : prologue (encoding) + epilogue (tcgen05.ld -> bias/act -> bf16 -> swizzled st.shared)
+//   warp  8         : weight producer (one thread)
+//   warp  9         : TMEM owner + tcgen05.mma issuer (one thread)
+//
+// Layer l+1's MMAs for K-chunk c start as soon as the epilogue of layer l has written hidden chunk c
+// (one mbarrier per chunk), so the tensor pipe only idles for the first 64-column slice of each
+// epilogue; the other accumulator absorbs layer l+1 while layer l is still being drained.
+#include <cuda_bf16.h>
+#include <string.h>
+
+#include <initializer_list>
+
+#include "nsff_common.cuh"
+#include "nsff_sm100.cuh"
+
+namespace nsff {
+namespace tc {
+
+using namespace sm100;
+
+// ---------------------------------------------------------------------------------------------
+// pack layout (shared by nsff_field_pack_bytes / nsff_field_pack / the forward launcher)
+// ---------------------------------------------------------------------------------------------
+enum ChunkId : uint8_t { CH_H0 = 0, CH_H1, CH_H2, CH_H3, CH_PE, CH_T, CH_DIR, CH_NONE = 255 };
+enum LayerId {
+  L_S1 = 0, L_S2, L_S3, L_S4, L_S5, L_S6, L_S7, L_S8, L_SSIG, L_SFIN, L_SDIR, L_SRGB,
+  L_T1, L_T2, L_T3, L_T4, L_T5, L_T6, L_T7, L_T8, L_TFIN, L_THEAD, L_COUNT
+};
+enum Epi : uint8_t { EPI_RELU_HID = 0, EPI_LIN_HID = 1, EPI_HEAD = 2 };
+enum HeadAct : uint8_t { HA_NONE = 0, HA_SIGMOID = 1, HA_FLOW = 2 };
+
+constexpr int kMaxChunks = 6;
+
+struct PackLayer {
+  bool present;
+  uint32_t w_off;      // byte offset of the first weight block
+  uint32_t bias_off;   // float index into the bias table
+  int n;               // 256 or 16
+  int nchunks;
+  uint8_t chunk[kMaxChunks];
+  uint8_t kcnt[kMaxChunks];   // number of K=16 MMAs issued from this chunk
+};
+
+struct PackLayout {
+  PackLayer layer[L_COUNT];
+  uint32_t bias_base;   // byte offset of the fp32 bias table
+  uint32_t n_bias;      // floats
+  size_t bytes;
+};
+
+static int build_layout(const nsff_field_desc& d, PackLayout& L) {
+  if (d.W != 256 || d.D != 8 || d.skip != 4 || d.in_xyz != 63) return NSFF_EUNSUPPORTED;
+  if (d.use_viewdir && d.in_dir != 27) return NSFF_EUNSUPPORTED;
+  if (d.in_a != 0) return NSFF_EUNSUPPORTED;   // appearance code: fp32 path only (for now)
+  if (d.has_transient && d.in_t != 48) return NSFF_EUNSUPPORTED;
+  memset(&L, 0, sizeof(L));
+  uint32_t off = 0, boff = 0;
+  auto add = [&](int id, int n, std::initializer_list<uint8_t> chunks) {
+    PackLayer& p = L.layer[id];
+    p.present = true;
+    p.n = n;
+    p.nchunks = 0;
+    for (uint8_t c : chunks) {
+      p.chunk[p.nchunks] = c;
+      p.kcnt[p.nchunks] = (c == CH_T) ? 3 : (c == CH_DIR) ? 2 : 4;
+      ++p.nchunks;
+    }
+    p.w_off = off;
+    p.bias_off = boff;
+    off += (uint32_t)p.nchunks * (uint32_t)n * 128u;
+    boff += (uint32_t)n;
+  };
+  // extras first so the tensor pipe has work while the previous epilogue is still producing hidden chunk 0
+  add(L_S1, 256, {CH_PE});
+  for (int i = L_S2; i <= L_S8; ++i) {
+    if (i == L_S5) add(i, 256, {CH_PE, CH_H0, CH_H1, CH_H2, CH_H3});
+    else add(i, 256, {CH_H0, CH_H1, CH_H2, CH_H3});
+  }
+  add(L_SSIG, 16, {CH_H0, CH_H1, CH_H2, CH_H3});
+  add(L_SFIN, 256, {CH_H0, CH_H1, CH_H2, CH_H3});
+  if (d.use_viewdir) add(L_SDIR, 256, {CH_DIR, CH_H0, CH_H1, CH_H2, CH_H3});
+  add(L_SRGB, 16, {CH_H0, CH_H1, CH_H2, CH_H3});
+  if (d.has_transient) {
+    add(L_T1, 256, {CH_PE, CH_T});
+    for (int i = L_T2; i <= L_T8; ++i) {
+      if (i == L_T5) add(i, 256, {CH_PE, CH_T, CH_H0, CH_H1, CH_H2, CH_H3});
+      else add(i, 256, {CH_H0, CH_H1, CH_H2, CH_H3});
+    }
+    add(L_TFIN, 256, {CH_H0, CH_H1, CH_H2, CH_H3});
+    add(L_THEAD, 16, {CH_H0, CH_H1, CH_H2, CH_H3});
+  }
+  L.bias_base = off;
+  L.n_bias = boff;
+  L.bytes = (size_t)off + (size_t)boff * 4;
+  return NSFF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pack kernel: fp32 (out,in) nn.Linear weights -> bf16 blocks [n rows x 64 cols], 128B-swizzled
+// ---------------------------------------------------------------------------------------------
+struct PackJob {
+  const float* src;   // weight (rows, ld) row-major, or bias (n) when is_bias
+  uint32_t dst_off;   // byte offset in the pack (weights) / float index (bias)
+  int32_t ld;         // source row stride
+  int32_t row0;       // first destination row inside the block
+  int32_t rows;       // rows to write
+  int32_t col0;       // first source column
+  int32_t cols;       // valid source columns (the rest of the 64 are zero)
+  int32_t is_bias;
+};
+constexpr int kMaxPackJobs = 160;
+struct PackJobs {
+  PackJob job[kMaxPackJobs];
+};
+
+__device__ __forceinline__ uint32_t swz_off(int row, int col /*bf16 column 0..63*/) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((col >> 3) ^ (row & 7)) & 7) << 4) + (col & 7) * 2);
+}
+
+__global__ void pack_kernel(const PackJobs* __restrict__ jobs_dev, uint8_t* __restrict__ pack, uint32_t bias_base) {
+  const PackJob j = jobs_dev->job[blockIdx.x];
+  if (j.is_bias) {
+    float* b = reinterpret_cast<float*>(pack + bias_base) + j.dst_off;
+    for (int i = threadIdx.x; i < j.rows; i += blockDim.x) b[i] = j.src ? j.src[i] : 0.f;
+    return;
+  }
+  for (int e = threadIdx.x; e < j.rows * 64; e += blockDim.x) {
+    int r = e >> 6, c = e & 63;
+    float v = (c < j.cols) ? j.src[(int64_t)r * j.ld + j.col0 + c] : 0.f;
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    *reinterpret_cast<__nv_bfloat16*>(pack + j.dst_off + swz_off(j.row0 + r, c)) = h;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward kernel
+// ---------------------------------------------------------------------------------------------
+constexpr int kTileM = 128;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = (kEpiWarps + 2) * 32;
+constexpr int kStages = 3;
+constexpr uint32_t kChunkBytes = 128 * 128;          // 128 rows x 64 bf16
+constexpr uint32_t kStageBytes = 256 * 128;          // 256 rows x 64 bf16
+constexpr uint32_t kSmemA = 7 * kChunkBytes;         // 4 hidden + PE + T + DIR
+constexpr uint32_t kSmemB = kStages * kStageBytes;
+constexpr uint32_t kSmemBar = 256;
+constexpr uint32_t kSmemTotal = kSmemA + kSmemB + kSmemBar + 1024;   // + alignment slack
+constexpr int kMaxSteps = 24;
+
+struct Step {
+  uint32_t w_off;
+  uint32_t bias_off;
+  uint16_t n;
+  uint8_t nchunks;
+  uint8_t epi;
+  uint8_t chunk[kMaxChunks];
+  uint8_t kcnt[kMaxChunks];
+  int8_t head_dst[16];
+  uint8_t head_act[16];
+};
+
+struct FwdParams {
+  const uint8_t* pack;
+  const float* bias;
+  nsff_points pts;          // raw-point mode
+  const float* x_emb;       // embedded mode (NeRF.forward drop-in); NULL in raw-point mode
+  int32_t x_ld, c_dir, c_t; // embedded-row column offsets
+  float* out;
+  int32_t out_ld;
+  int32_t n_steps;
+  int32_t n_tiles;
+  int32_t need_t, need_dir;
+  float flow_scale;
+  Step steps[kMaxSteps];
+};
+
+// barrier slots (8 bytes each) inside the barrier region
+enum {
+  BAR_W_FULL = 0,                       // [kStages]
+  BAR_W_EMPTY = BAR_W_FULL + kStages,   // [kStages]
+  BAR_HID_FULL = BAR_W_EMPTY + kStages, // [4]
+  BAR_EXTRA_FULL = BAR_HID_FULL + 4,    // [1]
+  BAR_ACC_FULL = BAR_EXTRA_FULL + 1,    // [2]
+  BAR_ACC_EMPTY = BAR_ACC_FULL + 2,     // [2]
+  BAR_COUNT = BAR_ACC_EMPTY + 2
+};
+static_assert(BAR_COUNT * 8 + 8 <= kSmemBar, "barrier region too small");
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// Writes 8 consecutive bf16 columns [8*unit, 8*unit+8) of `row` into a swizzled 64-column chunk.
+__device__ __forceinline__ void store_unit(uint32_t chunk_base, int row, int unit, const float (&f)[8]) {
+  uint32_t addr = chunk_base + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (((unit ^ (row & 7)) & 7) << 4));
+  st_shared_v4(addr, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+               pack_bf16x2(f[6], f[7]));
+}
+
+// column c (0..63) of the xyz encoding row [x, sin(2^0 x), cos(2^0 x), ...] (nerf.py:17-30); col 63 = pad
+template <int kNFreq>
+__device__ __forceinline__ float pe_col(int c, const float (&base)[3], const float (&sn)[kNFreq][3],
+                                        const float (&cs)[kNFreq][3], int f0) {
+  if (c < 3) return base[c];
+  int k = c - 3, f = k / 6, r = k % 6;
+  if (f - f0 < 0 || f - f0 >= kNFreq) return 0.f;
+  return r < 3 ? sn[f - f0][r] : cs[f - f0][r - 3];
+}
+
+__global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid_constant__ FwdParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base;                       // 7 chunks
+  const uint32_t sB = smem_base + kSmemA;              // ring
+  const uint32_t sBar = sB + kSmemB;
+  const uint32_t sTmemPtr = sBar + BAR_COUNT * 8;
+  auto bar = [&](int i) { return sBar + (uint32_t)i * 8u; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(bar(BAR_W_FULL + i), 1);
+      mbar_init(bar(BAR_W_EMPTY + i), 1);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_HID_FULL + i), kEpiWarps);
+    mbar_init(bar(BAR_EXTRA_FULL), kEpiWarps);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(BAR_ACC_FULL + i), 1);
+      mbar_init(bar(BAR_ACC_EMPTY + i), kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kEpiWarps + 1) tmem_alloc(sTmemPtr, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sTmemPtr));
+
+  const int n_steps = P.n_steps;
+
+  if (warp == kEpiWarps) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        for (int s = 0; s < n_steps; ++s) {
+          const Step& st = P.steps[s];
+          const uint32_t bytes = (uint32_t)st.n * 128u;
+          for (int kc = 0; kc < st.nchunks; ++kc, ++it) {
+            const uint32_t stage = it % kStages, use = it / kStages;
+            mbar_wait(bar(BAR_W_EMPTY + stage), (use & 1u) ^ 1u);
+            mbar_arrive_expect_tx(bar(BAR_W_FULL + stage), bytes);
+            bulk_g2s(sB + stage * kStageBytes, P.pack + st.w_off + (uint32_t)kc * bytes, bytes,
+                     bar(BAR_W_FULL + stage));
+          }
+        }
+      }
+    }
+  } else if (warp == kEpiWarps + 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t it = 0, gstep = 0, hid_gen = 0, tile_iter = 0;
+      for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tile_iter) {
+        mbar_wait(bar(BAR_EXTRA_FULL), tile_iter & 1u);
+        for (int s = 0; s < n_steps; ++s, ++gstep) {
+          const Step& st = P.steps[s];
+          const uint32_t slot = gstep & 1u, use = gstep >> 1;
+          mbar_wait(bar(BAR_ACC_EMPTY + slot), (use & 1u) ^ 1u);
+          const uint32_t d_tmem = tmem_base + slot * 256u;
+          const uint32_t idesc = make_idesc_bf16(kTileM, st.n);
+          uint32_t accumulate = 0;
+          for (int kc = 0; kc < st.nchunks; ++kc, ++it) {
+            const uint32_t ch = st.chunk[kc];
+            if (ch < 4) mbar_wait(bar(BAR_HID_FULL + ch), (hid_gen - 1u) & 1u);
+            const uint32_t stage = it % kStages, wuse = it / kStages;
+            mbar_wait(bar(BAR_W_FULL + stage), wuse & 1u);
+            tc_fence_after_sync();
+            const uint64_t a0 = make_desc_k128(sA + ch * kChunkBytes);
+            const uint64_t b0 = make_desc_k128(sB + stage * kStageBytes);
+            const int kcnt = st.kcnt[kc];
+            for (int k = 0; k < kcnt; ++k) {
+              // +32 B per K=16 step inside the 128 B swizzle row (descriptor address unit = 16 B)
+              mma_bf16_ss(d_tmem, a0 + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), idesc, accumulate);
+              accumulate = 1;
+            }
+            mma_commit(bar(BAR_W_EMPTY + stage));
+          }
+          mma_commit(bar(BAR_ACC_FULL + slot));
+          if (st.epi != EPI_HEAD) ++hid_gen;
+        }
+      }
+    }
+  } else {
+    // ===================== prologue + epilogue warps =====================
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_field = (uint32_t)(q * 32) << 16;
+    uint32_t gstep = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+      const int64_t p_raw = (int64_t)tile * kTileM + row;
+      const bool valid = p_raw < P.pts.B;
+      const int64_t p = valid ? p_raw : P.pts.B - 1;
+      // ---------------- prologue: encode this tile's inputs into the extra chunks ----------------
+      // (all MMAs of the previous tile have completed: its last acc_full was waited on below)
+      const uint32_t chPE = sA + CH_PE * kChunkBytes, chT = sA + CH_T * kChunkBytes, chD = sA + CH_DIR * kChunkBytes;
+      if (P.x_emb == nullptr) {
+        const int64_t ray = p / P.pts.S;
+        float base[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float v = P.pts.xyz[p * 3 + c];
+          if (P.pts.offset) v = __fadd_rn(v, P.pts.offset[p * P.pts.offset_ld + c]);
+          base[c] = v;
+        }
+        if (half == 0 && valid && P.pts.xyz_out) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) P.pts.xyz_out[p * 3 + c] = base[c];
+        }
+        // PE(xyz): half 0 -> columns 0..31 (freqs 0..4), half 1 -> columns 32..63 (freqs 4..9)
+        if (half == 0) {
+          float sn[5][3], cs[5][3];
+#pragma unroll
+          for (int f = 0; f < 5; ++f)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) sincosf(__fmul_rn((float)(1 << f), base[c]), &sn[f][c], &cs[f][c]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = pe_col<5>(u * 8 + i, base, sn, cs, 0);
+            store_unit(chPE, row, u, v);
+          }
+        } else {
+          float sn[6][3], cs[6][3];
+#pragma unroll
+          for (int f = 0; f < 6; ++f)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) sincosf(__fmul_rn((float)(16 << f), base[c]), &sn[f][c], &cs[f][c]);
+#pragma unroll
+          for (int u = 4; u < 8; ++u) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = (u * 8 + i == 63) ? 0.f : pe_col<6>(u * 8 + i, base, sn, cs, 4);
+            store_unit(chPE, row, u, v);
+          }
+        }
+        if (P.need_t) {
+          int64_t trow = ray;
+          if (P.pts.t_index) {
+            trow = P.pts.t_index[ray] + P.pts.t_shift;
+            trow = trow < 0 ? 0 : (trow > P.pts.max_t ? P.pts.max_t : trow);
+          }
+          const float4* tp = reinterpret_cast<const float4*>(P.pts.t_table + trow * 48) + half * 6;
+#pragma unroll
+          for (int u = 0; u < 3; ++u) {
+            float4 a = __ldg(tp + 2 * u), b = __ldg(tp + 2 * u + 1);
+            float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            store_unit(chT, row, half * 3 + u, v);
+          }
+        }
+        if (P.need_dir && half == 1) {
+          float d[3] = {P.pts.dirs[ray * 3 + 0], P.pts.dirs[ray * 3 + 1], P.pts.dirs[ray * 3 + 2]};
+          float sn[4][3], cs[4][3];
+#pragma unroll
+          for (int f = 0; f < 4; ++f)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) sincosf(__fmul_rn((float)(1 << f), d[c]), &sn[f][c], &cs[f][c]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = (u * 8 + i >= 27) ? 0.f : pe_col<4>(u * 8 + i, d, sn, cs, 0);
+            store_unit(chD, row, u, v);
+          }
+        }
+      } else {
+        // embedded mode: x row = [xyz63 | dir27 | a | t48] already encoded by the caller
+        const float* xr = P.x_emb + p * P.x_ld;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            int c = (half * 4 + u) * 8 + i;
+            v[i] = c < 63 ? xr[c] : 0.f;
+          }
+          store_unit(chPE, row, half * 4 + u, v);
+        }
+        if (P.need_t) {
+#pragma unroll
+          for (int u = 0; u < 3; ++u) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = xr[P.c_t + (half * 3 + u) * 8 + i];
+            store_unit(chT, row, half * 3 + u, v);
+          }
+        }
+        if (P.need_dir && half == 1) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = (u * 8 + i >= 27) ? 0.f : xr[P.c_dir + u * 8 + i];
+            store_unit(chD, row, u, v);
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(BAR_EXTRA_FULL));
+
+      float zrow = 0.f;
+      if (P.pts.zs && P.x_emb == nullptr) zrow = P.pts.zs[p];
+
+      // ---------------- epilogues, one per step ----------------
+      for (int s = 0; s < n_steps; ++s, ++gstep) {
+        const Step& st = P.steps[s];
+        const uint32_t slot = gstep & 1u, use = gstep >> 1;
+        mbar_wait(bar(BAR_ACC_FULL + slot), use & 1u);
+        tc_fence_after_sync();
+        const uint32_t t_acc = tmem_base + lane_field + slot * 256u;
+        if (st.epi != EPI_HEAD) {
+          const bool relu = st.epi == EPI_RELU_HID;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld32(t_acc + (uint32_t)(c * 64 + half * 32), v);
+            const float4* bp = reinterpret_cast<const float4*>(P.bias + st.bias_off + c * 64 + half * 32);
+            float4 b[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) b[i] = __ldg(bp + i);
+            tmem_ld_wait();
+            if (c == 3) {
+              // accumulator fully drained into registers: hand the TMEM slot back to the MMA warp
+              tc_fence_before_sync();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar(BAR_ACC_EMPTY + slot));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 bb = b[u * 2 + (i >> 2)];
+                const float bv = (i & 3) == 0 ? bb.x : (i & 3) == 1 ? bb.y : (i & 3) == 2 ? bb.z : bb.w;
+                float x = __uint_as_float(v[u * 8 + i]) + bv;
+                f[i] = relu ? fmaxf(x, 0.f) : x;
+              }
+              store_unit(sA + (uint32_t)c * kChunkBytes, row, half * 4 + u, f);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(BAR_HID_FULL + c));
+          }
+        } else {
+          if (half == 0) {
+            uint32_t v[16];
+            tmem_ld16(t_acc, v);
+            tmem_ld_wait();
+            if (valid) {
+              float* orow = P.out + p * P.out_ld;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int dst = st.head_dst[i];
+                if (dst < 0) continue;
+                float x = __uint_as_float(v[i]) + __ldg(P.bias + st.bias_off + i);
+                const int act = st.head_act[i];
+                if (act == HA_SIGMOID) x = sigmoid_f(x);
+                else if (act == HA_FLOW) x = (zrow > kZFar) ? 0.f : P.flow_scale * tanhf(x);
+                orow[dst] = x;
+              }
+            }
+          }
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(BAR_ACC_EMPTY + slot));
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kEpiWarps + 1) {
+    tc_fence_after_sync();
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace tc
+}  // namespace nsff
+
+using namespace nsff;
+using namespace nsff::tc;
+
+extern "C" int nsff_field_pack_bytes(const nsff_field_desc* desc, size_t* bytes) {
+  if (!desc || !bytes) return NSFF_EINVAL;
+  PackLayout L;
+  int rc = build_layout(*desc, L);
+  if (rc != NSFF_OK) return rc;
+  // the job table of nsff_field_pack() is staged right after the image
+  *bytes = ((L.bytes + 1023) & ~(size_t)1023) + sizeof(PackJobs);
+  return NSFF_OK;
+}
+
+extern "C" int nsff_field_pack(const nsff_field_desc* desc, const nsff_field_params* prm, void* pack,
+                               size_t pack_bytes, void* stream) {
+  if (!desc || !prm || !pack) return NSFF_EINVAL;
+  if (((uintptr_t)pack & 127u) != 0) return NSFF_EINVAL;   // bulk copies need 16 B; keep lines whole
+  PackLayout L;
+  int rc = build_layout(*desc, L);
+  if (rc != NSFF_OK) return rc;
+  const size_t jobs_off = (L.bytes + 1023) & ~(size_t)1023;
+  if (pack_bytes < jobs_off + sizeof(PackJobs)) return NSFF_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  static thread_local PackJobs jobs;   // host staging; copied synchronously w.r.t. the host below
+  int nj = 0;
+  bool missing = false;
+  auto wjob = [&](int lid, int kc, const float* w, int ld, int row0, int rows, int col0, int cols) {
+    const PackLayer& pl = L.layer[lid];
+    if (!w) { missing = true; return; }
+    PackJob& j = jobs.job[nj++];
+    j.src = w; j.ld = ld; j.row0 = row0; j.rows = rows; j.col0 = col0; j.cols = cols; j.is_bias = 0;
+    j.dst_off = pl.w_off + (uint32_t)kc * (uint32_t)pl.n * 128u;
+  };
+  auto bjob = [&](int lid, int idx0, const float* b, int n) {
+    if (!b) { missing = true; return; }
+    PackJob& j = jobs.job[nj++];
+    j.src = b; j.rows = n; j.is_bias = 1; j.dst_off = L.layer[lid].bias_off + idx0;
+    j.ld = j.row0 = j.col0 = j.cols = 0;
+  };
+  // a 256-wide layer whose K runs over [pre-columns..., hidden 256]; `pre` = {(chunk-slot, col0, cols)}
+  auto trunk_layer = [&](int lid, const float* w, const float* b, int ld, int hidden_col0, int n_pre,
+                         const int (*pre)[2]) {
+    int kc = 0;
+    for (int i = 0; i < n_pre; ++i, ++kc) wjob(lid, kc, w, ld, 0, 256, pre[i][0], pre[i][1]);
+    if (hidden_col0 >= 0)
+      for (int h = 0; h < 4; ++h, ++kc) wjob(lid, kc, w, ld, 0, 256, hidden_col0 + h * 64, 64);
+    bjob(lid, 0, b, 256);
+  };
+  const int pre_pe[1][2] = {{0, 63}};
+  const int pre_pe_t[2][2] = {{0, 63}, {63, 48}};
+  const int pre_dir[1][2] = {{256, 27}};
+  // static branch (nerf.py:74-91)
+  trunk_layer(L_S1, prm->static_w[0], prm->static_b[0], 63, -1, 1, pre_pe);
+  for (int i = 1; i < 8; ++i) {
+    if (i == 4) trunk_layer(L_S1 + i, prm->static_w[i], prm->static_b[i], 319, 63, 1, pre_pe);
+    else trunk_layer(L_S1 + i, prm->static_w[i], prm->static_b[i], 256, 0, 0, nullptr);
+  }
+  for (int h = 0; h < 4; ++h) wjob(L_SSIG, h, prm->static_sigma_w, 256, 0, 1, h * 64, 64);
+  bjob(L_SSIG, 0, prm->static_sigma_b, 1);
+  trunk_layer(L_SFIN, prm->static_final_w, prm->static_final_b, 256, 0, 0, nullptr);
+  if (desc->use_viewdir) trunk_layer(L_SDIR, prm->static_dir_w, prm->static_dir_b, 283, 0, 1, pre_dir);
+  for (int h = 0; h < 4; ++h) wjob(L_SRGB, h, prm->static_rgb_w, 256, 0, 3, h * 64, 64);
+  bjob(L_SRGB, 0, prm->static_rgb_b, 3);
+  if (desc->has_transient) {   // nerf.py:93-116
+    trunk_layer(L_T1, prm->trans_w[0], prm->trans_b[0], 111, -1, 2, pre_pe_t);
+    for (int i = 1; i < 8; ++i) {
+      if (i == 4) trunk_layer(L_T1 + i, prm->trans_w[i], prm->trans_b[i], 367, 111, 2, pre_pe_t);
+      else trunk_layer(L_T1 + i, prm->trans_w[i], prm->trans_b[i], 256, 0, 0, nullptr);
+    }
+    trunk_layer(L_TFIN, prm->trans_final_w, prm->trans_final_b, 256, 0, 0, nullptr);
+    // head block rows: 0-2 rgb, 3 sigma, 4-6 flow fw, 7-9 flow bw
+    for (int h = 0; h < 4; ++h) {
+      wjob(L_THEAD, h, prm->trans_rgb_w, 256, 0, 3, h * 64, 64);
+      wjob(L_THEAD, h, prm->trans_sigma_w, 256, 3, 1, h * 64, 64);
+      if (desc->has_flow) {
+        wjob(L_THEAD, h, prm->trans_fw_w, 256, 4, 3, h * 64, 64);
+        wjob(L_THEAD, h, prm->trans_bw_w, 256, 7, 3, h * 64, 64);
+      }
+    }
+    bjob(L_THEAD, 0, prm->trans_rgb_b, 3);
+    bjob(L_THEAD, 3, prm->trans_sigma_b, 1);
+    if (desc->has_flow) {
+      bjob(L_THEAD, 4, prm->trans_fw_b, 3);
+      bjob(L_THEAD, 7, prm->trans_bw_b, 3);
+    }
+  }
+  if (missing) return NSFF_EINVAL;
+  if (nj > kMaxPackJobs) return NSFF_EUNSUPPORTED;
+
+  uint8_t* p8 = static_cast<uint8_t*>(pack);
+  NSFF_CUDA_TRY(cudaMemsetAsync(p8, 0, jobs_off, st));   // zero padding rows/cols and unused bias slots
+  NSFF_CUDA_TRY(cudaMemcpyAsync(p8 + jobs_off, &jobs, sizeof(PackJob) * nj, cudaMemcpyHostToDevice, st));
+  // (pageable-source cudaMemcpyAsync returns once `jobs` has been staged, so the host copy may be reused)
+  pack_kernel<<<nj, 256, 0, st>>>(reinterpret_cast<const PackJobs*>(p8 + jobs_off), p8, L.bias_base);
+  return after_launch();
+}
+
+static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_mask, FwdParams& P, int* n_out_cols) {
+  const bool sigma_only = out_mask & NSFF_OUT_SIGMA_ONLY;
+  const bool want_s = out_mask & NSFF_OUT_STATIC, want_t = out_mask & NSFF_OUT_TRANSIENT;
+  const bool want_fw = out_mask & NSFF_OUT_FLOW_FW, want_bw = out_mask & NSFF_OUT_FLOW_BW;
+  if (!want_s && !want_t) return NSFF_EINVAL;
+  if (want_t && !d.has_transient) return NSFF_EINVAL;
+  if ((want_fw || want_bw) && (!want_t || !d.has_flow || sigma_only)) return NSFF_EINVAL;
+  int n = 0, col = 0;
+  auto push = [&](int lid, uint8_t epi) -> Step& {
+    const PackLayer& pl = L.layer[lid];
+    Step& s = P.steps[n++];
+    s.w_off = pl.w_off;
+    s.bias_off = pl.bias_off;
+    s.n = (uint16_t)pl.n;
+    s.nchunks = (uint8_t)pl.nchunks;
+    s.epi = epi;
+    for (int i = 0; i < kMaxChunks; ++i) s.chunk[i] = pl.chunk[i], s.kcnt[i] = pl.kcnt[i];
+    for (int i = 0; i < 16; ++i) s.head_dst[i] = -1, s.head_act[i] = HA_NONE;
+    return s;
+  };
+  P.need_dir = 0;
+  P.need_t = 0;
+  if (want_s) {
+    for (int i = L_S1; i <= L_S8; ++i) push(i, EPI_RELU_HID);
+    if (sigma_only) {
+      Step& s = push(L_SSIG, EPI_HEAD);
+      s.head_dst[0] = (int8_t)col;
+      col += 1;
+    } else {
+      Step& sg = push(L_SSIG, EPI_HEAD);
+      sg.head_dst[0] = (int8_t)(col + 3);
+      push(L_SFIN, EPI_LIN_HID);
+      if (d.use_viewdir) {
+        push(L_SDIR, EPI_RELU_HID);
+        P.need_dir = 1;
+      }
+      Step& rg = push(L_SRGB, EPI_HEAD);
+      for (int i = 0; i < 3; ++i) rg.head_dst[i] = (int8_t)(col + i), rg.head_act[i] = HA_SIGMOID;
+      col += 4;
+    }
+  }
+  if (want_t) {
+    P.need_t = 1;
+    for (int i = L_T1; i <= L_T8; ++i) push(i, EPI_RELU_HID);
+    push(L_TFIN, EPI_LIN_HID);
+    Step& h = push(L_THEAD, EPI_HEAD);
+    if (sigma_only) {
+      h.head_dst[3] = (int8_t)col;
+      col += 1;
+    } else {
+      for (int i = 0; i < 3; ++i) h.head_dst[i] = (int8_t)(col + i), h.head_act[i] = HA_SIGMOID;
+      h.head_dst[3] = (int8_t)(col + 3);
+      col += 4;
+      if (want_fw) {
+        for (int i = 0; i < 3; ++i) h.head_dst[4 + i] = (int8_t)(col + i), h.head_act[4 + i] = HA_FLOW;
+        col += 3;
+      }
+      if (want_bw) {
+        for (int i = 0; i < 3; ++i) h.head_dst[7 + i] = (int8_t)(col + i), h.head_act[7 + i] = HA_FLOW;
+        col += 3;
+      }
+    }
+  }
+  if (n > kMaxSteps) return NSFF_EUNSUPPORTED;
+  P.n_steps = n;
+  *n_out_cols = col;
+  return NSFF_OK;
+}
+
+static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdParams& P, int out_mask, int64_t B,
+                          float* out, int32_t out_ld, void* stream) {
+  if (!desc || !pack || !out) return NSFF_EINVAL;
+  if (B < 0 || B > ((int64_t)1 << 31) - 256) return NSFF_EINVAL;
+  if (B == 0) return NSFF_OK;
+  PackLayout L;
+  int rc = build_layout(*desc, L);
+  if (rc != NSFF_OK) return rc;
+  int ncols = 0;
+  rc = build_program(*desc, L, out_mask, P, &ncols);
+  if (rc != NSFF_OK) return rc;
+  if (out_ld < ncols) return NSFF_EINVAL;
+  int dev = 0, major = 0, sms = 0;
+  NSFF_CUDA_TRY(cudaGetDevice(&dev));
+  NSFF_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) return NSFF_EARCH;
+  NSFF_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  P.pack = static_cast<const uint8_t*>(pack);
+  P.bias = reinterpret_cast<const float*>(P.pack + L.bias_base);
+  P.out = out;
+  P.out_ld = out_ld;
+  P.n_tiles = (int)cdiv64(B, kTileM);
+  P.flow_scale = desc->flow_scale;
+  NSFF_CUDA_TRY(cudaFuncSetAttribute(field_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal));
+  const int grid = P.n_tiles < sms ? P.n_tiles : sms;
+  field_forward_kernel<<<grid, kThreads, kSmemTotal, (cudaStream_t)stream>>>(P);
+  return after_launch();
+}
+
+extern "C" int nsff_field_forward(const nsff_field_desc* desc, const void* pack, const nsff_points* pts,
+                                  int out_mask, float* out, int32_t out_ld, void* stream) {
+  if (!pts || !desc) return NSFF_EINVAL;
+  if (pts->B > 0 && (!pts->xyz || pts->S < 1)) return NSFF_EINVAL;
+  if ((out_mask & NSFF_OUT_TRANSIENT) && !pts->t_table) return NSFF_EINVAL;
+  if ((out_mask & NSFF_OUT_STATIC) && !(out_mask & NSFF_OUT_SIGMA_ONLY) && desc->use_viewdir && !pts->dirs)
+    return NSFF_EINVAL;
+  if (pts->t_table && ((uintptr_t)pts->t_table & 15u)) return NSFF_EINVAL;
+  FwdParams P;
+  memset(&P, 0, sizeof(P));
+  P.pts = *pts;
+  P.x_emb = nullptr;
+  return launch_forward(desc, pack, P, out_mask, pts->B, out, out_ld, stream);
+}
+
+extern "C" int nsff_field_forward_embedded(const nsff_field_desc* desc, const void* pack, const float* x,
+                                           int32_t x_ld, int64_t B, int out_mask, float* out, int32_t out_ld,
+                                           void* stream) {
+  if (!desc || (B > 0 && !x)) return NSFF_EINVAL;
+  FwdParams P;
+  memset(&P, 0, sizeof(P));
+  P.pts.B = B;
+  P.pts.S = 1;
+  P.x_emb = x;
+  P.x_ld = x_ld;
+  // column offsets of the embedded row (nerf.py:142-160); sigma_only rows carry no dir/a columns
+  if (out_mask & NSFF_OUT_SIGMA_ONLY) {
+    P.c_dir = 0;
+    P.c_t = desc->in_xyz;
+    if (x_ld < desc->in_xyz + ((out_mask & NSFF_OUT_TRANSIENT) ? desc->in_t : 0)) return NSFF_EINVAL;
+  } else {
+    P.c_dir = desc->in_xyz;
+    P.c_t = desc->in_xyz + desc->in_dir + desc->in_a;
+    if (x_ld < desc->in_xyz + desc->in_dir + desc->in_a + ((out_mask & NSFF_OUT_TRANSIENT) ? desc->in_t : 0))
+      return NSFF_EINVAL;
+  }
+  return launch_forward(desc, pack, P, out_mask, B, out, out_ld, stream);
+}
