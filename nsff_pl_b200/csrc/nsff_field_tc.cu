@@ -21,6 +21,7 @@
 // (one mbarrier per chunk), so the tensor pipe only idles for the first 64-column slice of each
 // epilogue; the other accumulator absorbs layer l+1 while layer l is still being drained.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <initializer_list>
@@ -158,8 +159,10 @@ constexpr uint32_t kChunkBytes = 128 * 128;          // 128 rows x 64 bf16
 constexpr uint32_t kStageBytes = 256 * 128;          // 256 rows x 64 bf16
 constexpr uint32_t kSmemA = 7 * kChunkBytes;         // 4 hidden + PE + T + DIR
 constexpr uint32_t kSmemB = kStages * kStageBytes;
+constexpr int kBiasSlots = 4;
+constexpr uint32_t kSmemBias = kBiasSlots * 1024;    // fp32 bias rows of the steps in flight
 constexpr uint32_t kSmemBar = 256;
-constexpr uint32_t kSmemTotal = kSmemA + kSmemB + kSmemBar + 1024;   // + alignment slack
+constexpr uint32_t kSmemTotal = kSmemA + kSmemB + kSmemBias + kSmemBar + 1024;   // + alignment slack
 constexpr int kMaxSteps = 24;
 
 struct Step {
@@ -197,7 +200,8 @@ enum {
   BAR_EXTRA_FULL = BAR_HID_FULL + 4,    // [1]
   BAR_ACC_FULL = BAR_EXTRA_FULL + 1,    // [2]
   BAR_ACC_EMPTY = BAR_ACC_FULL + 2,     // [2]
-  BAR_COUNT = BAR_ACC_EMPTY + 2
+  BAR_BIAS_FULL = BAR_ACC_EMPTY + 2,    // [kBiasSlots]
+  BAR_COUNT = BAR_BIAS_FULL + kBiasSlots
 };
 static_assert(BAR_COUNT * 8 + 8 <= kSmemBar, "barrier region too small");
 
@@ -227,7 +231,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;                       // 7 chunks
   const uint32_t sB = smem_base + kSmemA;              // ring
-  const uint32_t sBar = sB + kSmemB;
+  const uint32_t sBias = sB + kSmemB;
+  const uint32_t sBar = sBias + kSmemBias;
   const uint32_t sTmemPtr = sBar + BAR_COUNT * 8;
   auto bar = [&](int i) { return sBar + (uint32_t)i * 8u; };
 
@@ -244,6 +249,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
       mbar_init(bar(BAR_ACC_FULL + i), 1);
       mbar_init(bar(BAR_ACC_EMPTY + i), kEpiWarps);
     }
+    for (int i = 0; i < kBiasSlots; ++i) mbar_init(bar(BAR_BIAS_FULL + i), 1);
     fence_mbar_init();
   }
   if (warp == kEpiWarps + 1) tmem_alloc(sTmemPtr, 512);
@@ -256,55 +262,69 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
   const int n_steps = P.n_steps;
 
   if (warp == kEpiWarps) {
-    // ===================== weight producer =====================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-        for (int s = 0; s < n_steps; ++s) {
-          const Step& st = P.steps[s];
-          const uint32_t bytes = (uint32_t)st.n * 128u;
-          for (int kc = 0; kc < st.nchunks; ++kc, ++it) {
-            const uint32_t stage = it % kStages, use = it / kStages;
-            mbar_wait(bar(BAR_W_EMPTY + stage), (use & 1u) ^ 1u);
+    // ===================== weight + bias producer (whole warp walks the program, one elected lane copies) ====
+    uint32_t it = 0, gstep = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+      for (int s = 0; s < n_steps; ++s, ++gstep) {
+        const Step& st = P.steps[s];
+        const uint32_t bytes = (uint32_t)st.n * 128u;
+        {
+          // bias row of this step -> slot gstep%4.  Waiting for the epilogue of step gstep-2 (same TMEM slot)
+          // also proves that the epilogue of step gstep-4, the previous user of this bias slot, is over.
+          const uint32_t slot = gstep & 1u, use = gstep >> 1, bslot = gstep & (kBiasSlots - 1);
+          mbar_wait(bar(BAR_ACC_EMPTY + slot), (use & 1u) ^ 1u);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar(BAR_BIAS_FULL + bslot), (uint32_t)st.n * 4u);
+            bulk_g2s(sBias + bslot * 1024u, P.bias + st.bias_off, (uint32_t)st.n * 4u, bar(BAR_BIAS_FULL + bslot));
+          }
+          __syncwarp();
+        }
+        for (int kc = 0; kc < st.nchunks; ++kc, ++it) {
+          const uint32_t stage = it % kStages, use = it / kStages;
+          mbar_wait(bar(BAR_W_EMPTY + stage), (use & 1u) ^ 1u);
+          if (elect_one()) {
             mbar_arrive_expect_tx(bar(BAR_W_FULL + stage), bytes);
             bulk_g2s(sB + stage * kStageBytes, P.pack + st.w_off + (uint32_t)kc * bytes, bytes,
                      bar(BAR_W_FULL + stage));
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == kEpiWarps + 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      uint32_t it = 0, gstep = 0, hid_gen = 0, tile_iter = 0;
-      for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tile_iter) {
-        mbar_wait(bar(BAR_EXTRA_FULL), tile_iter & 1u);
-        for (int s = 0; s < n_steps; ++s, ++gstep) {
-          const Step& st = P.steps[s];
-          const uint32_t slot = gstep & 1u, use = gstep >> 1;
-          mbar_wait(bar(BAR_ACC_EMPTY + slot), (use & 1u) ^ 1u);
-          const uint32_t d_tmem = tmem_base + slot * 256u;
-          const uint32_t idesc = make_idesc_bf16(kTileM, st.n);
-          uint32_t accumulate = 0;
-          for (int kc = 0; kc < st.nchunks; ++kc, ++it) {
-            const uint32_t ch = st.chunk[kc];
-            if (ch < 4) mbar_wait(bar(BAR_HID_FULL + ch), (hid_gen - 1u) & 1u);
-            const uint32_t stage = it % kStages, wuse = it / kStages;
-            mbar_wait(bar(BAR_W_FULL + stage), wuse & 1u);
-            tc_fence_after_sync();
+    // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+    uint32_t it = 0, gstep = 0, hid_gen = 0, tile_iter = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tile_iter) {
+      mbar_wait(bar(BAR_EXTRA_FULL), tile_iter & 1u);
+      for (int s = 0; s < n_steps; ++s, ++gstep) {
+        const Step& st = P.steps[s];
+        const uint32_t slot = gstep & 1u, use = gstep >> 1;
+        mbar_wait(bar(BAR_ACC_EMPTY + slot), (use & 1u) ^ 1u);
+        const uint32_t d_tmem = tmem_base + slot * 256u;
+        const uint32_t idesc = make_idesc_bf16(kTileM, st.n);
+        const int nchunks = st.nchunks;
+        const uint32_t hid_parity = (hid_gen - 1u) & 1u;
+        for (int kc = 0; kc < nchunks; ++kc, ++it) {
+          const uint32_t ch = st.chunk[kc];
+          const int kcnt = st.kcnt[kc];
+          if (ch < 4) mbar_wait(bar(BAR_HID_FULL + ch), hid_parity);
+          const uint32_t stage = it % kStages, wuse = it / kStages;
+          mbar_wait(bar(BAR_W_FULL + stage), wuse & 1u);
+          tc_fence_after_sync();
+          if (elect_one()) {
             const uint64_t a0 = make_desc_k128(sA + ch * kChunkBytes);
             const uint64_t b0 = make_desc_k128(sB + stage * kStageBytes);
-            const int kcnt = st.kcnt[kc];
-            for (int k = 0; k < kcnt; ++k) {
-              // +32 B per K=16 step inside the 128 B swizzle row (descriptor address unit = 16 B)
-              mma_bf16_ss(d_tmem, a0 + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), idesc, accumulate);
-              accumulate = 1;
-            }
+            // +32 B per K=16 step inside the 128 B swizzle row (descriptor address unit = 16 B)
+            mma_bf16_ss(d_tmem, a0, b0, idesc, kc > 0 ? 1u : 0u);
+            mma_bf16_ss(d_tmem, a0 + 2, b0 + 2, idesc, 1u);
+            if (kcnt > 2) mma_bf16_ss(d_tmem, a0 + 4, b0 + 4, idesc, 1u);
+            if (kcnt > 3) mma_bf16_ss(d_tmem, a0 + 6, b0 + 6, idesc, 1u);
             mma_commit(bar(BAR_W_EMPTY + stage));
+            if (kc == nchunks - 1) mma_commit(bar(BAR_ACC_FULL + slot));
           }
-          mma_commit(bar(BAR_ACC_FULL + slot));
-          if (st.epi != EPI_HEAD) ++hid_gen;
+          __syncwarp();
         }
+        if (st.epi != EPI_HEAD) ++hid_gen;
       }
     }
   } else {
@@ -436,18 +456,24 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
         mbar_wait(bar(BAR_ACC_FULL + slot), use & 1u);
         tc_fence_after_sync();
         const uint32_t t_acc = tmem_base + lane_field + slot * 256u;
+        const uint32_t bslot = gstep & (kBiasSlots - 1);
+        mbar_wait(bar(BAR_BIAS_FULL + bslot), (gstep >> 2) & 1u);   // landed long ago: issued a step ahead
+        const uint32_t s_bias = sBias + bslot * 1024u;
         if (st.epi != EPI_HEAD) {
           const bool relu = st.epi == EPI_RELU_HID;
-#pragma unroll 1
+          // software pipeline over the four 64-column slices: TMEM load of slice c+1 is in flight while slice c
+          // is biased / activated / packed / stored.
+          uint32_t v[2][32];
+          tmem_ld32(t_acc + (uint32_t)(half * 32), v[0]);
+#pragma unroll
           for (int c = 0; c < 4; ++c) {
-            uint32_t v[32];
-            tmem_ld32(t_acc + (uint32_t)(c * 64 + half * 32), v);
-            const float4* bp = reinterpret_cast<const float4*>(P.bias + st.bias_off + c * 64 + half * 32);
             float4 b[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) b[i] = __ldg(bp + i);
+            for (int i = 0; i < 8; ++i) lds_v4(s_bias + (uint32_t)((c * 64 + half * 32 + i * 4) * 4), b[i]);
             tmem_ld_wait();
-            if (c == 3) {
+            if (c < 3) {
+              tmem_ld32(t_acc + (uint32_t)((c + 1) * 64 + half * 32), v[(c + 1) & 1]);
+            } else {
               // accumulator fully drained into registers: hand the TMEM slot back to the MMA warp
               tc_fence_before_sync();
               __syncwarp();
@@ -460,7 +486,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
               for (int i = 0; i < 8; ++i) {
                 const float4 bb = b[u * 2 + (i >> 2)];
                 const float bv = (i & 3) == 0 ? bb.x : (i & 3) == 1 ? bb.y : (i & 3) == 2 ? bb.z : bb.w;
-                float x = __uint_as_float(v[u * 8 + i]) + bv;
+                float x = __uint_as_float(v[c & 1][u * 8 + i]) + bv;
                 f[i] = relu ? fmaxf(x, 0.f) : x;
               }
               store_unit(sA + (uint32_t)c * kChunkBytes, row, half * 4 + u, f);
@@ -480,7 +506,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
               for (int i = 0; i < 16; ++i) {
                 const int dst = st.head_dst[i];
                 if (dst < 0) continue;
-                float x = __uint_as_float(v[i]) + __ldg(P.bias + st.bias_off + i);
+                float bi;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(bi) : "r"(s_bias + (uint32_t)(i * 4)));
+                float x = __uint_as_float(v[i]) + bi;
                 const int act = st.head_act[i];
                 if (act == HA_SIGMOID) x = sigmoid_f(x);
                 else if (act == HA_FLOW) x = (zrow > kZFar) ? 0.f : P.flow_scale * tanhf(x);
@@ -699,7 +727,11 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
   P.n_tiles = (int)cdiv64(B, kTileM);
   P.flow_scale = desc->flow_scale;
   NSFF_CUDA_TRY(cudaFuncSetAttribute(field_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal));
-  const int grid = P.n_tiles < sms ? P.n_tiles : sms;
+  int grid = P.n_tiles < sms ? P.n_tiles : sms;
+  if (const char* cap = getenv("NSFF_MAX_CTAS")) {          // experiment knob: fewer resident CTAs
+    int c = atoi(cap);
+    if (c > 0 && c < grid) grid = c;
+  }
   field_forward_kernel<<<grid, kThreads, kSmemTotal, (cudaStream_t)stream>>>(P);
   return after_launch();
 }
