@@ -154,16 +154,25 @@ __global__ void pack_kernel(const PackJobs* __restrict__ jobs_dev, uint8_t* __re
 constexpr int kTileM = 128;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (kEpiWarps + 2) * 32;
-constexpr int kStages = 3;
 constexpr uint32_t kChunkBytes = 128 * 128;          // 128 rows x 64 bf16
-constexpr uint32_t kStageBytes = 256 * 128;          // 256 rows x 64 bf16
 constexpr uint32_t kSmemA = 7 * kChunkBytes;         // 4 hidden + PE + T + DIR
-constexpr uint32_t kSmemB = kStages * kStageBytes;
 constexpr int kBiasSlots = 4;
 constexpr uint32_t kSmemBias = kBiasSlots * 1024;    // fp32 bias rows of the steps in flight
-constexpr uint32_t kSmemBar = 256;
-constexpr uint32_t kSmemTotal = kSmemA + kSmemB + kSmemBias + kSmemBar + 1024;   // + alignment slack
+constexpr uint32_t kSmemBar = 512;
 constexpr int kMaxSteps = 24;
+constexpr int kMaxStages = 6;
+
+// kCtas = 1: one CTA per tile, cta_group::1 MMAs (M=128), each CTA streams whole weight blocks.
+// kCtas = 2: CTA pair (cluster of 2, one TPC), cta_group::2 MMAs (M=256 = two tiles): each CTA stages only
+//            its half of every weight block (N/2 rows), so the L2->SM weight stream and the B-operand smem
+//            traffic halve and the ring holds twice as many K-chunks (6 stages of 16 KB).
+template <int kCtas>
+struct Cfg {
+  static constexpr int kStages = kCtas == 1 ? 3 : 6;
+  static constexpr uint32_t kStageBytes = (256 / kCtas) * 128;     // (N/kCtas) rows x 64 bf16
+  static constexpr uint32_t kSmemB = kStages * kStageBytes;
+  static constexpr uint32_t kSmemTotal = kSmemA + kSmemB + kSmemBias + kSmemBar + 1024;   // + alignment slack
+};
 
 struct Step {
   uint32_t w_off;
@@ -194,14 +203,16 @@ struct FwdParams {
 
 // barrier slots (8 bytes each) inside the barrier region
 enum {
-  BAR_W_FULL = 0,                       // [kStages]
-  BAR_W_EMPTY = BAR_W_FULL + kStages,   // [kStages]
-  BAR_HID_FULL = BAR_W_EMPTY + kStages, // [4]
-  BAR_EXTRA_FULL = BAR_HID_FULL + 4,    // [1]
-  BAR_ACC_FULL = BAR_EXTRA_FULL + 1,    // [2]
-  BAR_ACC_EMPTY = BAR_ACC_FULL + 2,     // [2]
-  BAR_BIAS_FULL = BAR_ACC_EMPTY + 2,    // [kBiasSlots]
-  BAR_COUNT = BAR_BIAS_FULL + kBiasSlots
+  BAR_W_FULL = 0,                           // [kMaxStages] own weight half landed (tx)
+  BAR_W_EMPTY = BAR_W_FULL + kMaxStages,    // [kMaxStages] MMAs that read the stage completed (commit)
+  BAR_W_PEER = BAR_W_EMPTY + kMaxStages,    // [kMaxStages] pair mode, leader: the peer CTA's half landed
+  BAR_HID_FULL = BAR_W_PEER + kMaxStages,   // [4]  hidden chunk written (by all CTAs of the group)
+  BAR_EXTRA_FULL = BAR_HID_FULL + 4,        // [1]  prologue chunks written
+  BAR_ACC_FULL = BAR_EXTRA_FULL + 1,        // [2]  accumulator complete (commit)
+  BAR_ACC_EMPTY = BAR_ACC_FULL + 2,         // [2]  accumulator drained
+  BAR_BIAS_FULL = BAR_ACC_EMPTY + 2,        // [kBiasSlots]
+  BAR_BIAS_EMPTY = BAR_BIAS_FULL + kBiasSlots,   // [kBiasSlots]
+  BAR_COUNT = BAR_BIAS_EMPTY + kBiasSlots
 };
 static_assert(BAR_COUNT * 8 + 8 <= kSmemBar, "barrier region too small");
 
@@ -226,35 +237,164 @@ __device__ __forceinline__ float pe_col(int c, const float (&base)[3], const flo
   return r < 3 ? sn[f - f0][r] : cs[f - f0][r - 3];
 }
 
+// Prologue of one tile: encode the inputs of `row` into the PE / time-code / PE(dir) chunks (bf16, swizzled).
+__device__ __forceinline__ void encode_tile_row(const FwdParams& P, uint32_t sA, int row, int half, int64_t p,
+                                                bool valid) {
+  const uint32_t chPE = sA + CH_PE * kChunkBytes, chT = sA + CH_T * kChunkBytes, chD = sA + CH_DIR * kChunkBytes;
+  if (P.x_emb == nullptr) {
+    const int64_t ray = p / P.pts.S;
+    float base[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = P.pts.xyz[p * 3 + c];
+      if (P.pts.offset) v = __fadd_rn(v, P.pts.offset[p * P.pts.offset_ld + c]);
+      base[c] = v;
+    }
+    if (half == 0 && valid && P.pts.xyz_out) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) P.pts.xyz_out[p * 3 + c] = base[c];
+    }
+    // PE(xyz): half 0 -> columns 0..31 (freqs 0..4), half 1 -> columns 32..63 (freqs 4..9)
+    if (half == 0) {
+      float sn[5][3], cs[5][3];
+#pragma unroll
+      for (int f = 0; f < 5; ++f)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sincosf(__fmul_rn((float)(1 << f), base[c]), &sn[f][c], &cs[f][c]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = pe_col<5>(u * 8 + i, base, sn, cs, 0);
+        store_unit(chPE, row, u, v);
+      }
+    } else {
+      float sn[6][3], cs[6][3];
+#pragma unroll
+      for (int f = 0; f < 6; ++f)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sincosf(__fmul_rn((float)(16 << f), base[c]), &sn[f][c], &cs[f][c]);
+#pragma unroll
+      for (int u = 4; u < 8; ++u) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (u * 8 + i == 63) ? 0.f : pe_col<6>(u * 8 + i, base, sn, cs, 4);
+        store_unit(chPE, row, u, v);
+      }
+    }
+    if (P.need_t) {
+      int64_t trow = ray;
+      if (P.pts.t_index) {
+        trow = P.pts.t_index[ray] + P.pts.t_shift;
+        trow = trow < 0 ? 0 : (trow > P.pts.max_t ? P.pts.max_t : trow);
+      }
+      const float4* tp = reinterpret_cast<const float4*>(P.pts.t_table + trow * 48) + half * 6;
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        float4 a = __ldg(tp + 2 * u), b = __ldg(tp + 2 * u + 1);
+        float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        store_unit(chT, row, half * 3 + u, v);
+      }
+    }
+    if (P.need_dir && half == 1) {
+      float d[3] = {P.pts.dirs[ray * 3 + 0], P.pts.dirs[ray * 3 + 1], P.pts.dirs[ray * 3 + 2]};
+      float sn[4][3], cs[4][3];
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sincosf(__fmul_rn((float)(1 << f), d[c]), &sn[f][c], &cs[f][c]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (u * 8 + i >= 27) ? 0.f : pe_col<4>(u * 8 + i, d, sn, cs, 0);
+        store_unit(chD, row, u, v);
+      }
+    }
+  } else {
+    // embedded mode: x row = [xyz63 | dir27 | a | t48] already encoded by the caller
+    const float* xr = P.x_emb + p * P.x_ld;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int c = (half * 4 + u) * 8 + i;
+        v[i] = c < 63 ? xr[c] : 0.f;
+      }
+      store_unit(chPE, row, half * 4 + u, v);
+    }
+    if (P.need_t) {
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = xr[P.c_t + (half * 3 + u) * 8 + i];
+        store_unit(chT, row, half * 3 + u, v);
+      }
+    }
+    if (P.need_dir && half == 1) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (u * 8 + i >= 27) ? 0.f : xr[P.c_dir + u * 8 + i];
+        store_unit(chD, row, u, v);
+      }
+    }
+  }
+}
+
+template <int kCtas>
 __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid_constant__ FwdParams P) {
+  using C = Cfg<kCtas>;
+  constexpr int kStages = C::kStages;
+  constexpr uint32_t kStageBytes = C::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;                       // 7 chunks
   const uint32_t sB = smem_base + kSmemA;              // ring
-  const uint32_t sBias = sB + kSmemB;
+  const uint32_t sBias = sB + C::kSmemB;
   const uint32_t sBar = sBias + kSmemBias;
   const uint32_t sTmemPtr = sBar + BAR_COUNT * 8;
   auto bar = [&](int i) { return sBar + (uint32_t)i * 8u; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = kCtas == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  // barriers the MMA issuer waits on live in the leader CTA; both CTAs of a pair arrive there
+  auto arrive_leader = [&](int i) {
+    if constexpr (kCtas == 1) mbar_arrive(bar(i));
+    else mbar_arrive_cluster(mapa_cluster(bar(i), 0));
+  };
+  const int group = blockIdx.x / kCtas, n_groups = gridDim.x / kCtas;
+  const int n_units = (P.n_tiles + kCtas - 1) / kCtas;       // tiles (1 CTA) or tile pairs (CTA pair)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(bar(BAR_W_FULL + i), 1);
       mbar_init(bar(BAR_W_EMPTY + i), 1);
+      mbar_init(bar(BAR_W_PEER + i), 1);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_HID_FULL + i), kEpiWarps);
-    mbar_init(bar(BAR_EXTRA_FULL), kEpiWarps);
+    for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_HID_FULL + i), kEpiWarps * kCtas);
+    mbar_init(bar(BAR_EXTRA_FULL), kEpiWarps * kCtas);
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(BAR_ACC_FULL + i), 1);
-      mbar_init(bar(BAR_ACC_EMPTY + i), kEpiWarps);
+      mbar_init(bar(BAR_ACC_EMPTY + i), kEpiWarps * kCtas);
     }
-    for (int i = 0; i < kBiasSlots; ++i) mbar_init(bar(BAR_BIAS_FULL + i), 1);
+    for (int i = 0; i < kBiasSlots; ++i) {
+      mbar_init(bar(BAR_BIAS_FULL + i), 1);
+      mbar_init(bar(BAR_BIAS_EMPTY + i), kEpiWarps);
+    }
     fence_mbar_init();
   }
-  if (warp == kEpiWarps + 1) tmem_alloc(sTmemPtr, 512);
+  if (warp == kEpiWarps + 1) {
+    if constexpr (kCtas == 1) tmem_alloc(sTmemPtr, 512);
+    else tmem_alloc_pair(sTmemPtr, 512);
+  }
   tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (kCtas == 1) __syncthreads();
+  else cluster_sync_all();              // also: the peer's barriers are initialised before any remote arrive
   tc_fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sTmemPtr));
@@ -264,15 +404,14 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
   if (warp == kEpiWarps) {
     // ===================== weight + bias producer (whole warp walks the program, one elected lane copies) ====
     uint32_t it = 0, gstep = 0;
-    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+    for (int unit = group; unit < n_units; unit += n_groups) {
       for (int s = 0; s < n_steps; ++s, ++gstep) {
         const Step& st = P.steps[s];
-        const uint32_t bytes = (uint32_t)st.n * 128u;
+        const uint32_t block_bytes = (uint32_t)st.n * 128u;          // whole N x 64 block
+        const uint32_t bytes = block_bytes / kCtas;                  // this CTA's N/kCtas rows
         {
-          // bias row of this step -> slot gstep%4.  Waiting for the epilogue of step gstep-2 (same TMEM slot)
-          // also proves that the epilogue of step gstep-4, the previous user of this bias slot, is over.
-          const uint32_t slot = gstep & 1u, use = gstep >> 1, bslot = gstep & (kBiasSlots - 1);
-          mbar_wait(bar(BAR_ACC_EMPTY + slot), (use & 1u) ^ 1u);
+          const uint32_t bslot = gstep & (kBiasSlots - 1), buse = gstep / kBiasSlots;
+          mbar_wait(bar(BAR_BIAS_EMPTY + bslot), (buse & 1u) ^ 1u);
           if (elect_one()) {
             mbar_arrive_expect_tx(bar(BAR_BIAS_FULL + bslot), (uint32_t)st.n * 4u);
             bulk_g2s(sBias + bslot * 1024u, P.bias + st.bias_off, (uint32_t)st.n * 4u, bar(BAR_BIAS_FULL + bslot));
@@ -284,7 +423,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
           mbar_wait(bar(BAR_W_EMPTY + stage), (use & 1u) ^ 1u);
           if (elect_one()) {
             mbar_arrive_expect_tx(bar(BAR_W_FULL + stage), bytes);
-            bulk_g2s(sB + stage * kStageBytes, P.pack + st.w_off + (uint32_t)kc * bytes, bytes,
+            bulk_g2s(sB + stage * kStageBytes, P.pack + st.w_off + (uint32_t)kc * block_bytes + cta_rank * bytes, bytes,
                      bar(BAR_W_FULL + stage));
           }
           __syncwarp();
@@ -292,39 +431,70 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
       }
     }
   } else if (warp == kEpiWarps + 1) {
-    // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
-    uint32_t it = 0, gstep = 0, hid_gen = 0, tile_iter = 0;
-    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tile_iter) {
-      mbar_wait(bar(BAR_EXTRA_FULL), tile_iter & 1u);
-      for (int s = 0; s < n_steps; ++s, ++gstep) {
-        const Step& st = P.steps[s];
-        const uint32_t slot = gstep & 1u, use = gstep >> 1;
-        mbar_wait(bar(BAR_ACC_EMPTY + slot), (use & 1u) ^ 1u);
-        const uint32_t d_tmem = tmem_base + slot * 256u;
-        const uint32_t idesc = make_idesc_bf16(kTileM, st.n);
-        const int nchunks = st.nchunks;
-        const uint32_t hid_parity = (hid_gen - 1u) & 1u;
-        for (int kc = 0; kc < nchunks; ++kc, ++it) {
-          const uint32_t ch = st.chunk[kc];
-          const int kcnt = st.kcnt[kc];
-          if (ch < 4) mbar_wait(bar(BAR_HID_FULL + ch), hid_parity);
-          const uint32_t stage = it % kStages, wuse = it / kStages;
-          mbar_wait(bar(BAR_W_FULL + stage), wuse & 1u);
-          tc_fence_after_sync();
-          if (elect_one()) {
-            const uint64_t a0 = make_desc_k128(sA + ch * kChunkBytes);
-            const uint64_t b0 = make_desc_k128(sB + stage * kStageBytes);
-            // +32 B per K=16 step inside the 128 B swizzle row (descriptor address unit = 16 B)
-            mma_bf16_ss(d_tmem, a0, b0, idesc, kc > 0 ? 1u : 0u);
-            mma_bf16_ss(d_tmem, a0 + 2, b0 + 2, idesc, 1u);
-            if (kcnt > 2) mma_bf16_ss(d_tmem, a0 + 4, b0 + 4, idesc, 1u);
-            if (kcnt > 3) mma_bf16_ss(d_tmem, a0 + 6, b0 + 6, idesc, 1u);
-            mma_commit(bar(BAR_W_EMPTY + stage));
-            if (kc == nchunks - 1) mma_commit(bar(BAR_ACC_FULL + slot));
+    if (leader) {
+      // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+      auto wait_group = [&](int i, uint32_t parity) {      // barriers both CTAs of a pair arrive on
+        if constexpr (kCtas == 1) mbar_wait(bar(i), parity);
+        else mbar_wait(bar(i), parity);
+      };
+      uint32_t it = 0, gstep = 0, hid_gen = 0, unit_iter = 0;
+      for (int unit = group; unit < n_units; unit += n_groups, ++unit_iter) {
+        wait_group(BAR_EXTRA_FULL, unit_iter & 1u);
+        for (int s = 0; s < n_steps; ++s, ++gstep) {
+          const Step& st = P.steps[s];
+          const uint32_t slot = gstep & 1u, use = gstep >> 1;
+          wait_group(BAR_ACC_EMPTY + slot, (use & 1u) ^ 1u);
+          const uint32_t d_tmem = tmem_base + slot * 256u;
+          const uint32_t idesc = make_idesc_bf16(kTileM * kCtas, st.n);
+          const int nchunks = st.nchunks;
+          const uint32_t hid_parity = (hid_gen - 1u) & 1u;
+          for (int kc = 0; kc < nchunks; ++kc, ++it) {
+            const uint32_t ch = st.chunk[kc];
+            const int kcnt = st.kcnt[kc];
+            if (ch < 4) wait_group(BAR_HID_FULL + ch, hid_parity);
+            const uint32_t stage = it % kStages, wuse = it / kStages;
+            mbar_wait(bar(BAR_W_FULL + stage), wuse & 1u);
+            if constexpr (kCtas == 2) mbar_wait(bar(BAR_W_PEER + stage), wuse & 1u);
+            tc_fence_after_sync();
+            if (elect_one()) {
+              const uint64_t a0 = make_desc_k128(sA + ch * kChunkBytes);
+              const uint64_t b0 = make_desc_k128(sB + stage * kStageBytes);
+              const uint32_t acc0 = kc > 0 ? 1u : 0u;
+              // +32 B per K=16 step inside the 128 B swizzle row (descriptor address unit = 16 B)
+              if constexpr (kCtas == 1) {
+                mma_bf16_ss(d_tmem, a0, b0, idesc, acc0);
+                mma_bf16_ss(d_tmem, a0 + 2, b0 + 2, idesc, 1u);
+                if (kcnt > 2) mma_bf16_ss(d_tmem, a0 + 4, b0 + 4, idesc, 1u);
+                if (kcnt > 3) mma_bf16_ss(d_tmem, a0 + 6, b0 + 6, idesc, 1u);
+                mma_commit(bar(BAR_W_EMPTY + stage));
+                if (kc == nchunks - 1) mma_commit(bar(BAR_ACC_FULL + slot));
+              } else {
+                mma_bf16_ss_pair(d_tmem, a0, b0, idesc, acc0);
+                mma_bf16_ss_pair(d_tmem, a0 + 2, b0 + 2, idesc, 1u);
+                if (kcnt > 2) mma_bf16_ss_pair(d_tmem, a0 + 4, b0 + 4, idesc, 1u);
+                if (kcnt > 3) mma_bf16_ss_pair(d_tmem, a0 + 6, b0 + 6, idesc, 1u);
+                mma_commit_pair_mc(bar(BAR_W_EMPTY + stage), 3);       // frees the stage in BOTH CTAs
+                if (kc == nchunks - 1) mma_commit_pair_mc(bar(BAR_ACC_FULL + slot), 3);
+              }
+            }
+            __syncwarp();
           }
-          __syncwarp();
+          if (st.epi != EPI_HEAD) ++hid_gen;
         }
-        if (st.epi != EPI_HEAD) ++hid_gen;
+      }
+    } else {
+      // ===================== pair mode, peer CTA: relay "my weight half has landed" to the leader ==============
+      uint32_t it = 0;
+      for (int unit = group; unit < n_units; unit += n_groups) {
+        for (int s = 0; s < n_steps; ++s) {
+          const int nchunks = P.steps[s].nchunks;
+          for (int kc = 0; kc < nchunks; ++kc, ++it) {
+            const uint32_t stage = it % kStages, wuse = it / kStages;
+            mbar_wait(bar(BAR_W_FULL + stage), wuse & 1u);
+            if (lane == 0) mbar_arrive_cluster(mapa_cluster(bar(BAR_W_PEER + stage), 0));
+            __syncwarp();
+          }
+        }
       }
     }
   } else {
@@ -333,118 +503,17 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
     const int row = q * 32 + lane;
     const uint32_t lane_field = (uint32_t)(q * 32) << 16;
     uint32_t gstep = 0;
-    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+    for (int unit = group; unit < n_units; unit += n_groups) {
+      const int tile = unit * kCtas + (int)cta_rank;
       const int64_t p_raw = (int64_t)tile * kTileM + row;
       const bool valid = p_raw < P.pts.B;
       const int64_t p = valid ? p_raw : P.pts.B - 1;
       // ---------------- prologue: encode this tile's inputs into the extra chunks ----------------
       // (all MMAs of the previous tile have completed: its last acc_full was waited on below)
-      const uint32_t chPE = sA + CH_PE * kChunkBytes, chT = sA + CH_T * kChunkBytes, chD = sA + CH_DIR * kChunkBytes;
-      if (P.x_emb == nullptr) {
-        const int64_t ray = p / P.pts.S;
-        float base[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          float v = P.pts.xyz[p * 3 + c];
-          if (P.pts.offset) v = __fadd_rn(v, P.pts.offset[p * P.pts.offset_ld + c]);
-          base[c] = v;
-        }
-        if (half == 0 && valid && P.pts.xyz_out) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) P.pts.xyz_out[p * 3 + c] = base[c];
-        }
-        // PE(xyz): half 0 -> columns 0..31 (freqs 0..4), half 1 -> columns 32..63 (freqs 4..9)
-        if (half == 0) {
-          float sn[5][3], cs[5][3];
-#pragma unroll
-          for (int f = 0; f < 5; ++f)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) sincosf(__fmul_rn((float)(1 << f), base[c]), &sn[f][c], &cs[f][c]);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = pe_col<5>(u * 8 + i, base, sn, cs, 0);
-            store_unit(chPE, row, u, v);
-          }
-        } else {
-          float sn[6][3], cs[6][3];
-#pragma unroll
-          for (int f = 0; f < 6; ++f)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) sincosf(__fmul_rn((float)(16 << f), base[c]), &sn[f][c], &cs[f][c]);
-#pragma unroll
-          for (int u = 4; u < 8; ++u) {
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = (u * 8 + i == 63) ? 0.f : pe_col<6>(u * 8 + i, base, sn, cs, 4);
-            store_unit(chPE, row, u, v);
-          }
-        }
-        if (P.need_t) {
-          int64_t trow = ray;
-          if (P.pts.t_index) {
-            trow = P.pts.t_index[ray] + P.pts.t_shift;
-            trow = trow < 0 ? 0 : (trow > P.pts.max_t ? P.pts.max_t : trow);
-          }
-          const float4* tp = reinterpret_cast<const float4*>(P.pts.t_table + trow * 48) + half * 6;
-#pragma unroll
-          for (int u = 0; u < 3; ++u) {
-            float4 a = __ldg(tp + 2 * u), b = __ldg(tp + 2 * u + 1);
-            float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-            store_unit(chT, row, half * 3 + u, v);
-          }
-        }
-        if (P.need_dir && half == 1) {
-          float d[3] = {P.pts.dirs[ray * 3 + 0], P.pts.dirs[ray * 3 + 1], P.pts.dirs[ray * 3 + 2]};
-          float sn[4][3], cs[4][3];
-#pragma unroll
-          for (int f = 0; f < 4; ++f)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) sincosf(__fmul_rn((float)(1 << f), d[c]), &sn[f][c], &cs[f][c]);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = (u * 8 + i >= 27) ? 0.f : pe_col<4>(u * 8 + i, d, sn, cs, 0);
-            store_unit(chD, row, u, v);
-          }
-        }
-      } else {
-        // embedded mode: x row = [xyz63 | dir27 | a | t48] already encoded by the caller
-        const float* xr = P.x_emb + p * P.x_ld;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          float v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            int c = (half * 4 + u) * 8 + i;
-            v[i] = c < 63 ? xr[c] : 0.f;
-          }
-          store_unit(chPE, row, half * 4 + u, v);
-        }
-        if (P.need_t) {
-#pragma unroll
-          for (int u = 0; u < 3; ++u) {
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = xr[P.c_t + (half * 3 + u) * 8 + i];
-            store_unit(chT, row, half * 3 + u, v);
-          }
-        }
-        if (P.need_dir && half == 1) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = (u * 8 + i >= 27) ? 0.f : xr[P.c_dir + u * 8 + i];
-            store_unit(chD, row, u, v);
-          }
-        }
-      }
+      encode_tile_row(P, sA, row, half, p, valid);
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(BAR_EXTRA_FULL));
+      if (lane == 0) arrive_leader(BAR_EXTRA_FULL);
 
       float zrow = 0.f;
       if (P.pts.zs && P.x_emb == nullptr) zrow = P.pts.zs[p];
@@ -453,11 +522,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
       for (int s = 0; s < n_steps; ++s, ++gstep) {
         const Step& st = P.steps[s];
         const uint32_t slot = gstep & 1u, use = gstep >> 1;
+        const uint32_t bslot = gstep & (kBiasSlots - 1);
+        mbar_wait(bar(BAR_BIAS_FULL + bslot), (gstep / kBiasSlots) & 1u);   // landed long ago: issued a step ahead
         mbar_wait(bar(BAR_ACC_FULL + slot), use & 1u);
         tc_fence_after_sync();
         const uint32_t t_acc = tmem_base + lane_field + slot * 256u;
-        const uint32_t bslot = gstep & (kBiasSlots - 1);
-        mbar_wait(bar(BAR_BIAS_FULL + bslot), (gstep >> 2) & 1u);   // landed long ago: issued a step ahead
         const uint32_t s_bias = sBias + bslot * 1024u;
         if (st.epi != EPI_HEAD) {
           const bool relu = st.epi == EPI_RELU_HID;
@@ -477,7 +546,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
               // accumulator fully drained into registers: hand the TMEM slot back to the MMA warp
               tc_fence_before_sync();
               __syncwarp();
-              if (lane == 0) mbar_arrive(bar(BAR_ACC_EMPTY + slot));
+              if (lane == 0) {
+                arrive_leader(BAR_ACC_EMPTY + slot);
+                mbar_arrive(bar(BAR_BIAS_EMPTY + bslot));      // bias row is in registers too
+              }
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -493,7 +565,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(BAR_HID_FULL + c));
+            if (lane == 0) arrive_leader(BAR_HID_FULL + c);
           }
         } else {
           if (half == 0) {
@@ -518,18 +590,23 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
           }
           tc_fence_before_sync();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar(BAR_ACC_EMPTY + slot));
+          if (lane == 0) {
+            arrive_leader(BAR_ACC_EMPTY + slot);
+            mbar_arrive(bar(BAR_BIAS_EMPTY + bslot));
+          }
         }
       }
     }
   }
 
   tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (kCtas == 1) __syncthreads();
+  else cluster_sync_all();              // no CTA of the pair may exit while its partner can still signal it
   if (warp == kEpiWarps + 1) {
     tc_fence_after_sync();
     __syncwarp();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (kCtas == 1) tmem_dealloc(tmem_base, 512);
+    else tmem_dealloc_pair(tmem_base, 512);
   }
 }
 
@@ -726,13 +803,41 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
   P.out_ld = out_ld;
   P.n_tiles = (int)cdiv64(B, kTileM);
   P.flow_scale = desc->flow_scale;
-  NSFF_CUDA_TRY(cudaFuncSetAttribute(field_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal));
-  int grid = P.n_tiles < sms ? P.n_tiles : sms;
+  // CTA pairs (cta_group::2) are the default; NSFF_TC_CTAS=1 selects the single-CTA kernel (A/B experiments).
+  int ctas = 2;
+  if (const char* e = getenv("NSFF_TC_CTAS")) ctas = atoi(e) == 1 ? 1 : 2;
+  int max_ctas = sms;
   if (const char* cap = getenv("NSFF_MAX_CTAS")) {          // experiment knob: fewer resident CTAs
     int c = atoi(cap);
-    if (c > 0 && c < grid) grid = c;
+    if (c > 0 && c < max_ctas) max_ctas = c;
   }
-  field_forward_kernel<<<grid, kThreads, kSmemTotal, (cudaStream_t)stream>>>(P);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ctas == 1) {
+    NSFF_CUDA_TRY(cudaFuncSetAttribute(field_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Cfg<1>::kSmemTotal));
+    const int grid = P.n_tiles < max_ctas ? P.n_tiles : max_ctas;
+    field_forward_kernel<1><<<grid, kThreads, Cfg<1>::kSmemTotal, st>>>(P);
+  } else {
+    NSFF_CUDA_TRY(cudaFuncSetAttribute(field_forward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Cfg<2>::kSmemTotal));
+    const int n_pairs = (P.n_tiles + 1) / 2;
+    int clusters = max_ctas / 2;
+    if (clusters < 1) clusters = 1;
+    if (n_pairs < clusters) clusters = n_pairs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg<2>::kSmemTotal;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    NSFF_CUDA_TRY(cudaLaunchKernelEx(&cfg, field_forward_kernel<2>, P));
+  }
   return after_launch();
 }
 
