@@ -56,7 +56,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.index, self.samples, self.reasons, self.max_mhz, self.power = index, [], set(), None, []
         self._stop_evt = threading.Event()
 
     def run(self):
@@ -72,6 +72,7 @@ class ClockSampler(threading.Thread):
                      nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
             while not self._stop_evt.is_set():
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 for bit, nm in names.items():
                     if r & bit:
@@ -84,7 +85,10 @@ class ClockSampler(threading.Thread):
         self._stop_evt.set()
         self.join(timeout=2)
         med = statistics.median(self.samples) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "sm_mhz_min": min(self.samples) if self.samples else None,
+                "power_w_median": statistics.median(self.power) if self.power else None,
+                "power_w_max": max(self.power) if self.power else None}
 
 
 def _cpu_setup(n_rays):

@@ -21,6 +21,7 @@
 // (one mbarrier per chunk), so the tensor pipe only idles for the first 64-column slice of each
 // epilogue; the other accumulator absorbs layer l+1 while layer l is still being drained.
 #include <cuda_bf16.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -152,7 +153,8 @@ __global__ void pack_kernel(const PackJobs* __restrict__ jobs_dev, uint8_t* __re
 // forward kernel
 // ---------------------------------------------------------------------------------------------
 constexpr int kTileM = 128;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;        // 4 TMEM lane quadrants x 4 column parts: enough warps per SMSP to hide
+                                     // the TMEM-load / st.shared / proxy-fence latencies of the epilogue
 constexpr int kThreads = (kEpiWarps + 2) * 32;
 constexpr uint32_t kChunkBytes = 128 * 128;          // 128 rows x 64 bf16
 constexpr uint32_t kSmemA = 7 * kChunkBytes;         // 4 hidden + PE + T + DIR
@@ -177,6 +179,8 @@ struct Cfg {
 struct Step {
   uint32_t w_off;
   uint32_t bias_off;
+  uint32_t chunk_pack;      // 4 bits per K-chunk: A-operand chunk id      (hot-loop copies of chunk[]/kcnt[])
+  uint32_t kcnt_pack;       // 4 bits per K-chunk: number of K=16 MMAs
   uint16_t n;
   uint8_t nchunks;
   uint8_t epi;
@@ -198,15 +202,34 @@ struct FwdParams {
   int32_t n_tiles;
   int32_t need_t, need_dir;
   float flow_scale;
+  unsigned long long* dbg;  // NSFF_TIMELINE builds only: (tag, clock64) event log of CTA 0
+  int32_t exp_flags;        // NSFF_EXPERIMENT builds only: 1 = MMA ignores hidden-chunk readiness (wrong results),
+                            // 2 = MMA ignores accumulator-drained, 4 = MMA ignores weight readiness
   Step steps[kMaxSteps];
 };
 
+// Timeline instrumentation (compiled in only with -DNSFF_TIMELINE; see tools/timeline.py).
+#ifdef NSFF_TIMELINE
+constexpr int kDbgPerRole = 8192;
+#define NSFF_TL_DECL(role) unsigned long long* tl_ptr = (P.dbg && blockIdx.x == 0) ? P.dbg + (role) * 2 * kDbgPerRole : nullptr; int tl_n = 0
+#define NSFF_TL(tag)                                                          \
+  do {                                                                        \
+    if (tl_ptr && tl_n < kDbgPerRole && lane == 0) {                          \
+      tl_ptr[2 * tl_n] = (unsigned long long)(tag);                           \
+      tl_ptr[2 * tl_n + 1] = (unsigned long long)clock64();                   \
+      ++tl_n;                                                                 \
+    }                                                                         \
+  } while (0)
+#else
+#define NSFF_TL_DECL(role) do {} while (0)
+#define NSFF_TL(tag) do {} while (0)
+#endif
+
 // barrier slots (8 bytes each) inside the barrier region
 enum {
-  BAR_W_FULL = 0,                           // [kMaxStages] own weight half landed (tx)
+  BAR_W_FULL = 0,                           // [kMaxStages] weight stage landed (tx; + partner relay in pair mode)
   BAR_W_EMPTY = BAR_W_FULL + kMaxStages,    // [kMaxStages] MMAs that read the stage completed (commit)
-  BAR_W_PEER = BAR_W_EMPTY + kMaxStages,    // [kMaxStages] pair mode, leader: the peer CTA's half landed
-  BAR_HID_FULL = BAR_W_PEER + kMaxStages,   // [4]  hidden chunk written (by all CTAs of the group)
+  BAR_HID_FULL = BAR_W_EMPTY + kMaxStages,  // [4]  hidden chunk written (by all CTAs of the group)
   BAR_EXTRA_FULL = BAR_HID_FULL + 4,        // [1]  prologue chunks written
   BAR_ACC_FULL = BAR_EXTRA_FULL + 1,        // [2]  accumulator complete (commit)
   BAR_ACC_EMPTY = BAR_ACC_FULL + 2,         // [2]  accumulator drained
@@ -226,6 +249,17 @@ __device__ __forceinline__ void store_unit(uint32_t chunk_base, int row, int uni
   st_shared_v4(addr, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
                pack_bf16x2(f[6], f[7]));
 }
+// Same for a row whose swizzle-row offset is precomputed; ReLU (if kRelu) rides on the bf16 conversion.
+template <bool kRelu>
+__device__ __forceinline__ void store_unit_at(uint32_t row_base, int rsw, int unit, const float (&f)[8]) {
+  const uint32_t addr = row_base + (uint32_t)(((unit ^ rsw) & 7) << 4);
+  if constexpr (kRelu)
+    st_shared_v4(addr, pack_bf16x2_relu(f[0], f[1]), pack_bf16x2_relu(f[2], f[3]), pack_bf16x2_relu(f[4], f[5]),
+                 pack_bf16x2_relu(f[6], f[7]));
+  else
+    st_shared_v4(addr, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                 pack_bf16x2(f[6], f[7]));
+}
 
 // column c (0..63) of the xyz encoding row [x, sin(2^0 x), cos(2^0 x), ...] (nerf.py:17-30); col 63 = pad
 template <int kNFreq>
@@ -237,8 +271,33 @@ __device__ __forceinline__ float pe_col(int c, const float (&base)[3], const flo
   return r < 3 ? sn[f - f0][r] : cs[f - f0][r - 3];
 }
 
+// PE(xyz) columns [16*kPart, 16*kPart+16) of one row: the frequencies those columns touch are
+// part 0: 2^0..2^2, part 1: 2^2..2^4, part 2: 2^4..2^7, part 3: 2^7..2^9 (+ the zero pad column 63).
+template <int kPart>
+__device__ __forceinline__ void encode_pe_part(uint32_t chPE, int row, const float (&base)[3]) {
+  constexpr int f0 = kPart == 0 ? 0 : kPart == 1 ? 2 : kPart == 2 ? 4 : 7;
+  constexpr int nf = kPart == 2 ? 4 : 3;
+  float sn[nf][3], cs[nf][3];
+#pragma unroll
+  for (int f = 0; f < nf; ++f)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sincosf(__fmul_rn((float)(1 << (f0 + f)), base[c]), &sn[f][c], &cs[f][c]);
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = (kPart * 2 + u) * 8 + i;
+      v[i] = c == 63 ? 0.f : pe_col<nf>(c, base, sn, cs, f0);
+    }
+    store_unit(chPE, row, kPart * 2 + u, v);
+  }
+}
+
 // Prologue of one tile: encode the inputs of `row` into the PE / time-code / PE(dir) chunks (bf16, swizzled).
-__device__ __forceinline__ void encode_tile_row(const FwdParams& P, uint32_t sA, int row, int half, int64_t p,
+// Four threads (part 0..3) share a row: each writes 2 of the 8 PE units; parts 0-2 also write 2 of the 6
+// time-code units, part 3 the 4 PE(dir) units.
+__device__ __forceinline__ void encode_tile_row(const FwdParams& P, uint32_t sA, int row, int part, int64_t p,
                                                 bool valid) {
   const uint32_t chPE = sA + CH_PE * kChunkBytes, chT = sA + CH_T * kChunkBytes, chD = sA + CH_DIR * kChunkBytes;
   if (P.x_emb == nullptr) {
@@ -250,53 +309,29 @@ __device__ __forceinline__ void encode_tile_row(const FwdParams& P, uint32_t sA,
       if (P.pts.offset) v = __fadd_rn(v, P.pts.offset[p * P.pts.offset_ld + c]);
       base[c] = v;
     }
-    if (half == 0 && valid && P.pts.xyz_out) {
+    if (part == 0 && valid && P.pts.xyz_out) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) P.pts.xyz_out[p * 3 + c] = base[c];
     }
-    // PE(xyz): half 0 -> columns 0..31 (freqs 0..4), half 1 -> columns 32..63 (freqs 4..9)
-    if (half == 0) {
-      float sn[5][3], cs[5][3];
-#pragma unroll
-      for (int f = 0; f < 5; ++f)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) sincosf(__fmul_rn((float)(1 << f), base[c]), &sn[f][c], &cs[f][c]);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = pe_col<5>(u * 8 + i, base, sn, cs, 0);
-        store_unit(chPE, row, u, v);
-      }
-    } else {
-      float sn[6][3], cs[6][3];
-#pragma unroll
-      for (int f = 0; f < 6; ++f)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) sincosf(__fmul_rn((float)(16 << f), base[c]), &sn[f][c], &cs[f][c]);
-#pragma unroll
-      for (int u = 4; u < 8; ++u) {
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = (u * 8 + i == 63) ? 0.f : pe_col<6>(u * 8 + i, base, sn, cs, 4);
-        store_unit(chPE, row, u, v);
-      }
-    }
-    if (P.need_t) {
+    if (part == 0) encode_pe_part<0>(chPE, row, base);
+    else if (part == 1) encode_pe_part<1>(chPE, row, base);
+    else if (part == 2) encode_pe_part<2>(chPE, row, base);
+    else encode_pe_part<3>(chPE, row, base);
+    if (P.need_t && part < 3) {
       int64_t trow = ray;
       if (P.pts.t_index) {
         trow = P.pts.t_index[ray] + P.pts.t_shift;
         trow = trow < 0 ? 0 : (trow > P.pts.max_t ? P.pts.max_t : trow);
       }
-      const float4* tp = reinterpret_cast<const float4*>(P.pts.t_table + trow * 48) + half * 6;
+      const float4* tp = reinterpret_cast<const float4*>(P.pts.t_table + trow * 48) + part * 4;
 #pragma unroll
-      for (int u = 0; u < 3; ++u) {
+      for (int u = 0; u < 2; ++u) {
         float4 a = __ldg(tp + 2 * u), b = __ldg(tp + 2 * u + 1);
         float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        store_unit(chT, row, half * 3 + u, v);
+        store_unit(chT, row, part * 2 + u, v);
       }
     }
-    if (P.need_dir && half == 1) {
+    if (P.need_dir && part == 3) {
       float d[3] = {P.pts.dirs[ray * 3 + 0], P.pts.dirs[ray * 3 + 1], P.pts.dirs[ray * 3 + 2]};
       float sn[4][3], cs[4][3];
 #pragma unroll
@@ -315,25 +350,25 @@ __device__ __forceinline__ void encode_tile_row(const FwdParams& P, uint32_t sA,
     // embedded mode: x row = [xyz63 | dir27 | a | t48] already encoded by the caller
     const float* xr = P.x_emb + p * P.x_ld;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 2; ++u) {
       float v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        int c = (half * 4 + u) * 8 + i;
+        int c = (part * 2 + u) * 8 + i;
         v[i] = c < 63 ? xr[c] : 0.f;
       }
-      store_unit(chPE, row, half * 4 + u, v);
+      store_unit(chPE, row, part * 2 + u, v);
     }
-    if (P.need_t) {
+    if (P.need_t && part < 3) {
 #pragma unroll
-      for (int u = 0; u < 3; ++u) {
+      for (int u = 0; u < 2; ++u) {
         float v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = xr[P.c_t + (half * 3 + u) * 8 + i];
-        store_unit(chT, row, half * 3 + u, v);
+        for (int i = 0; i < 8; ++i) v[i] = xr[P.c_t + (part * 2 + u) * 8 + i];
+        store_unit(chT, row, part * 2 + u, v);
       }
     }
-    if (P.need_dir && half == 1) {
+    if (P.need_dir && part == 3) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         float v[8];
@@ -372,9 +407,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(bar(BAR_W_FULL + i), 1);
+      // pair mode, leader: own half (producer arrive + tx) AND the partner's relay arrive complete a stage
+      mbar_init(bar(BAR_W_FULL + i), (kCtas == 2 && leader) ? 2 : 1);
       mbar_init(bar(BAR_W_EMPTY + i), 1);
-      mbar_init(bar(BAR_W_PEER + i), 1);
     }
     for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_HID_FULL + i), kEpiWarps * kCtas);
     mbar_init(bar(BAR_EXTRA_FULL), kEpiWarps * kCtas);
@@ -403,7 +438,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
 
   if (warp == kEpiWarps) {
     // ===================== weight + bias producer (whole warp walks the program, one elected lane copies) ====
-    uint32_t it = 0, gstep = 0;
+    uint32_t stage = 0, epar = 1, gstep = 0;       // epar: parity that means "stage is free" (fresh barrier: 1)
+    NSFF_TL_DECL(0);
     for (int unit = group; unit < n_units; unit += n_groups) {
       for (int s = 0; s < n_steps; ++s, ++gstep) {
         const Step& st = P.steps[s];
@@ -418,102 +454,141 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
           }
           __syncwarp();
         }
-        for (int kc = 0; kc < st.nchunks; ++kc, ++it) {
-          const uint32_t stage = it % kStages, use = it / kStages;
-          mbar_wait(bar(BAR_W_EMPTY + stage), (use & 1u) ^ 1u);
+        const uint8_t* src = P.pack + st.w_off + cta_rank * bytes;
+        const int nchunks = st.nchunks;
+        for (int kc = 0; kc < nchunks; ++kc, src += block_bytes) {
+          mbar_wait(bar(BAR_W_EMPTY + stage), epar);
+          NSFF_TL((gstep << 8) | (kc << 4) | 1);            // producer: stage free, issuing copy
           if (elect_one()) {
             mbar_arrive_expect_tx(bar(BAR_W_FULL + stage), bytes);
-            bulk_g2s(sB + stage * kStageBytes, P.pack + st.w_off + (uint32_t)kc * block_bytes + cta_rank * bytes, bytes,
-                     bar(BAR_W_FULL + stage));
+            bulk_g2s(sB + stage * kStageBytes, src, bytes, bar(BAR_W_FULL + stage));
           }
-          __syncwarp();
+          if (++stage == (uint32_t)kStages) stage = 0, epar ^= 1u;
         }
       }
     }
   } else if (warp == kEpiWarps + 1) {
     if (leader) {
       // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
-      auto wait_group = [&](int i, uint32_t parity) {      // barriers both CTAs of a pair arrive on
-        if constexpr (kCtas == 1) mbar_wait(bar(i), parity);
-        else mbar_wait(bar(i), parity);
-      };
-      uint32_t it = 0, gstep = 0, hid_gen = 0, unit_iter = 0;
-      for (int unit = group; unit < n_units; unit += n_groups, ++unit_iter) {
-        wait_group(BAR_EXTRA_FULL, unit_iter & 1u);
-        for (int s = 0; s < n_steps; ++s, ++gstep) {
-          const Step& st = P.steps[s];
-          const uint32_t slot = gstep & 1u, use = gstep >> 1;
-          wait_group(BAR_ACC_EMPTY + slot, (use & 1u) ^ 1u);
-          const uint32_t d_tmem = tmem_base + slot * 256u;
-          const uint32_t idesc = make_idesc_bf16(kTileM * kCtas, st.n);
-          const int nchunks = st.nchunks;
-          const uint32_t hid_parity = (hid_gen - 1u) & 1u;
-          for (int kc = 0; kc < nchunks; ++kc, ++it) {
-            const uint32_t ch = st.chunk[kc];
-            const int kcnt = st.kcnt[kc];
-            if (ch < 4) wait_group(BAR_HID_FULL + ch, hid_parity);
-            const uint32_t stage = it % kStages, wuse = it / kStages;
-            mbar_wait(bar(BAR_W_FULL + stage), wuse & 1u);
-            if constexpr (kCtas == 2) mbar_wait(bar(BAR_W_PEER + stage), wuse & 1u);
-            tc_fence_after_sync();
-            if (elect_one()) {
-              const uint64_t a0 = make_desc_k128(sA + ch * kChunkBytes);
-              const uint64_t b0 = make_desc_k128(sB + stage * kStageBytes);
+      // The loop body is the serial critical path of the kernel (one instruction stream feeds the tensor pipe), so it
+      // is kept to a few dozen instructions per K-chunk: running stage/parity counters, per-step packed chunk
+      // tables, both barrier probes issued back to back, descriptors built from precomputed 32-bit halves.
+      const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);          // SBO | version | SWIZZLE_128B
+      const uint32_t a_lo0 = ((sA & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t b_lo0 = ((sB & 0x3FFFFu) >> 4) | (1u << 16);
+      auto desc = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; };
+      // One elected lane runs the whole role (the other 31 park at the reconvergence point): no per-chunk
+      // elect / reconverge, and ptxas knows the tcgen05 operands are uniform.
+      if (elect_one()) {
+        uint32_t stage = 0, wpar = 0, gstep = 0, hid_gen = 0, unit_iter = 0;
+        NSFF_TL_DECL(1);
+        for (int unit = group; unit < n_units; unit += n_groups, ++unit_iter) {
+          mbar_wait(bar(BAR_EXTRA_FULL), unit_iter & 1u);
+          NSFF_TL((gstep << 8) | 15);                          // mma: prologue chunks ready
+          for (int s = 0; s < n_steps; ++s, ++gstep) {
+            const Step& st = P.steps[s];
+            uint32_t chunks = st.chunk_pack, kcnts = st.kcnt_pack;
+            const int nchunks = st.nchunks;
+            const uint32_t slot = gstep & 1u;
+            const uint32_t d_tmem = tmem_base + slot * 256u;
+            const uint32_t idesc = make_idesc_bf16(kTileM * kCtas, st.n);
+            const uint32_t hid_parity = (hid_gen - 1u) & 1u;
+            const uint32_t acc_full_bar = bar(BAR_ACC_FULL + slot);
+            // probes of K-chunk kc+1 are issued before the MMAs of chunk kc so that their round trip to the
+            // barrier unit overlaps the issue work; `*_ok` carry the result into the next iteration
+            uint32_t ch = chunks & 15u;
+#ifdef NSFF_EXPERIMENT
+            const bool x_hid = P.exp_flags & 1, x_acc = P.exp_flags & 2, x_w = P.exp_flags & 4;
+#else
+            constexpr bool x_hid = false, x_acc = false, x_w = false;
+#endif
+            bool hid_ok = x_hid || ch >= 4 || mbar_try_wait(bar(BAR_HID_FULL + ch), hid_parity);
+            bool w_ok = x_w || mbar_try_wait(bar(BAR_W_FULL + stage), wpar);
+            if (!x_acc) mbar_wait(bar(BAR_ACC_EMPTY + slot), ((gstep >> 1) & 1u) ^ 1u);
+            NSFF_TL((gstep << 8) | 14);                        // mma: accumulator slot free
+            for (int kc = 0; kc < nchunks; ++kc) {
+              const uint32_t kcnt = kcnts & 15u;
+              chunks >>= 4;
+              kcnts >>= 4;
+              NSFF_TL((gstep << 8) | (kc << 4) | 2);         // mma: chunk loop top
+              if (!hid_ok) mbar_wait(bar(BAR_HID_FULL + ch), hid_parity);
+              NSFF_TL((gstep << 8) | (kc << 4) | 3);         // mma: A chunk ready
+              if (!w_ok) mbar_wait(bar(BAR_W_FULL + stage), wpar);
+              NSFF_TL((gstep << 8) | (kc << 4) | 4);         // mma: weights ready -> issue
+              const uint32_t a_lo = a_lo0 + ch * (kChunkBytes >> 4);
+              const uint32_t b_lo = b_lo0 + stage * (kStageBytes >> 4);
+              const uint32_t empty_bar = bar(BAR_W_EMPTY + stage);
+              if (++stage == (uint32_t)kStages) stage = 0, wpar ^= 1u;
+              if (kc + 1 < nchunks) {                          // early probes for the next K-chunk
+                ch = chunks & 15u;
+                hid_ok = x_hid || ch >= 4 || mbar_try_wait(bar(BAR_HID_FULL + ch), hid_parity);
+                w_ok = x_w || mbar_try_wait(bar(BAR_W_FULL + stage), wpar);
+              }
+              tc_fence_after_sync();
               const uint32_t acc0 = kc > 0 ? 1u : 0u;
               // +32 B per K=16 step inside the 128 B swizzle row (descriptor address unit = 16 B)
               if constexpr (kCtas == 1) {
-                mma_bf16_ss(d_tmem, a0, b0, idesc, acc0);
-                mma_bf16_ss(d_tmem, a0 + 2, b0 + 2, idesc, 1u);
-                if (kcnt > 2) mma_bf16_ss(d_tmem, a0 + 4, b0 + 4, idesc, 1u);
-                if (kcnt > 3) mma_bf16_ss(d_tmem, a0 + 6, b0 + 6, idesc, 1u);
-                mma_commit(bar(BAR_W_EMPTY + stage));
-                if (kc == nchunks - 1) mma_commit(bar(BAR_ACC_FULL + slot));
+                mma_bf16_ss(d_tmem, desc(a_lo), desc(b_lo), idesc, acc0);
+                mma_bf16_ss(d_tmem, desc(a_lo + 2), desc(b_lo + 2), idesc, 1u);
+                if (kcnt > 2) mma_bf16_ss(d_tmem, desc(a_lo + 4), desc(b_lo + 4), idesc, 1u);
+                if (kcnt > 3) mma_bf16_ss(d_tmem, desc(a_lo + 6), desc(b_lo + 6), idesc, 1u);
+                mma_commit(empty_bar);
+                if (kc == nchunks - 1) mma_commit(acc_full_bar);
               } else {
-                mma_bf16_ss_pair(d_tmem, a0, b0, idesc, acc0);
-                mma_bf16_ss_pair(d_tmem, a0 + 2, b0 + 2, idesc, 1u);
-                if (kcnt > 2) mma_bf16_ss_pair(d_tmem, a0 + 4, b0 + 4, idesc, 1u);
-                if (kcnt > 3) mma_bf16_ss_pair(d_tmem, a0 + 6, b0 + 6, idesc, 1u);
-                mma_commit_pair_mc(bar(BAR_W_EMPTY + stage), 3);       // frees the stage in BOTH CTAs
-                if (kc == nchunks - 1) mma_commit_pair_mc(bar(BAR_ACC_FULL + slot), 3);
+                mma_bf16_ss_pair(d_tmem, desc(a_lo), desc(b_lo), idesc, acc0);
+                mma_bf16_ss_pair(d_tmem, desc(a_lo + 2), desc(b_lo + 2), idesc, 1u);
+                if (kcnt > 2) mma_bf16_ss_pair(d_tmem, desc(a_lo + 4), desc(b_lo + 4), idesc, 1u);
+                if (kcnt > 3) mma_bf16_ss_pair(d_tmem, desc(a_lo + 6), desc(b_lo + 6), idesc, 1u);
+                mma_commit_pair_mc(empty_bar, 3);               // frees the stage in BOTH CTAs
+                if (kc == nchunks - 1) mma_commit_pair_mc(acc_full_bar, 3);
               }
+              NSFF_TL((gstep << 8) | (kc << 4) | 11);        // mma: committed
             }
-            __syncwarp();
+            if (st.epi != EPI_HEAD) ++hid_gen;
           }
-          if (st.epi != EPI_HEAD) ++hid_gen;
         }
       }
+      __syncwarp();
     } else {
       // ===================== pair mode, peer CTA: relay "my weight half has landed" to the leader ==============
-      uint32_t it = 0;
+      uint32_t stage = 0, wpar = 0;
+      const uint32_t leader_w_full = mapa_cluster(bar(BAR_W_FULL), 0);
       for (int unit = group; unit < n_units; unit += n_groups) {
         for (int s = 0; s < n_steps; ++s) {
           const int nchunks = P.steps[s].nchunks;
-          for (int kc = 0; kc < nchunks; ++kc, ++it) {
-            const uint32_t stage = it % kStages, wuse = it / kStages;
-            mbar_wait(bar(BAR_W_FULL + stage), wuse & 1u);
-            if (lane == 0) mbar_arrive_cluster(mapa_cluster(bar(BAR_W_PEER + stage), 0));
-            __syncwarp();
+          for (int kc = 0; kc < nchunks; ++kc) {
+            mbar_wait(bar(BAR_W_FULL + stage), wpar);
+            if (lane == 0) mbar_arrive_cluster(leader_w_full + stage * 8u);
+            if (++stage == (uint32_t)kStages) stage = 0, wpar ^= 1u;
           }
         }
       }
     }
   } else {
     // ===================== prologue + epilogue warps =====================
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, part = warp >> 2;      // TMEM lane quadrant, 16-column part of every 64-column slice
     const int row = q * 32 + lane;
     const uint32_t lane_field = (uint32_t)(q * 32) << 16;
+    const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+    const int rsw = row & 7;
     uint32_t gstep = 0;
+#ifdef NSFF_TIMELINE
+    unsigned long long* tl_ptr = (P.dbg && blockIdx.x == 0 && warp == 0) ? P.dbg + 2 * 2 * kDbgPerRole : nullptr;
+    int tl_n = 0;
+#endif
     for (int unit = group; unit < n_units; unit += n_groups) {
+      NSFF_TL((gstep << 8) | 13);                            // epi: tile start (prologue begins)
       const int tile = unit * kCtas + (int)cta_rank;
       const int64_t p_raw = (int64_t)tile * kTileM + row;
       const bool valid = p_raw < P.pts.B;
       const int64_t p = valid ? p_raw : P.pts.B - 1;
       // ---------------- prologue: encode this tile's inputs into the extra chunks ----------------
       // (all MMAs of the previous tile have completed: its last acc_full was waited on below)
-      encode_tile_row(P, sA, row, half, p, valid);
+      encode_tile_row(P, sA, row, part, p, valid);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) arrive_leader(BAR_EXTRA_FULL);
+      NSFF_TL((gstep << 8) | 12);                            // epi: prologue published
 
       float zrow = 0.f;
       if (P.pts.zs && P.x_emb == nullptr) zrow = P.pts.zs[p];
@@ -524,51 +599,62 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
         const uint32_t slot = gstep & 1u, use = gstep >> 1;
         const uint32_t bslot = gstep & (kBiasSlots - 1);
         mbar_wait(bar(BAR_BIAS_FULL + bslot), (gstep / kBiasSlots) & 1u);   // landed long ago: issued a step ahead
-        mbar_wait(bar(BAR_ACC_FULL + slot), use & 1u);
-        tc_fence_after_sync();
-        const uint32_t t_acc = tmem_base + lane_field + slot * 256u;
         const uint32_t s_bias = sBias + bslot * 1024u;
+        const uint32_t t_acc = tmem_base + lane_field + slot * 256u;
         if (st.epi != EPI_HEAD) {
+          // bias of the first slice is fetched before the accumulator is awaited: it is off the critical path
+          float4 b[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) lds_v4(s_bias + (uint32_t)((part * 16 + i * 4) * 4), b[i]);
+          NSFF_TL((gstep << 8) | 5);                           // epi: waiting for the accumulator
+          mbar_wait(bar(BAR_ACC_FULL + slot), use & 1u);
+          NSFF_TL((gstep << 8) | 6);                           // epi: accumulator complete
+          tc_fence_after_sync();
           const bool relu = st.epi == EPI_RELU_HID;
           // software pipeline over the four 64-column slices: TMEM load of slice c+1 is in flight while slice c
           // is biased / activated / packed / stored.
-          uint32_t v[2][32];
-          tmem_ld32(t_acc + (uint32_t)(half * 32), v[0]);
+          uint32_t v[2][16];
+          tmem_ld16(t_acc + (uint32_t)(part * 16), v[0]);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            float4 b[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) lds_v4(s_bias + (uint32_t)((c * 64 + half * 32 + i * 4) * 4), b[i]);
             tmem_ld_wait();
             if (c < 3) {
-              tmem_ld32(t_acc + (uint32_t)((c + 1) * 64 + half * 32), v[(c + 1) & 1]);
+              tmem_ld16(t_acc + (uint32_t)((c + 1) * 64 + part * 16), v[(c + 1) & 1]);
             } else {
               // accumulator fully drained into registers: hand the TMEM slot back to the MMA warp
               tc_fence_before_sync();
               __syncwarp();
-              if (lane == 0) {
-                arrive_leader(BAR_ACC_EMPTY + slot);
-                mbar_arrive(bar(BAR_BIAS_EMPTY + bslot));      // bias row is in registers too
-              }
+              if (lane == 0) arrive_leader(BAR_ACC_EMPTY + slot);
             }
+            const uint32_t row_base = sA + (uint32_t)c * kChunkBytes + row_off;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 2; ++u) {
               float f[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const float4 bb = b[u * 2 + (i >> 2)];
                 const float bv = (i & 3) == 0 ? bb.x : (i & 3) == 1 ? bb.y : (i & 3) == 2 ? bb.z : bb.w;
-                float x = __uint_as_float(v[c & 1][u * 8 + i]) + bv;
-                f[i] = relu ? fmaxf(x, 0.f) : x;
+                f[i] = __uint_as_float(v[c & 1][u * 8 + i]) + bv;
               }
-              store_unit(sA + (uint32_t)c * kChunkBytes, row, half * 4 + u, f);
+              if (relu) store_unit_at<true>(row_base, rsw, part * 2 + u, f);
+              else store_unit_at<false>(row_base, rsw, part * 2 + u, f);
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) arrive_leader(BAR_HID_FULL + c);
+            NSFF_TL((gstep << 8) | (c << 4) | 7);            // epi: hidden chunk c published
+            if (c < 3) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) lds_v4(s_bias + (uint32_t)(((c + 1) * 64 + part * 16 + i * 4) * 4), b[i]);
+            } else {
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar(BAR_BIAS_EMPTY + bslot));      // bias row fully consumed
+            }
           }
         } else {
-          if (half == 0) {
+          mbar_wait(bar(BAR_ACC_FULL + slot), use & 1u);
+          tc_fence_after_sync();
+          if (part == 0) {
             uint32_t v[16];
             tmem_ld16(t_acc, v);
             tmem_ld_wait();
@@ -727,7 +813,11 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
     s.n = (uint16_t)pl.n;
     s.nchunks = (uint8_t)pl.nchunks;
     s.epi = epi;
-    for (int i = 0; i < kMaxChunks; ++i) s.chunk[i] = pl.chunk[i], s.kcnt[i] = pl.kcnt[i];
+    s.chunk_pack = s.kcnt_pack = 0;
+    for (int i = 0; i < kMaxChunks; ++i) {
+      s.chunk[i] = pl.chunk[i], s.kcnt[i] = pl.kcnt[i];
+      if (i < pl.nchunks) s.chunk_pack |= (uint32_t)pl.chunk[i] << (4 * i), s.kcnt_pack |= (uint32_t)pl.kcnt[i] << (4 * i);
+    }
     for (int i = 0; i < 16; ++i) s.head_dst[i] = -1, s.head_act[i] = HA_NONE;
     return s;
   };
@@ -812,6 +902,19 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
     if (c > 0 && c < max_ctas) max_ctas = c;
   }
   cudaStream_t st = (cudaStream_t)stream;
+#ifdef NSFF_EXPERIMENT
+  if (const char* xf = getenv("NSFF_EXP_FLAGS")) P.exp_flags = atoi(xf);
+#endif
+#ifdef NSFF_TIMELINE
+  const char* tl_path = getenv("NSFF_TIMELINE_OUT");
+  unsigned long long* tl_dev = nullptr;
+  const size_t tl_bytes = (size_t)3 * 2 * kDbgPerRole * sizeof(unsigned long long);
+  if (tl_path) {
+    NSFF_CUDA_TRY(cudaMalloc(&tl_dev, tl_bytes));
+    NSFF_CUDA_TRY(cudaMemsetAsync(tl_dev, 0, tl_bytes, st));
+    P.dbg = tl_dev;
+  }
+#endif
   if (ctas == 1) {
     NSFF_CUDA_TRY(cudaFuncSetAttribute(field_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)Cfg<1>::kSmemTotal));
@@ -838,6 +941,22 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
     cfg.numAttrs = 1;
     NSFF_CUDA_TRY(cudaLaunchKernelEx(&cfg, field_forward_kernel<2>, P));
   }
+#ifdef NSFF_TIMELINE
+  if (tl_dev) {
+    static int tl_seq = 0;
+    unsigned long long* host = (unsigned long long*)malloc(tl_bytes);
+    NSFF_CUDA_TRY(cudaStreamSynchronize(st));
+    NSFF_CUDA_TRY(cudaMemcpy(host, tl_dev, tl_bytes, cudaMemcpyDeviceToHost));
+    char name[512];
+    snprintf(name, sizeof(name), "%s.%d.bin", tl_path, tl_seq++);
+    if (FILE* f = fopen(name, "wb")) {
+      fwrite(host, 1, tl_bytes, f);
+      fclose(f);
+    }
+    free(host);
+    cudaFree(tl_dev);
+  }
+#endif
   return after_launch();
 }
 
