@@ -164,6 +164,32 @@ NSFF_API int nsff_field_forward_fp32(const nsff_field_desc* desc /*host*/, const
                             int64_t B_embedded, int out_mask, float* out, int32_t out_ld, float* scratch,
                             void* stream);
 
+/* Backward of NeRF.forward (fp32, CUDA cores; the reference relies on torch autograd through nn.Linear):
+ * recomputes the forward on `pts` storing every layer, then back-propagates d_out (B, C) through the heads and
+ * trunks.  Parameter gradients are ACCUMULATED (+=) into `grads` (same layout as nsff_field_params, fp32, caller
+ * zeroes them); d_pos (B,3) (gradient w.r.t. the encoded positions: used by the flow-warped passes), d_t (R,in_t)
+ * and d_a (R,in_a) (gradients w.r.t. the per-ray codes) are overwritten when non-NULL.  `out` is the forward
+ * output (needed for the sigmoid / tanh derivatives).  pts->t_index / a_index must be NULL (per-ray code rows). */
+typedef struct {
+  float* static_w[8];   float* static_b[8];
+  float* static_final_w; float* static_final_b;
+  float* static_dir_w;  float* static_dir_b;
+  float* static_sigma_w; float* static_sigma_b;
+  float* static_rgb_w;  float* static_rgb_b;
+  float* trans_w[8];    float* trans_b[8];
+  float* trans_final_w; float* trans_final_b;
+  float* trans_sigma_w; float* trans_sigma_b;
+  float* trans_rgb_w;   float* trans_rgb_b;
+  float* trans_fw_w;    float* trans_fw_b;
+  float* trans_bw_w;    float* trans_bw_b;
+} nsff_field_grads;
+
+NSFF_API size_t nsff_field_bwd_scratch_floats(const nsff_field_desc* desc /*host*/, int64_t B);
+NSFF_API int nsff_field_backward_fp32(const nsff_field_desc* desc /*host*/, const nsff_field_params* params /*host*/,
+                                      const nsff_points* pts /*host*/, int out_mask, const float* out,
+                                      const float* d_out, int32_t out_ld, const nsff_field_grads* grads /*host*/,
+                                      float* d_pos, float* d_t, float* d_a, float* scratch, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a8  eval-only camera visibility                rendering.py:190-200, ray_utils.py:127-181
  *     vis[p] = number of cameras whose image contains the world-space projection of NDC point p.
@@ -209,6 +235,25 @@ typedef struct {
 } nsff_composite_args;
 
 NSFF_API int nsff_composite(const nsff_composite_args* args /*host*/, void* stream);
+
+/* Backward of nsff_composite (autograd of rendering.py:202-298 / 98-140; the reference gets it from torch autograd,
+ * train.py:178-198).  Upstream gradients of the differentiable outputs (NULL = zero; disocc* are detached in the
+ * reference and have none) -> gradients w.r.t. raw (R,S,raw_ld), raw_fw / raw_bw (R,S,7).  The gradient w.r.t. the
+ * warped points equals the upstream gradient of xyzs_fw_bw / xyzs_bw_fw and is left to the caller.  Training
+ * composites only (static + transient); S <= 256. */
+typedef struct {
+  const float* static_sigmas; const float* transient_sigmas;
+  const float* static_weights; const float* transient_weights; const float* weights;
+  const float* xyzs_fw_bw; const float* xyzs_bw_fw;
+  const float* depth; const float* rgb; const float* transient_alpha; const float* transient_rgb;
+  const float* static_only_rgb; const float* static_only_depth;
+  const float* xyz_fine; const float* flow_fw; const float* xyz_fw_ray; const float* flow_bw; const float* xyz_bw_ray;
+  const float* rgb_fw; const float* rgb_bw;
+  float* d_raw; float* d_raw_fw; float* d_raw_bw;      /* outputs, fully overwritten */
+} nsff_composite_grads;
+
+NSFF_API int nsff_composite_backward(const nsff_composite_args* args /*host*/,
+                                     const nsff_composite_grads* grads /*host*/, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a13  sample_pdf + merge                                   models/rendering.py:10-49, 335-348

@@ -71,6 +71,18 @@ class CompositeArgs(C.Structure):
                 ("rgb_fw", C.c_void_p), ("rgb_bw", C.c_void_p), ("disocc_fw", C.c_void_p), ("disocc_bw", C.c_void_p)]
 
 
+class FieldGrads(C.Structure):        # same layout as FieldParams, but writable fp32 gradient buffers
+    _fields_ = FieldParams._fields_
+
+
+class CompositeGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("static_sigmas", "transient_sigmas", "static_weights", "transient_weights", "weights",
+                 "xyzs_fw_bw", "xyzs_bw_fw", "depth", "rgb", "transient_alpha", "transient_rgb",
+                 "static_only_rgb", "static_only_depth", "xyz_fine", "flow_fw", "xyz_fw_ray", "flow_bw", "xyz_bw_ray",
+                 "rgb_fw", "rgb_bw", "d_raw", "d_raw_fw", "d_raw_bw")]
+
+
 # name -> (restype, argtypes); also the list tests/test_cabi_symbols.py checks against the header
 PROTOTYPES = {
     "nsff_abi_version": (C.c_int, []),
@@ -92,6 +104,11 @@ PROTOTYPES = {
     "nsff_field_forward_fp32": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(FieldParams), C.POINTER(Points),
                                           C.c_void_p, C.c_int32, C.c_int64, C.c_int, C.c_void_p, C.c_int32,
                                           C.c_void_p, C.c_void_p]),
+    "nsff_field_bwd_scratch_floats": (C.c_size_t, [C.POINTER(FieldDesc), C.c_int64]),
+    "nsff_field_backward_fp32": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(FieldParams), C.POINTER(Points), C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(FieldGrads), C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsff_composite_backward": (C.c_int, [C.POINTER(CompositeArgs), C.POINTER(CompositeGrads), C.c_void_p]),
     "nsff_visibility": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.c_void_p, C.c_int, C.c_int,
                                   C.c_int, C.c_void_p, C.c_void_p]),
     "nsff_composite": (C.c_int, [C.POINTER(CompositeArgs), C.c_void_p]),

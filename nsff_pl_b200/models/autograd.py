@@ -1,0 +1,307 @@
+"""Differentiable training path of render_rays: torch.autograd.Function wrappers around the CUDA kernels.
+
+The reference gets its backward from torch autograd over ~25 nn.Linear layers and the einops/cumprod composite
+(train.py:178-198 -> rendering.py:83-300).  Here the forward is the same pair of kernels as inference
+(tcgen05 field kernel + composite) and the backward is hand-written:
+    FieldFn      -> nsff_field_backward_fp32   (recompute + dgrad/wgrad per layer, PE and code gradients)
+    CompositeFn  -> nsff_composite_backward    (reverse transmittance scans)
+Only cheap glue stays in torch (xyz + flow, embedding-table gathers), so their gradients come for free.
+"""
+import ctypes as C
+import re
+
+import torch
+
+from .. import _cabi
+
+_FIELD_OF = [  # parameter-name pattern -> (FieldGrads field stem, has layer index)
+    (re.compile(r"^static_xyz_encoding_(\d+)\.0\.(weight|bias)$"), "static", True),
+    (re.compile(r"^transient_xyz_encoding_(\d+)\.0\.(weight|bias)$"), "trans", True),
+    (re.compile(r"^static_xyz_encoding_final\.(weight|bias)$"), "static_final", False),
+    (re.compile(r"^transient_xyz_encoding_final\.(weight|bias)$"), "trans_final", False),
+    (re.compile(r"^static_dir_encoding\.0\.(weight|bias)$"), "static_dir", False),
+    (re.compile(r"^static_sigma\.(weight|bias)$"), "static_sigma", False),
+    (re.compile(r"^static_rgb\.0\.(weight|bias)$"), "static_rgb", False),
+    (re.compile(r"^transient_sigma\.(weight|bias)$"), "trans_sigma", False),
+    (re.compile(r"^transient_rgb\.0\.(weight|bias)$"), "trans_rgb", False),
+    (re.compile(r"^transient_flow_fw\.0\.(weight|bias)$"), "trans_fw", False),
+    (re.compile(r"^transient_flow_bw\.0\.(weight|bias)$"), "trans_bw", False),
+]
+
+
+def _grad_slot(name):
+    for rx, stem, indexed in _FIELD_OF:
+        m = rx.match(name)
+        if m:
+            if indexed:
+                return stem, int(m.group(1)) - 1, m.group(2)
+            return stem, None, m.group(1)
+    raise KeyError(f"parameter {name!r} has no slot in nsff_field_grads")
+
+
+def _branch_active(stem, mask):
+    if stem.startswith("static"):
+        return bool(mask & _cabi.OUT_STATIC)
+    if stem == "trans_fw":
+        return bool(mask & _cabi.OUT_FLOW_FW)
+    if stem == "trans_bw":
+        return bool(mask & _cabi.OUT_FLOW_BW)
+    return bool(mask & _cabi.OUT_TRANSIENT)
+
+
+class FieldFn(torch.autograd.Function):
+    """raw (B,C) = NeRF heads at `pos` (B,3) for per-ray codes `t_code` / `a_code` (R,*)."""
+
+    @staticmethod
+    def forward(ctx, model, mask, S, pos, t_code, a_code, dirs, zs, *params):
+        from .nerf import NeRF
+        B = pos.shape[0]
+        out = torch.empty(B, NeRF.out_channels(mask), device=pos.device, dtype=torch.float32)
+        pts = _cabi.Points()
+        pts.xyz, pts.dirs, pts.zs = pos.data_ptr(), dirs.data_ptr(), zs.data_ptr()
+        pts.t_table = None if t_code is None else t_code.data_ptr()
+        pts.a_table = None if a_code is None else a_code.data_ptr()
+        pts.B, pts.S = B, S
+        with torch.no_grad():
+            model.run_field(mask, out, pts=pts)
+        ctx.model, ctx.mask, ctx.S = model, mask, S
+        ctx.save_for_backward(pos, t_code, a_code, dirs, zs, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        model, mask, S = ctx.model, ctx.mask, ctx.S
+        pos, t_code, a_code, dirs, zs, out = ctx.saved_tensors
+        L = _cabi.lib()
+        dev = pos.device
+        B = pos.shape[0]
+        R = B // S
+        d_out = d_out.contiguous()
+        desc = model.field_desc()
+        fp, keep = model.field_params()
+        named = list(model.named_parameters())
+        fg = _cabi.FieldGrads()
+        grads = []
+        for name, p in named:
+            stem, idx, kind = _grad_slot(name)
+            if not _branch_active(stem, mask) or (stem == "static_dir" and not model.use_viewdir):
+                grads.append(None)
+                continue
+            gbuf = torch.zeros_like(p, dtype=torch.float32)
+            grads.append(gbuf)
+            field = stem + ("_w" if kind == "weight" else "_b")
+            if idx is None:
+                setattr(fg, field, gbuf.data_ptr())
+            else:
+                getattr(fg, field)[idx] = gbuf.data_ptr()
+        need_pos, need_t, need_a = ctx.needs_input_grad[3], ctx.needs_input_grad[4], ctx.needs_input_grad[5]
+        need_t = need_t and t_code is not None and bool(mask & _cabi.OUT_TRANSIENT)
+        need_a = need_a and a_code is not None and bool(mask & _cabi.OUT_STATIC)
+        d_pos = torch.empty(B, 3, device=dev) if need_pos and (mask & _cabi.OUT_TRANSIENT) else None
+        d_t = torch.empty(R, t_code.shape[1], device=dev) if need_t else None
+        d_a = torch.empty(R, a_code.shape[1], device=dev) if need_a else None
+        _cabi.select_device(pos)
+        st = _cabi.stream_ptr(dev)
+        rays_per = max(1, 32768 // S)
+        ld = out.stride(0)
+        for r0 in range(0, R, rays_per):
+            nr = min(rays_per, R - r0)
+            b0, nb = r0 * S, nr * S
+            pts = _cabi.Points()
+            pts.xyz = pos.data_ptr() + b0 * 12
+            pts.dirs = dirs.data_ptr() + r0 * 12
+            pts.zs = zs.data_ptr() + b0 * 4
+            pts.t_table = None if t_code is None else t_code.data_ptr() + r0 * t_code.shape[1] * 4
+            pts.a_table = None if a_code is None else a_code.data_ptr() + r0 * a_code.shape[1] * 4
+            pts.B, pts.S = nb, S
+            scratch = torch.empty(L.nsff_field_bwd_scratch_floats(C.byref(desc), nb), device=dev, dtype=torch.float32)
+            rc = L.nsff_field_backward_fp32(
+                C.byref(desc), C.byref(fp), C.byref(pts), mask, C.c_void_p(out.data_ptr() + b0 * ld * 4),
+                C.c_void_p(d_out.data_ptr() + b0 * ld * 4), ld, C.byref(fg),
+                None if d_pos is None else C.c_void_p(d_pos.data_ptr() + b0 * 12),
+                None if d_t is None else C.c_void_p(d_t.data_ptr() + r0 * d_t.shape[1] * 4),
+                None if d_a is None else C.c_void_p(d_a.data_ptr() + r0 * d_a.shape[1] * 4),
+                _cabi.ptr(scratch), st)
+            _cabi.check(rc, "nsff_field_backward_fp32")
+        del keep
+        return (None, None, None, d_pos, d_t, d_a, None, None, *grads)
+
+
+# output order of CompositeFn (subset chosen by the mode flags)
+_SAMPLE_OUT = ["static_sigmas", "transient_sigmas", "static_weights", "transient_weights", "weights"]
+_WARP_SAMPLE_OUT = ["xyzs_fw_bw", "xyzs_bw_fw"]
+_RAY_OUT = ["depth", "rgb", "transient_alpha", "transient_rgb", "static_only_rgb", "static_only_depth"]
+_FLOW_RAY_OUT = ["xyz_fine", "flow_fw", "xyz_fw_ray", "flow_bw", "xyz_bw_ray"]
+_WARP_RAY_OUT = ["rgb_fw", "rgb_bw"]
+_DISOCC_OUT = ["disocc_fw", "disoccs_fw", "disocc_bw", "disoccs_bw"]
+_SHAPES = {"depth": (), "transient_alpha": (), "static_only_depth": (), "disocc_fw": (1,), "disocc_bw": (1,)}
+
+
+def composite_outputs(has_flow, warp, disocc):
+    names = list(_SAMPLE_OUT)
+    if warp:
+        names += _WARP_SAMPLE_OUT
+    names += _RAY_OUT
+    if has_flow:
+        names += _FLOW_RAY_OUT
+    if warp:
+        names += _WARP_RAY_OUT
+        if disocc:
+            names += _DISOCC_OUT
+    return names
+
+
+def _composite_args(cfg, zs, xyz, noises, raw, raw_fw, raw_bw, xyz_fw, xyz_bw):
+    R, S = zs.shape
+    a = _cabi.CompositeArgs()
+    a.R, a.S = R, S
+    a.zs, a.xyz, a.raw, a.raw_ld = zs.data_ptr(), xyz.data_ptr(), raw.data_ptr(), raw.shape[-1]
+    a.has_static_rgb, a.has_transient, a.has_flow = 1, 1, int(cfg["has_flow"])
+    a.noise_std = float(cfg["noise_std"])
+    if cfg["noise_std"] > 0:
+        a.noise_static, a.noise_trans = noises[0].data_ptr(), noises[1].data_ptr()
+    if cfg["warp"]:
+        a.raw_fw, a.raw_bw, a.raw_w_ld = raw_fw.data_ptr(), raw_bw.data_ptr(), 7
+        a.xyz_fw, a.xyz_bw = xyz_fw.data_ptr(), xyz_bw.data_ptr()
+        if cfg["noise_std"] > 0:
+            a.noise_fw, a.noise_bw = noises[2].data_ptr(), noises[3].data_ptr()
+    return a
+
+
+class CompositeFn(torch.autograd.Function):
+    """All outputs of rendering.py:202-298 for the static+transient training composite."""
+
+    @staticmethod
+    def forward(ctx, cfg, zs, xyz, n_s, n_t, n_fw, n_bw, raw, raw_fw, raw_bw, xyz_fw, xyz_bw):
+        R, S = zs.shape
+        dev = zs.device
+        names = composite_outputs(cfg["has_flow"], cfg["warp"], cfg["disocc"])
+        a = _composite_args(cfg, zs, xyz, (n_s, n_t, n_fw, n_bw), raw, raw_fw, raw_bw, xyz_fw, xyz_bw)
+        outs = []
+        for nm in names:
+            if nm in _SAMPLE_OUT:
+                shape = (R, S)
+            elif nm in _WARP_SAMPLE_OUT:
+                shape = (R, S, 3)
+            elif nm in ("disoccs_fw", "disoccs_bw"):
+                shape = (R, S, 1)
+            else:
+                shape = (R,) + _SHAPES.get(nm, (3,))
+            t = torch.empty(*shape, device=dev, dtype=torch.float32)
+            setattr(a, nm, t.data_ptr())
+            outs.append(t)
+        _cabi.select_device(zs)
+        _cabi.check(_cabi.lib().nsff_composite(C.byref(a), _cabi.stream_ptr(dev)), "nsff_composite")
+        ctx.cfg, ctx.names = cfg, names
+        ctx.save_for_backward(zs, xyz, n_s, n_t, n_fw, n_bw, raw, raw_fw, raw_bw, xyz_fw, xyz_bw)
+        ctx.mark_non_differentiable(*[t for nm, t in zip(names, outs) if nm in _DISOCC_OUT])   # rendering.py:290-291
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        cfg, names = ctx.cfg, ctx.names
+        zs, xyz, n_s, n_t, n_fw, n_bw, raw, raw_fw, raw_bw, xyz_fw, xyz_bw = ctx.saved_tensors
+        dev = zs.device
+        a = _composite_args(cfg, zs, xyz, (n_s, n_t, n_fw, n_bw), raw, raw_fw, raw_bw, xyz_fw, xyz_bw)
+        g = _cabi.CompositeGrads()
+        keep = {}
+        for nm, go in zip(names, gouts):
+            if go is None or nm in _DISOCC_OUT:
+                continue
+            keep[nm] = go.contiguous()
+            setattr(g, nm, keep[nm].data_ptr())
+        d_raw = torch.empty_like(raw)
+        g.d_raw = d_raw.data_ptr()
+        d_raw_fw = d_raw_bw = None
+        if cfg["warp"]:
+            d_raw_fw, d_raw_bw = torch.empty_like(raw_fw), torch.empty_like(raw_bw)
+            g.d_raw_fw, g.d_raw_bw = d_raw_fw.data_ptr(), d_raw_bw.data_ptr()
+        _cabi.select_device(zs)
+        _cabi.check(_cabi.lib().nsff_composite_backward(C.byref(a), C.byref(g), _cabi.stream_ptr(dev)),
+                    "nsff_composite_backward")
+        return (None, None, None, None, None, None, None, d_raw, d_raw_fw, d_raw_bw,
+                keep.get("xyzs_fw_bw"), keep.get("xyzs_bw_fw"))
+
+
+def field_pass_train(results, model, embeddings, xyz, zs, dirs, ts, max_t, want_transient, flow_heads, noise_std,
+                     t_embedded, a_embedded):
+    """Differentiable counterpart of rendering._field_pass for test_time=False (same keys, same order)."""
+    from .nerf import NeRF
+    if not want_transient:
+        raise NotImplementedError("nsff_pl_b200: training a field without the transient branch is not built yet "
+                                  "(composite backward covers the static+transient composite)")
+    typ = model.typ
+    R, S = zs.shape
+    B = R * S
+    dev = zs.device
+    f32 = dict(device=dev, dtype=torch.float32)
+    params = list(model.parameters())
+    results[f"zs_{typ}"] = zs
+    results[f"xyzs_{typ}"] = xyz
+    zs_flat = zs.reshape(B)
+
+    def t_rows(shift):
+        if shift == 0 and t_embedded is not None:
+            return t_embedded
+        idx = ts if shift == 0 else (torch.clamp(ts + 1, max=max_t) if shift > 0 else torch.clamp(ts - 1, min=0))
+        return torch.nn.functional.embedding(idx, embeddings["t"].weight).contiguous()      # rendering.py:220,226,331
+
+    mask = NeRF.out_mask(False, True, True, flow_heads)
+    Cn = NeRF.out_channels(mask)
+    raw = FieldFn.apply(model, mask, S, xyz.reshape(B, 3), t_rows(0), a_embedded, dirs, zs_flat, *params).view(R, S, Cn)
+    results[f"static_rgbs_{typ}"] = raw[..., :3]
+    results[f"transient_rgbs_{typ}"] = raw[..., 4:7]
+    if flow_heads:
+        results["transient_flows_fw"] = raw[..., 8:11]
+        results["transient_flows_bw"] = raw[..., 11:14]
+
+    def noise():
+        return torch.randn(R, S, **f32)       # drawn in the reference's order (rendering.py:207,213,128)
+
+    n_s, n_t = noise(), noise()
+    warp = bool(flow_heads)
+    raw_fw = raw_bw = xyz_fw = xyz_bw = n_fw = n_bw = None
+    if warp:                                                               # rendering.py:217-232
+        xyz_fw = xyz + raw[..., 8:11]
+        raw_fw = FieldFn.apply(model, NeRF.out_mask(False, False, True, ["bw"]), S, xyz_fw.reshape(B, 3), t_rows(+1),
+                               a_embedded, dirs, zs_flat, *params).view(R, S, 7)
+        n_fw = noise()
+        xyz_bw = xyz + raw[..., 11:14]
+        raw_bw = FieldFn.apply(model, NeRF.out_mask(False, False, True, ["fw"]), S, xyz_bw.reshape(B, 3), t_rows(-1),
+                               a_embedded, dirs, zs_flat, *params).view(R, S, 7)
+        n_bw = noise()
+    cfg = dict(has_flow=bool(flow_heads), warp=warp, disocc=warp and "disocc" in flow_heads, noise_std=float(noise_std))
+    outs = dict(zip(composite_outputs(cfg["has_flow"], cfg["warp"], cfg["disocc"]),
+                    CompositeFn.apply(cfg, zs, xyz, n_s, n_t, n_fw, n_bw, raw.contiguous(),
+                                      None if raw_fw is None else raw_fw.contiguous(),
+                                      None if raw_bw is None else raw_bw.contiguous(),
+                                      None if xyz_fw is None else xyz_fw.contiguous(),
+                                      None if xyz_bw is None else xyz_bw.contiguous())))
+    # ---- same key order as rendering.py:206-295 ----
+    results[f"static_sigmas_{typ}"] = outs["static_sigmas"]
+    results[f"transient_sigmas_{typ}"] = outs["transient_sigmas"]
+    if warp:
+        results["xyzs_fw"] = xyz_fw
+        results["rgb_fw"] = outs["rgb_fw"]
+        results["xyzs_bw"] = xyz_bw
+        results["rgb_bw"] = outs["rgb_bw"]
+        results["xyzs_fw_bw"] = outs["xyzs_fw_bw"]
+        results["xyzs_bw_fw"] = outs["xyzs_bw_fw"]
+    results[f"static_weights_{typ}"] = outs["static_weights"]
+    results[f"transient_weights_{typ}"] = outs["transient_weights"]
+    results[f"weights_{typ}"] = outs["weights"]
+    results[f"depth_{typ}"] = outs["depth"]
+    results[f"rgb_{typ}"] = outs["rgb"]
+    results[f"transient_alpha_{typ}"] = outs["transient_alpha"]
+    results[f"transient_rgb_{typ}"] = outs["transient_rgb"]
+    results[f"_static_rgb_{typ}"] = outs["static_only_rgb"]
+    results[f"_static_depth_{typ}"] = outs["static_only_depth"]
+    if flow_heads:
+        results["xyz_fine"] = outs["xyz_fine"]
+        results["transient_flow_fw"] = outs["flow_fw"]
+        results["xyz_fw"] = outs["xyz_fw_ray"]
+        results["transient_flow_bw"] = outs["flow_bw"]
+        results["xyz_bw"] = outs["xyz_bw_ray"]
+        if cfg["disocc"]:
+            for k in _DISOCC_OUT:
+                results[k] = outs[k]

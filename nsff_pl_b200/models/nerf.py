@@ -219,8 +219,8 @@ class NeRF(nn.Module):
     def _guard_grad(self):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError(
-                "nsff_pl_b200: the backward kernels are not built yet - run the forward under torch.no_grad() "
-                "(or set requires_grad_(False)); no autograd graph is recorded by the CUDA path.")
+                "nsff_pl_b200: NeRF.forward on a pre-embedded row records no autograd graph - call it under "
+                "torch.no_grad(); training goes through render_rays (models/autograd.py), which is differentiable.")
 
     def run_field(self, mask, out, pts=None, x=None):
         """Launch the MLP on raw points (`pts`: _cabi.Points) or an embedded matrix `x` into `out` (B, C)."""

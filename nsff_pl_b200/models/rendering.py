@@ -223,7 +223,14 @@ def render_rays(models, embeddings, rays, ts, max_t, N_samples=64, perturb=0, no
     for m in models.values():
         if not isinstance(m, NeRF):
             raise TypeError("models must be nsff_pl_b200.models.nerf.NeRF instances")
-        m._guard_grad()
+    # differentiable path: hand-written backward kernels behind autograd.Functions (models/autograd.py)
+    grad_mode = torch.is_grad_enabled() and (
+        any(p.requires_grad for m in models.values() for p in m.parameters()) or
+        any(getattr(embeddings.get(k), "weight", None) is not None and embeddings[k].weight.requires_grad
+            for k in ("t", "a")))
+    if grad_mode and test_time:
+        raise NotImplementedError("nsff_pl_b200: test_time=True is an inference mode (the reference calls it under "
+                                  "torch.no_grad(), eval.py:81); use test_time=False to train")
     if ts is not None:
         ts = _cabi.dev_tensor(ts if ts.is_contiguous() else ts.contiguous(), "ts", torch.int64)
     st = _cabi.stream_ptr(dev)
@@ -256,21 +263,26 @@ def render_rays(models, embeddings, rays, ts, max_t, N_samples=64, perturb=0, no
             t_embedded = fixed("t_embedded")
             if t_embedded is None and ts is None:
                 raise KeyError("ts is required when the transient field is rendered")
-        _field_pass(results, model, embeddings, xyz, zs, dirs, ts, max_t, want_transient, [], test_time, noise_std,
-                    t_embedded, None, kwargs)
+        if grad_mode:
+            from .autograd import field_pass_train
+            field_pass_train(results, model, embeddings, xyz, zs, dirs, ts, max_t, want_transient, [], noise_std,
+                             t_embedded, None)
+        else:
+            _field_pass(results, model, embeddings, xyz, zs, dirs, ts, max_t, want_transient, [], test_time,
+                        noise_std, t_embedded, None, kwargs)
         # bins are the mid-points of the UN-jittered depths (rendering.py:315), one row for all rays
         lin = torch.linspace(0, 1, N_samples, **f32)
         zs_mid = (0.5 * (lin[:-1] + lin[1:])).contiguous()
         det = perturb == 0
         parts = [zs]
-        w = results["static_weights_coarse"][:, 1:-1]
+        w = results["static_weights_coarse"][:, 1:-1].detach()                 # rendering.py:336: no grad through the pdf
         zs_static = sample_pdf(zs_mid.expand(R, -1), w, N_importance, det=det)
         parts.append(zs_static)
         if test_time:
             results["static_zs_fine"] = zs_static
         if want_transient:
-            zs_trans = sample_pdf(zs_mid.expand(R, -1), results["transient_weights_coarse"][:, 1:-1], N_importance,
-                                  det=det)
+            zs_trans = sample_pdf(zs_mid.expand(R, -1), results["transient_weights_coarse"][:, 1:-1].detach(),
+                                  N_importance, det=det)
             parts.append(zs_trans)
             if test_time:
                 results["transient_zs_fine"] = zs_trans
@@ -297,6 +309,11 @@ def render_rays(models, embeddings, rays, ts, max_t, N_samples=64, perturb=0, no
             if t_embedded is None and ts is None:
                 raise KeyError("ts is required when the transient field is rendered")
     flow_heads = list(kwargs.get("output_transient_flow", [])) if want_transient else []
-    _field_pass(results, model, embeddings, xyz, zs, dirs, ts, max_t, want_transient, flow_heads, test_time,
-                noise_std, t_embedded, a_embedded, kwargs)
+    if grad_mode:
+        from .autograd import field_pass_train
+        field_pass_train(results, model, embeddings, xyz, zs, dirs, ts, max_t, want_transient, flow_heads, noise_std,
+                         t_embedded, a_embedded)
+    else:
+        _field_pass(results, model, embeddings, xyz, zs, dirs, ts, max_t, want_transient, flow_heads, test_time,
+                    noise_std, t_embedded, a_embedded, kwargs)
     return results

@@ -24,8 +24,9 @@ def declared_symbols():
 
 def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
-    assert len(syms) == 18, syms
-    for must in ("nsff_field_forward", "nsff_composite", "nsff_sample_points", "nsff_sample_pdf", "nsff_field_pack"):
+    assert len(syms) == 21, syms
+    for must in ("nsff_field_forward", "nsff_composite", "nsff_sample_points", "nsff_sample_pdf", "nsff_field_pack",
+                 "nsff_field_backward_fp32", "nsff_composite_backward"):
         assert must in syms
 
 
@@ -68,6 +69,8 @@ def test_struct_layouts_match_the_c_header(libpath, tmp_path):
         "nsff_points": ["xyz", "offset_ld", "xyz_out", "t_shift", "a_table", "zs", "B", "S"],
         "nsff_composite_args": ["R", "S", "raw_ld", "noise_std", "vis", "raw_w_ld", "xyz_fw", "static_sigmas",
                                 "disoccs_bw", "depth", "disocc_bw"],
+        "nsff_composite_grads": ["static_sigmas", "xyzs_fw_bw", "depth", "xyz_bw_ray", "rgb_bw", "d_raw", "d_raw_bw"],
+        "nsff_field_grads": ["static_w", "static_dir_b", "trans_w", "trans_bw_b"],
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "nsff_b200.h"', "int main(void){"]
     for st, fs in fields.items():
@@ -80,7 +83,8 @@ def test_struct_layouts_match_the_c_header(libpath, tmp_path):
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = dict(l.rsplit(" ", 1) for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
     mirror = {"nsff_field_desc": _cabi.FieldDesc, "nsff_field_params": _cabi.FieldParams,
-              "nsff_points": _cabi.Points, "nsff_composite_args": _cabi.CompositeArgs}
+              "nsff_points": _cabi.Points, "nsff_composite_args": _cabi.CompositeArgs,
+              "nsff_composite_grads": _cabi.CompositeGrads, "nsff_field_grads": _cabi.FieldGrads}
     for st, cls in mirror.items():
         assert int(got[st]) == C.sizeof(cls), st
         for f in fields[st]:

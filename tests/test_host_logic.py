@@ -67,7 +67,7 @@ def test_cpu_tensors_and_missing_backward_raise():
     emb = {"xyz": PosEmbedding(9, 10), "dir": PosEmbedding(3, 4)}
     with pytest.raises(NotImplementedError):
         render_rays({"fine": net}, emb, torch.zeros(2, 6), None, 0, N_samples=4)
-    with pytest.raises(NotImplementedError):          # requires_grad params + grad mode: backward not built
+    with pytest.raises(NotImplementedError):          # NeRF.forward on an embedded row records no graph
         net(torch.zeros(2, 90))
 
 
