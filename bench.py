@@ -154,6 +154,89 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_train(args, rank, local_rank, world):
+    """BASELINE.json configs[2]: training step, 1024-ray batch x 128 samples, bf16 tensor-core forward, CUDA backward,
+    surrogate photometric + warped-photometric + cycle + flow-regulariser loss (the reference's NeRFWLoss needs
+    kornia and dataset tensors), Adam step and bf16 re-pack inside the timed region; gradients all-reduced over ranks."""
+    import torch.distributed as dist
+    from nsff_pl_b200 import _cabi
+    from nsff_pl_b200.models.rendering import render_rays
+    from parity_util import build_fields, synthetic_rays
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    R, S = 1024, 128
+    models, emb, _, _ = build_fields(W=256, seed=0, n_frames=N_FRAMES, device=dev, precision="bf16")
+    import scenes
+    for m in models.values():
+        m.requires_grad_(True)
+    emb["t"].weight.requires_grad_(True)
+    params = [p for m in models.values() for p in m.parameters()] + [emb["t"].weight]
+    opt = torch.optim.Adam(params, lr=5e-4)
+    rays, ts = synthetic_rays(R, n_frames=N_FRAMES, seed=100 + rank)
+    rays, ts = rays.to(dev), ts.to(dev)
+    target = torch.rand(R, 3, device=dev)
+    kw = dict(N_samples=S, perturb=1.0, noise_std=1.0, N_importance=0, test_time=False,
+              output_transient_flow=["fw", "bw", "disocc"])
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        res = render_rays(models, emb, rays, ts, N_FRAMES - 1, **kw)
+        loss = ((res["rgb_fine"] - target) ** 2).mean()
+        loss = loss + (res["disocc_fw"] * (res["rgb_fw"] - target) ** 2).mean() + (res["disocc_bw"] * (res["rgb_bw"] - target) ** 2).mean()
+        loss = loss + (res["disoccs_fw"] * (res["xyzs_fw_bw"] - res["xyzs_fine"]).abs()).mean()
+        loss = loss + (res["disoccs_bw"] * (res["xyzs_bw_fw"] - res["xyzs_fine"]).abs()).mean()
+        loss = loss + 0.1 * (res["transient_flows_fw"].abs().mean() + res["transient_flows_bw"].abs().mean())
+        loss = loss + 0.01 * (res["transient_weights_fine"] * res["static_weights_fine"]).mean()
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
+            dist.all_reduce(flat)
+            flat /= world
+            o = 0
+            for p in params:
+                if p.grad is not None:
+                    n = p.grad.numel()
+                    p.grad.copy_(flat[o:o + n].view_as(p.grad))
+                    o += n
+        opt.step()
+        return loss
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n0 = _cabi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        value = R * S * world * args.steps / (ms * 1e-3)
+        print(json.dumps({"metric": "ray-samples/sec (training step fwd+bwd+Adam)", "value": value, "unit": "ray-samples/s",
+                          "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "bf16 fwd / f32 bwd", "data": "synthetic",
+                          "config": {"workload": "training step, 1024 rays x 128 samples per GPU, full NSFF + warp, surrogate "
+                                                 "photometric/cycle/flow loss, Adam (BASELINE.json configs[2])",
+                                     "backward": "fp32 CUDA-core kernels (recompute); tensor-core backward is round-2 work"},
+                          "gpu_launches": int(_cabi.launch_count() - n0), "final_loss": float(loss)}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def workload_config(args, world):
     return {"workload": "full NSFF static+dynamic+flow-warp +-1, 512x288 frame x 128 samples/ray, inference "
                         "(BASELINE.json configs[1])",
@@ -172,6 +255,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--precision", default="bf16", choices=["bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="render", choices=["render", "train"],
+                    help="render = BASELINE.json metric (default, what the driver runs); train = configs[2] step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -180,6 +265,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "train":
+        run_train(args, rank, local_rank, world)
         return
 
     import torch.distributed as dist

@@ -369,7 +369,7 @@ def render_rays(models: Dict[str, FieldSpec], enc: Encoders, rays: torch.Tensor,
                 results["transient_flow_bw"] = _wsum(w_all, flow_bw)
                 results["xyz_bw"] = results["xyz_fine"] + results["transient_flow_bw"]
                 if (not test_time) and "disocc" in flow_heads:
-                    occ_fw, occ_bw = w_t_fw - w_t, w_t_bw - w_t
+                    occ_fw, occ_bw = (w_t_fw - w_t).detach(), (w_t_bw - w_t).detach()      # :290-291
                     results["disocc_fw"] = 1 - occ_fw.sum(1, keepdim=True).abs()
                     results["disoccs_fw"] = 1 - occ_fw.unsqueeze(-1).abs()
                     results["disocc_bw"] = 1 - occ_bw.sum(1, keepdim=True).abs()
@@ -395,12 +395,12 @@ def render_rays(models: Dict[str, FieldSpec], enc: Encoders, rays: torch.Tensor,
         xyz_c = rays_o.unsqueeze(1) + rays_d.unsqueeze(1) * zs.unsqueeze(-1)
         field_pass(spec, xyz_c, zs, want_transient, [], t_embedded, None)
         det = perturb == 0
-        zs_static = sample_pdf(zs_mid, results["static_weights_coarse"][:, 1:-1], N_importance, det=det)
+        zs_static = sample_pdf(zs_mid, results["static_weights_coarse"][:, 1:-1].detach(), N_importance, det=det)   # :336
         merged = [zs, zs_static]
         if test_time:
             results["static_zs_fine"] = zs_static
         if want_transient:
-            zs_trans = sample_pdf(zs_mid, results["transient_weights_coarse"][:, 1:-1], N_importance, det=det)
+            zs_trans = sample_pdf(zs_mid, results["transient_weights_coarse"][:, 1:-1].detach(), N_importance, det=det)   # :343
             merged.append(zs_trans)
             if test_time:
                 results["transient_zs_fine"] = zs_trans

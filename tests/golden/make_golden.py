@@ -226,6 +226,38 @@ def main():
                   output_transient_flow=["fw", "bw"]), seed=111, dataset=ds,
              extra_arrays={"ds.K": ds.Ks[0].numpy(), "ds.poses": np.asarray(ds.poses, dtype=np.float32)})
 
+    # ---- 2b. gradients: autograd of the reference through a fixed scalar loss over EVERY differentiable output ----
+    def loss_of(res, seed):
+        g = torch.Generator().manual_seed(seed)
+        tot = 0.0
+        for k, v in res.items():
+            w = torch.randn(v.shape, generator=g)
+            if v.requires_grad:
+                tot = tot + (v * w).sum()
+        return tot
+
+    for name, kw, coarse in (
+            ("grads_train_warp_w64", dict(N_samples=16, perturb=0, noise_std=0, N_importance=0, test_time=False,
+                                          output_transient_flow=["fw", "bw", "disocc"]), False),
+            ("grads_hier_train_w64", dict(N_samples=12, perturb=0, noise_std=0, N_importance=6, test_time=False,
+                                          output_transient_flow=["fw", "bw", "disocc"]), True)):
+        models_g, emb_g = build(W=64, coarse=coarse, seed=21)
+        rays_g, ts_g = synthetic_rays(10, n_frames=N_FRAMES, seed=13)
+        res = ref_rendering.render_rays(models_g, emb_g, rays_g, ts_g, N_FRAMES - 1, **kw)
+        loss = loss_of(res, 77)
+        loss.backward()
+        arrays, meta_models = pack_models(models_g)
+        arrays["emb.t"] = emb_g["t"].weight.detach().numpy().copy()
+        arrays["rays"], arrays["ts"] = rays_g.numpy(), ts_g.numpy()
+        for key, m in models_g.items():
+            for n, p_ in m.named_parameters():
+                if p_.grad is not None:
+                    arrays[f"grad.{key}.{n}"] = p_.grad.numpy().copy()
+        arrays["grad.emb.t"] = emb_g["t"].weight.grad.numpy().copy()
+        save(name, dict(models=meta_models, call=dict(kw, max_t=N_FRAMES - 1), loss_seed=77, loss=float(loss),
+                        n_frames=N_FRAMES, grad_keys=[k for k, v in res.items() if v.requires_grad],
+                        result_keys=list(res.keys())), arrays)
+
     # ---- 3. full-width network (the shape the CUDA path is built for) ----------
     # weights are NOT stored (4.9 MB each); they are re-created from the seed and
     # guarded by a checksum so a different torch RNG is detected, not mis-compared.

@@ -60,7 +60,7 @@ def _run(precision, R, S, kw, coarse=False, seed=3, energise=True):
     assert list(want.keys()) == list(res.keys())
     loss_ref = _loss(want)
     loss_ref.backward()
-    return models, emb, specs, enc, float(loss), float(loss_ref), res, want
+    return models, emb, specs, enc, float(loss.detach()), float(loss_ref.detach()), res, want
 
 
 def _check_grads(models, emb, specs, enc, tol, flow_tol=None, median_tol=None):
@@ -112,7 +112,7 @@ def test_no_flow_and_hierarchical_gradients_fp32():
                                                                              test_time=False,
                                                                              output_transient_flow=["fw", "bw", "disocc"]),
                                                          coarse=True)
-    _check_grads(models, emb, specs, enc, tol=0.15)
+    _check_grads(models, emb, specs, enc, tol=5e-2)
 
 
 def test_full_nsff_gradients_bf16_forward():

@@ -12,7 +12,8 @@ from scenes import FakeDataset, energise_
 from oracle import nsff_oracle as O
 
 ATOL = RTOL = 2e-6
-RENDER_CASES = [c for c in golden_io.list_cases("*_w64") if c != "ops_w64"]
+RENDER_CASES = [c for c in golden_io.list_cases("*_w64") if c != "ops_w64" and not c.startswith("grads_")]
+GRAD_CASES = golden_io.list_cases("grads_*")
 
 
 def _spec(meta_m, state):
@@ -81,6 +82,41 @@ def test_render_rays_matches_reference(case):
     assert list(got.keys()) == meta["result_keys"], "result dict keys / order differ from the reference"
     for k in want:
         _close(k, got[k], want[k])
+
+
+@pytest.mark.parametrize("case", GRAD_CASES)
+def test_oracle_autograd_matches_reference_autograd(case):
+    """The oracle is also the gradient reference of tests/test_gpu_backward.py, so its autograd is pinned too:
+    same differentiable-output set (disocc* detached, resampling pdf detached), same loss value, same gradients."""
+    meta, a = golden_io.load(case)
+    models = {k: _spec(m, golden_io.model_state(a, k)) for k, m in meta["models"].items()}
+    for sp in models.values():
+        for k in sp.params:
+            sp.params[k] = sp.params[k].clone().requires_grad_(True)
+    enc = _encoders(a)
+    enc.t_table = enc.t_table.clone().requires_grad_(True)
+    kw = dict(meta["call"])
+    max_t = kw.pop("max_t")
+    got = O.render_rays(models, enc, a["rays"], a["ts"], max_t, **kw)
+    assert [k for k, v in got.items() if v.requires_grad] == meta["grad_keys"]
+    g = torch.Generator().manual_seed(meta["loss_seed"])
+    loss = 0.0
+    for k, v in got.items():
+        w = torch.randn(v.shape, generator=g)
+        if v.requires_grad:
+            loss = loss + (v * w).sum()
+    assert abs(float(loss) - meta["loss"]) <= 1e-4 * max(1.0, abs(meta["loss"]))
+    loss.backward()
+    for key, sp in models.items():
+        for n, p in sp.params.items():
+            ref = a.get(f"grad.{key}.{n}")
+            if ref is None:
+                assert p.grad is None or float(p.grad.abs().max()) == 0.0, f"{key}.{n}"
+                continue
+            err = float((p.grad - ref).norm() / (ref.norm() + 1e-12))
+            assert err <= 1e-4, f"{key}.{n}: {err:.3e}"
+    ref = a["grad.emb.t"]
+    assert float((enc.t_table.grad - ref).norm() / ref.norm()) <= 1e-4
 
 
 def test_full_width_seeded_case():
