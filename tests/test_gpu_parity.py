@@ -368,3 +368,23 @@ def test_cpu_tensor_and_missing_grad_support_fail_loudly():
     with torch.no_grad():
         out = render_rays(models, emb, rays.cuda(), ts.cuda(), 29, N_samples=8)
     assert out["rgb_fine"].shape == (8, 3)
+
+
+def test_ray_sharded_render_is_bitwise_identical_to_unsharded():
+    """Config 4's invariant: rays are independent, so rendering a frame in contiguous
+    ray blocks (what each rank of an N-GPU job does, nsff_pl_b200/parallel.py) and concatenating equals the
+    one-shot render bit for bit - for uneven block sizes too."""
+    from nsff_pl_b200 import parallel
+    from nsff_pl_b200.models.rendering import render_rays
+    models, emb, _, _ = build_fields(W=256, seed=23, precision="bf16")
+    rays, ts = synthetic_rays(1000, n_frames=30, seed=8)
+    rays, ts = rays.cuda(), ts.cuda()
+    kw = dict(N_samples=128, test_time=False, output_transient_flow=["fw", "bw", "disocc"])
+    full = render_rays(models, emb, rays, ts, 29, **kw)
+    for world in (2, 8, 3):
+        parts = []
+        for rank in range(world):
+            lo, hi = parallel.shard_bounds(1000, rank, world)
+            parts.append(parallel.pack_pixels(render_rays(models, emb, rays[lo:hi].contiguous(), ts[lo:hi].contiguous(),
+                                                          29, **kw)))
+        assert torch.equal(torch.cat(parts, 0), parallel.pack_pixels(full)), f"world={world}"
