@@ -269,6 +269,30 @@ NSFF_API int nsff_sample_pdf(const float* bins, int64_t bins_row_stride, const f
 NSFF_API int nsff_merge_sorted(const float* a, int na, const float* b, int nb, const float* c, int nc,
                       int64_t R, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * f1  interpolate + softmax-splat ("average")            models/rendering.py:365-460, softsplat.py:6-44,303-329
+ *     Renders time t+dt from two render_rays(test_time=True, flows) results of the same rays: every sample plane of
+ *     the dynamic RGBA of frame t is forward-splatted by the projected dt-scaled forward flow, that of frame t+1 by
+ *     the (1-dt)-scaled backward flow, both are blended and composited front to back with the static plane.
+ *     Per-sample inputs are (R,S,*) with row stride ld_t / ld_tp1 floats (they are views of the field output);
+ *     R = w*h rays in pixel order.  P = K @ w2c (rows 1,2 of w2c negated), row-major 3x4.
+ */
+typedef struct {
+  int64_t R; int32_t S; int32_t w, h;
+  float dt, fx, fy, cx, cy;
+  float P[12];
+  const float* xyzs;          /* (R,S,3) contiguous                                   */
+  const float* zs;            /* (R,S)                                                */
+  const float* static_rgb;    /* (R,S,3) view, stride ld_t                            */
+  const float* static_alpha;  /* (R,S)                                                */
+  const float* rgb_t;  const float* alpha_t;  const float* flow_fw;   int32_t ld_t;   /* frame t   */
+  const float* rgb_tp1; const float* alpha_tp1; const float* flow_bw; int32_t ld_tp1; /* frame t+1 */
+} nsff_interpolate_args;
+
+NSFF_API size_t nsff_interpolate_scratch_floats(int64_t R, int S);
+NSFF_API int nsff_interpolate(const nsff_interpolate_args* args /*host*/, float* scratch, float* rgb /*(h,w,3)*/,
+                              float* depth /*(h,w)*/, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

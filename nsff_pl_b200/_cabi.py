@@ -83,6 +83,15 @@ class CompositeGrads(C.Structure):
                  "rgb_fw", "rgb_bw", "d_raw", "d_raw_fw", "d_raw_bw")]
 
 
+class InterpolateArgs(C.Structure):
+    _fields_ = [("R", C.c_int64), ("S", C.c_int32), ("w", C.c_int32), ("h", C.c_int32),
+                ("dt", C.c_float), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("P", C.c_float * 12),
+                ("xyzs", C.c_void_p), ("zs", C.c_void_p), ("static_rgb", C.c_void_p), ("static_alpha", C.c_void_p),
+                ("rgb_t", C.c_void_p), ("alpha_t", C.c_void_p), ("flow_fw", C.c_void_p), ("ld_t", C.c_int32),
+                ("rgb_tp1", C.c_void_p), ("alpha_tp1", C.c_void_p), ("flow_bw", C.c_void_p), ("ld_tp1", C.c_int32)]
+
+
 # name -> (restype, argtypes); also the list tests/test_cabi_symbols.py checks against the header
 PROTOTYPES = {
     "nsff_abi_version": (C.c_int, []),
@@ -109,6 +118,8 @@ PROTOTYPES = {
                                            C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(FieldGrads), C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsff_composite_backward": (C.c_int, [C.POINTER(CompositeArgs), C.POINTER(CompositeGrads), C.c_void_p]),
+    "nsff_interpolate_scratch_floats": (C.c_size_t, [C.c_int64, C.c_int]),
+    "nsff_interpolate": (C.c_int, [C.POINTER(InterpolateArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsff_visibility": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.c_void_p, C.c_int, C.c_int,
                                   C.c_int, C.c_void_p, C.c_void_p]),
     "nsff_composite": (C.c_int, [C.POINTER(CompositeArgs), C.c_void_p]),

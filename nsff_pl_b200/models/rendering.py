@@ -16,7 +16,7 @@ import torch
 from .. import _cabi
 from .nerf import NeRF
 
-__all__ = ["render_rays", "sample_pdf"]
+__all__ = ["render_rays", "sample_pdf", "interpolate"]
 
 
 def sample_pdf(bins, weights, N_importance, det=False, eps=1e-5):
@@ -317,3 +317,64 @@ def render_rays(models, embeddings, rays, ts, max_t, N_samples=64, perturb=0, no
         _field_pass(results, model, embeddings, xyz, zs, dirs, ts, max_t, want_transient, flow_heads, test_time,
                     noise_std, t_embedded, a_embedded, kwargs)
     return results
+
+
+def _sample_view(t, name, S, cols=3):
+    """(R,S,cols) view of a field output (row stride in floats) or a contiguous tensor -> (tensor, ld)."""
+    if not t.is_cuda:
+        raise NotImplementedError(f"{name} is a CPU tensor: nsff_pl_b200 kernels are CUDA-only (no CPU fallback)")
+    if t.dtype != torch.float32 or t.dim() != 3 or t.shape[1] != S or t.shape[2] != cols:
+        raise ValueError(f"{name} must be float32 (R, {S}, {cols}), got {t.dtype} {tuple(t.shape)}")
+    if t.stride(2) != 1 or t.stride(0) != S * t.stride(1):
+        t = t.contiguous()
+    return t, t.stride(1)
+
+
+def interpolate(results_t, results_tp1, dt, K, c2w, img_wh):
+    """reference rendering.py:365-460.  results_t / results_tp1: render_rays(test_time=True,
+    output_transient_flow=['fw','bw']) of the SAME rays at frames t and t+1; returns ((h,w,3) rgb, (h,w) depth) at
+    time t+dt.  All S sample planes are splatted and composited on the device in two launches."""
+    L = _cabi.lib()
+    xyzs = _cabi.dev_tensor(results_t["xyzs_fine"].contiguous(), "xyzs_fine")
+    R, S = xyzs.shape[:2]
+    w, h = int(img_wh[0]), int(img_wh[1])
+    if w * h != R:
+        raise ValueError(f"img_wh {img_wh} does not match {R} rays")
+    dev = xyzs.device
+    K = torch.as_tensor(K, dtype=torch.float32).cpu()
+    c2w4 = torch.eye(4)
+    c2w4[:3] = torch.as_tensor(c2w, dtype=torch.float32).cpu()
+    w2c = torch.inverse(c2w4)[:3]
+    w2c[1:] *= -1                                   # "right up back" -> "right down forward" (rendering.py:391-393)
+    P = (K @ w2c).reshape(12)
+    a = _cabi.InterpolateArgs()
+    a.R, a.S, a.w, a.h, a.dt = R, S, w, h, float(dt)
+    a.fx, a.fy, a.cx, a.cy = float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
+    for i in range(12):
+        a.P[i] = float(P[i])
+    zs = _cabi.dev_tensor(results_t["zs_fine"].contiguous(), "zs_fine")
+    s_rgb, ld_s = _sample_view(results_t["static_rgbs_fine"], "static_rgbs_fine", S)
+    rgb_t, ld_rt = _sample_view(results_t["transient_rgbs_fine"], "transient_rgbs_fine", S)
+    ffw, ld_f = _sample_view(results_t["transient_flows_fw"], "transient_flows_fw", S)
+    rgb_p, ld_rp = _sample_view(results_tp1["transient_rgbs_fine"], "transient_rgbs_fine (t+1)", S)
+    fbw, ld_b = _sample_view(results_tp1["transient_flows_bw"], "transient_flows_bw (t+1)", S)
+    if not (ld_s == ld_rt == ld_f):                 # mixed layouts: fall back to packed copies of frame t
+        s_rgb, rgb_t, ffw = s_rgb.contiguous(), rgb_t.contiguous(), ffw.contiguous()
+        ld_s = ld_rt = ld_f = 3
+    if ld_rp != ld_b:
+        rgb_p, fbw = rgb_p.contiguous(), fbw.contiguous()
+        ld_rp = ld_b = 3
+    s_a = _cabi.dev_tensor(results_t["static_alphas_fine"].contiguous(), "static_alphas_fine")
+    a_t = _cabi.dev_tensor(results_t["transient_alphas_fine"].contiguous(), "transient_alphas_fine")
+    a_p = _cabi.dev_tensor(results_tp1["transient_alphas_fine"].contiguous(), "transient_alphas_fine (t+1)")
+    a.xyzs, a.zs = xyzs.data_ptr(), zs.data_ptr()
+    a.static_rgb, a.static_alpha = s_rgb.data_ptr(), s_a.data_ptr()
+    a.rgb_t, a.alpha_t, a.flow_fw, a.ld_t = rgb_t.data_ptr(), a_t.data_ptr(), ffw.data_ptr(), ld_s
+    a.rgb_tp1, a.alpha_tp1, a.flow_bw, a.ld_tp1 = rgb_p.data_ptr(), a_p.data_ptr(), fbw.data_ptr(), ld_rp
+    scratch = torch.empty(L.nsff_interpolate_scratch_floats(R, S), device=dev, dtype=torch.float32)
+    rgb = torch.empty(h, w, 3, device=dev, dtype=torch.float32)
+    depth = torch.empty(h, w, device=dev, dtype=torch.float32)
+    _cabi.select_device(xyzs)
+    _cabi.check(L.nsff_interpolate(C.byref(a), _cabi.ptr(scratch), _cabi.ptr(rgb), _cabi.ptr(depth),
+                                   _cabi.stream_ptr(dev)), "nsff_interpolate")
+    return rgb, depth

@@ -417,3 +417,77 @@ def render_rays(models: Dict[str, FieldSpec], enc: Encoders, rays: torch.Tensor,
     xyz_f = rays_o.unsqueeze(1) + rays_d.unsqueeze(1) * zs.unsqueeze(-1)
     field_pass(spec, xyz_f, zs, want_transient, flow_heads, t_embedded, a_embedded)
     return results
+
+
+# --------------------------------------------------------------------------
+# test-time frame interpolation (models/rendering.py:365-460) with the forward
+# "average" softmax-splat of models/softsplat.py:6-44,303-329 restated on CPU
+# --------------------------------------------------------------------------
+def splat_average(inp: torch.Tensor, flow: torch.Tensor) -> torch.Tensor:
+    """FunctionSoftsplat(tenInput (1,C,H,W), tenFlow (1,2,H,W), None, 'average'): every source pixel adds
+    input*bilinear_weight to the 4 integer neighbours of (x+flow_x, y+flow_y); a ones channel accumulates the
+    weights and the result is divided by it (zero weight -> 1)."""
+    _, Cc, H, W = inp.shape
+    src = torch.cat([inp, torch.ones(1, 1, H, W)], 1)[0].reshape(Cc + 1, -1)          # (C+1, HW)
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    ox = (xs + flow[0, 0]).reshape(-1)
+    oy = (ys + flow[0, 1]).reshape(-1)
+    x0, y0 = torch.floor(ox), torch.floor(oy)
+    out = torch.zeros(Cc + 1, H * W)
+    for dx, dy in ((0, 0), (1, 0), (0, 1), (1, 1)):
+        xi, yi = x0 + dx, y0 + dy
+        wgt = (1 - (ox - xi).abs()) * (1 - (oy - yi).abs())
+        ok = (xi >= 0) & (xi < W) & (yi >= 0) & (yi < H)
+        idx = (yi * W + xi).long()[ok]
+        out.index_add_(1, idx, src[:, ok] * wgt[ok])
+    norm = out[-1:]
+    norm = torch.where(norm == 0, torch.ones_like(norm), norm)
+    return (out[:-1] / norm).reshape(1, Cc, H, W)
+
+
+def interpolate(results_t, results_tp1, dt, K, c2w, img_wh):
+    """models/rendering.py:365-460: per-sample-plane forward splat of the dynamic RGBA of frame t (by dt * flow_fw)
+    and of frame t+1 (by (1-dt) * flow_bw), blended and composited front to back with the static plane."""
+    w, h = img_wh
+    xyzs = results_t["xyzs_fine"]
+    R, S = xyzs.shape[:2]
+    c2w4 = torch.eye(4)
+    c2w4[:3] = c2w
+    w2c = torch.inverse(c2w4)[:3]
+    w2c[1:] *= -1
+    P = K @ w2c
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+    grid = torch.stack([xs, ys], -1)                                                  # (h, w, 2) = (x, y)
+    pts = xyzs.reshape(-1, 3)
+    world = ndc2world(pts, K)
+
+    def plane_flow(flows, scale):
+        moved = ndc2world((xyzs + flows).reshape(-1, 3), K)
+        moved = world + scale * (moved - world)
+        uvd = P[:, :3] @ moved.T + P[:, 3:]
+        uv = (uvd[:2] / uvd[2]).reshape(2, h, w, S)
+        return uv.permute(3, 0, 1, 2) - grid.permute(2, 0, 1).unsqueeze(0)           # (S, 2, h, w)
+
+    of_fw = plane_flow(results_t["transient_flows_fw"], dt)
+    of_bw = plane_flow(results_tp1["transient_flows_bw"], 1 - dt)
+
+    def rgba(res):
+        rgb = res["transient_rgbs_fine"].reshape(h, w, S, 3).permute(2, 3, 0, 1)
+        a = res["transient_alphas_fine"].reshape(h, w, S).permute(2, 0, 1).unsqueeze(1)
+        return torch.cat([rgb, a], 1)                                                 # (S, 4, h, w)
+
+    rgba_t, rgba_tp1 = rgba(results_t), rgba(results_tp1)
+    static_rgb = results_t["static_rgbs_fine"].reshape(h, w, S, 3)
+    static_a = results_t["static_alphas_fine"].reshape(h, w, S, 1)
+    zs = results_t["zs_fine"].reshape(h, w, S)
+    acc = torch.zeros(h, w, 4)
+    depth = torch.zeros(h, w)
+    for s in range(S):
+        fw = splat_average(rgba_t[s:s + 1], of_fw[s:s + 1])[0].permute(1, 2, 0)
+        bw = splat_average(rgba_tp1[s:s + 1], of_bw[s:s + 1])[0].permute(1, 2, 0)
+        c_rgb = fw[..., :3] * fw[..., 3:] * (1 - dt) + bw[..., :3] * bw[..., 3:] * dt + static_rgb[:, :, s] * static_a[:, :, s]
+        c_a = 1 - (1 - (fw[..., 3:] * (1 - dt) + bw[..., 3:] * dt)) * (1 - static_a[:, :, s])
+        acc[..., :3] += (1 - acc[..., 3:]) * c_rgb
+        depth += (1 - acc[..., 3]) * c_a[..., 0] * zs[..., s]
+        acc[..., 3:] += (1 - acc[..., 3:]) * c_a
+    return acc[..., :3], depth

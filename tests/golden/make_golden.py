@@ -24,6 +24,7 @@ import torch
 REF = os.environ.get("NSFF_REFERENCE", "/root/reference")
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, ".."))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
 from scenes import energise_, synthetic_rays, FakeDataset  # noqa: E402  (tests/scenes.py)
 
 
@@ -257,6 +258,38 @@ def main():
         save(name, dict(models=meta_models, call=dict(kw, max_t=N_FRAMES - 1), loss_seed=77, loss=float(loss),
                         n_frames=N_FRAMES, grad_keys=[k for k, v in res.items() if v.requires_grad],
                         result_keys=list(res.keys())), arrays)
+
+    # ---- 2c. test-time interpolation (rendering.py:365-460).  The splat op is a cupy kernel that cannot run here: the
+    # reference's interpolate() is executed with FunctionSoftsplat replaced by the oracle's CPU restatement of
+    # softsplat.py:6-44 ('average') and Tensor.cuda() made a no-op, so the projection / blend / MPI composite are the
+    # reference's own code and only the splat itself is restated.
+    from oracle import nsff_oracle as O
+    models_i, emb_i = build(W=64, seed=31)
+    wi, hi = 12, 7
+    rays_i, _ = synthetic_rays(wi * hi, n_frames=N_FRAMES, seed=14, img_wh=(wi, hi), frame=2)
+    ts_i = torch.full((wi * hi,), 2, dtype=torch.long)
+    kw_i = dict(N_samples=10, N_importance=0, test_time=True, output_transient_flow=["fw", "bw"])
+    with torch.no_grad():
+        rt = ref_rendering.render_rays(models_i, emb_i, rays_i, ts_i, N_FRAMES - 1, **kw_i)
+        rp = ref_rendering.render_rays(models_i, emb_i, rays_i, ts_i + 1, N_FRAMES - 1, **kw_i)
+    ds_i = FakeDataset(n_frames=N_FRAMES, n_cams=1, img_wh=(wi, hi), seed=8)
+    K_i, c2w_i = ds_i.Ks[0], torch.tensor(ds_i.poses[1])
+    saved = ref_rendering.FunctionSoftsplat, torch.Tensor.cuda
+    ref_rendering.FunctionSoftsplat = lambda tenInput, tenFlow, tenMetric, strType: O.splat_average(tenInput, tenFlow)
+    torch.Tensor.cuda = lambda self, *a_, **k_: self
+    try:
+        arrays = {}
+        for dt in (0.0, 0.3, 0.75):
+            rgb_i, depth_i = ref_rendering.interpolate(rt, rp, dt, K_i, c2w_i, (wi, hi))
+            arrays[f"out.rgb.{dt}"], arrays[f"out.depth.{dt}"] = rgb_i.numpy(), depth_i.numpy()
+    finally:
+        ref_rendering.FunctionSoftsplat, torch.Tensor.cuda = saved
+    keys = ("xyzs_fine", "zs_fine", "static_rgbs_fine", "static_alphas_fine", "transient_rgbs_fine",
+            "transient_alphas_fine", "transient_flows_fw", "transient_flows_bw")
+    for k in keys:
+        arrays[f"t.{k}"], arrays[f"tp1.{k}"] = rt[k].numpy().copy(), rp[k].numpy().copy()
+    arrays["K"], arrays["c2w"] = K_i.numpy(), c2w_i.numpy()
+    save("interpolate_w64", dict(img_wh=[wi, hi], dts=[0.0, 0.3, 0.75], keys=list(keys)), arrays)
 
     # ---- 3. full-width network (the shape the CUDA path is built for) ----------
     # weights are NOT stored (4.9 MB each); they are re-created from the seed and

@@ -12,7 +12,8 @@ from scenes import FakeDataset, energise_
 from oracle import nsff_oracle as O
 
 ATOL = RTOL = 2e-6
-RENDER_CASES = [c for c in golden_io.list_cases("*_w64") if c != "ops_w64" and not c.startswith("grads_")]
+RENDER_CASES = [c for c in golden_io.list_cases("*_w64")
+                if c not in ("ops_w64", "interpolate_w64") and not c.startswith("grads_")]
 GRAD_CASES = golden_io.list_cases("grads_*")
 
 
@@ -117,6 +118,31 @@ def test_oracle_autograd_matches_reference_autograd(case):
             assert err <= 1e-4, f"{key}.{n}: {err:.3e}"
     ref = a["grad.emb.t"]
     assert float((enc.t_table.grad - ref).norm() / ref.norm()) <= 1e-4
+
+
+def test_interpolate_matches_reference():
+    """rendering.py:365-460 run by the reference itself with the splat op swapped for the oracle's restatement."""
+    meta, a = golden_io.load("interpolate_w64")
+    rt = {k: a[f"t.{k}"] for k in meta["keys"]}
+    rp = {k: a[f"tp1.{k}"] for k in meta["keys"]}
+    for dt in meta["dts"]:
+        rgb, depth = O.interpolate(rt, rp, dt, a["K"], a["c2w"], tuple(meta["img_wh"]))
+        _close(f"rgb@{dt}", rgb, a[f"out.rgb.{dt}"])
+        _close(f"depth@{dt}", depth, a[f"out.depth.{dt}"])
+
+
+def test_splat_average_known_answers():
+    """softsplat.py:6-44 semantics on hand-checkable cases: integer flow moves pixels, half-pixel flow splits 50/50,
+    out-of-frame contributions are dropped, untouched pixels stay 0 (weight 0 -> divide by 1)."""
+    inp = torch.arange(1.0, 7.0).reshape(1, 1, 2, 3)
+    flow = torch.zeros(1, 2, 2, 3)
+    assert torch.equal(O.splat_average(inp, flow), inp)
+    flow[:, 0] = 1.0                                           # everything one pixel to the right
+    out = O.splat_average(inp, flow)
+    assert torch.equal(out[0, 0], torch.tensor([[0.0, 1.0, 2.0], [0.0, 4.0, 5.0]]))
+    flow[:, 0] = 0.5                                           # split between x and x+1: average of the two sources
+    out = O.splat_average(inp, flow)
+    assert torch.allclose(out[0, 0], torch.tensor([[1.0, 1.5, 2.5], [4.0, 4.5, 5.5]]))
 
 
 def test_full_width_seeded_case():
