@@ -201,6 +201,8 @@ struct FwdParams {
   int32_t n_steps;
   int32_t n_tiles;
   int32_t need_t, need_dir;
+  int32_t last_extra_step;  // last step whose K-chunks include PE / time code / PE(dir): after its MMAs the three
+                            // prologue chunks are dead and the NEXT tile's prologue can be written early
   float flow_scale;
   unsigned long long* dbg;  // NSFF_TIMELINE builds only: (tag, clock64) event log of CTA 0
   int32_t exp_flags;        // NSFF_EXPERIMENT builds only: 1 = MMA ignores hidden-chunk readiness (wrong results),
@@ -576,19 +578,24 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
     unsigned long long* tl_ptr = (P.dbg && blockIdx.x == 0 && warp == 0) ? P.dbg + 2 * 2 * kDbgPerRole : nullptr;
     int tl_n = 0;
 #endif
+    // Prologue: encode a tile's inputs into the three extra chunks.  Only the first tile pays for it up front; for
+    // every later tile it is run during the previous tile, right after the last step that reads those chunks
+    // (P.last_extra_step), i.e. hidden behind the remaining layers instead of idling the tensor pipe.
+    auto prologue = [&](int unit_) {
+      const int64_t pr = (int64_t)(unit_ * kCtas + (int)cta_rank) * kTileM + row;
+      const bool ok = pr < P.pts.B;
+      encode_tile_row(P, sA, row, part, ok ? pr : P.pts.B - 1, ok);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) arrive_leader(BAR_EXTRA_FULL);
+    };
+    if (group < n_units) prologue(group);
     for (int unit = group; unit < n_units; unit += n_groups) {
-      NSFF_TL((gstep << 8) | 13);                            // epi: tile start (prologue begins)
+      NSFF_TL((gstep << 8) | 13);                            // epi: tile start
       const int tile = unit * kCtas + (int)cta_rank;
       const int64_t p_raw = (int64_t)tile * kTileM + row;
       const bool valid = p_raw < P.pts.B;
       const int64_t p = valid ? p_raw : P.pts.B - 1;
-      // ---------------- prologue: encode this tile's inputs into the extra chunks ----------------
-      // (all MMAs of the previous tile have completed: its last acc_full was waited on below)
-      encode_tile_row(P, sA, row, part, p, valid);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) arrive_leader(BAR_EXTRA_FULL);
-      NSFF_TL((gstep << 8) | 12);                            // epi: prologue published
 
       float zrow = 0.f;
       if (P.pts.zs && P.x_emb == nullptr) zrow = P.pts.zs[p];
@@ -681,6 +688,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
             mbar_arrive(bar(BAR_BIAS_EMPTY + bslot));
           }
         }
+        // this step's accumulator was complete => every MMA up to and including it has finished reading smem
+        if (s == P.last_extra_step && unit + n_groups < n_units) prologue(unit + n_groups);
       }
     }
   }
@@ -866,6 +875,10 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
   }
   if (n > kMaxSteps) return NSFF_EUNSUPPORTED;
   P.n_steps = n;
+  P.last_extra_step = 0;
+  for (int i = 0; i < n; ++i)
+    for (int kc = 0; kc < P.steps[i].nchunks; ++kc)
+      if (P.steps[i].chunk[kc] >= CH_PE) P.last_extra_step = i;
   *n_out_cols = col;
   return NSFF_OK;
 }
