@@ -340,10 +340,14 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     nerf_mod.FIELD_EVENTS = field_events
+    from nsff_pl_b200.models import rendering as rendering_mod
+    composite_events = []
+    rendering_mod.COMPOSITE_EVENTS = composite_events
     n0 = _cabi.launch_count()
     ms = timed(lambda: step(rays_d, ts_d), args.steps)
     launches = _cabi.launch_count() - n0
     nerf_mod.FIELD_EVENTS = None
+    rendering_mod.COMPOSITE_EVENTS = None
     clocks = sampler.stop()
     value = units_per_step * args.steps / (ms * 1e-3)
 
@@ -377,6 +381,15 @@ def main():
                     "launches_timed": len(kern_ms), "avg_launch_ms": per_launch_ms,
                     "kernel_share_of_step": (sum(kern_ms) / ms) if kern_ms else None,
                     "algorithmic_flop_per_launch": (sum(flops) / len(flops)) if flops else None}
+        comp_ms = [a.elapsed_time(b) for a, b, _ in composite_events]
+        comp_bytes = [n for _, _, n in composite_events]
+        comp_gbs = (sum(comp_bytes) / (sum(comp_ms) * 1e-3)) / 1e9 if comp_ms else None
+        roofline_composite = {"bound": "hbm", "kernel": "nsff::composite_kernel<1,1,1>", "achieved": comp_gbs,
+                              "peak": peaks["hbm"], "unit": "GB/s", "frac": None if comp_gbs is None else comp_gbs / peaks["hbm"],
+                              "traffic": None, "peak_source": f"{peaks['source']} hbm_gbs",
+                              "launches_timed": len(comp_ms), "avg_launch_ms": sum(comp_ms) / max(1, len(comp_ms)),
+                              "kernel_share_of_step": (sum(comp_ms) / ms) if comp_ms else None,
+                              "algorithmic_bytes_per_launch": (sum(comp_bytes) / len(comp_bytes)) if comp_bytes else None}
         cpu = None
         if not args.no_cpu_baseline and world >= 1:
             v, times, cores = cpu_port_throughput(CPU_SAMPLE_RAYS, reps=2)
@@ -389,7 +402,8 @@ def main():
                 "data": "synthetic", "config": workload_config(args, world),
                 "e2e": {"value": e2e_value, "unit": "ray-samples/s", "h2d_bytes_per_step": int(rays_pin.numel() * 4 + ts_pin.numel() * 8),
                         "d2h_bytes_per_step": int(pix_host.numel() * 4), "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_composite": roofline_composite,
+                "cpu_baseline": cpu,
                 "tflops_whole_step": units_per_step * FLOP_PER_POINT / (ms / args.steps * 1e-3) / 1e12 / world}
         print(json.dumps(line), flush=True)
     if world > 1:

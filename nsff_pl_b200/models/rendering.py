@@ -18,6 +18,27 @@ from .nerf import NeRF
 
 __all__ = ["render_rays", "sample_pdf", "interpolate"]
 
+# Optional profiling hook (bench.py): when a list, every inference composite launch appends
+# (start_event, end_event, algorithmic_hbm_bytes) recorded on the launching stream.
+COMPOSITE_EVENTS = None
+_PER_SAMPLE_OUT = {"static_sigmas": 1, "transient_sigmas": 1, "static_weights": 1, "transient_weights": 1, "weights": 1,
+                   "static_alphas": 1, "transient_alphas": 1, "xyzs_fw_bw": 3, "xyzs_bw_fw": 3, "disoccs_fw": 1,
+                   "disoccs_bw": 1}
+
+
+def _composite_bytes(a, B):
+    """Algorithmic HBM bytes of one nsff_composite launch: every per-sample input read once, every per-sample
+    output written once (per-ray outputs are ~0.2 % and ignored); SURVEY.md section 8d."""
+    floats = a.raw_ld + 1                                   # raw row + z
+    if a.has_flow:
+        floats += 3                                         # xyz (for xyz_fine)
+    for name in ("noise_static", "noise_trans", "noise_fw", "noise_bw", "vis"):
+        floats += 1 if getattr(a, name) else 0
+    if a.raw_fw:
+        floats += 14 + (6 if (a.xyzs_fw_bw or a.xyzs_bw_fw) else 0)
+    floats += sum(n for k, n in _PER_SAMPLE_OUT.items() if getattr(a, k))
+    return 4 * B * floats
+
 
 def sample_pdf(bins, weights, N_importance, det=False, eps=1e-5):
     """reference rendering.py:10-49.  bins (R, n+1), weights (R, n) -> (R, N_importance)."""
@@ -200,7 +221,14 @@ def _field_pass(results, model, embeddings, xyz, zs, dirs, ts, max_t, want_trans
                     results["disoccs_bw"], a.disoccs_bw = out("dsbw", R, S, 1)
         else:
             results[f"rgb_{typ}"], a.rgb = out("rgb", R, 3)
+    ev = None
+    if COMPOSITE_EVENTS is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record(torch.cuda.current_stream(dev))
     _cabi.check(L.nsff_composite(C.byref(a), st), "nsff_composite")
+    if ev is not None:
+        ev[1].record(torch.cuda.current_stream(dev))
+        COMPOSITE_EVENTS.append((ev[0], ev[1], _composite_bytes(a, B)))
     del keep
 
 
