@@ -212,6 +212,63 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(const nsff_composite
   }
 }
 
+// Static-only field (no transient branch): outputs static_sigmas, static_weights (= weights), depth, rgb
+// (rendering.py:206-208, 234-248, 256, 298).
+__global__ void __launch_bounds__(128) composite_bwd_static_kernel(const nsff_composite_args a,
+                                                                   const nsff_composite_grads g) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (ray >= a.R) return;
+  const int S = a.S;
+  const int64_t base = ray * S;
+  const int nch = (S + 31) / 32;
+  float al_[kMaxChunksBwd], T_[kMaxChunksBwd], x_[kMaxChunksBwd];
+  float carry = 1.f;
+#pragma unroll
+  for (int k = 0; k < kMaxChunksBwd; ++k) {
+    if (k >= nch) break;
+    const int s = k * 32 + lane;
+    const bool ok = s < S;
+    const int64_t i = base + (ok ? s : S - 1);
+    const bool last = s >= S - 1;
+    const float z = a.zs[i];
+    const float d_s = last ? kLastDeltaStatic : a.zs[i + 1] - z;
+    float x = a.raw[i * a.raw_ld + 3];
+    if (a.noise_static) x += a.noise_static[i] * a.noise_std;
+    const float al = 1.f - expf(-d_s * softplus_f(x));
+    x_[k] = x; al_[k] = al;
+    T_[k] = warp_excl_prod_b(ok ? 1.f - al : 1.f, carry, lane);
+  }
+  const float g_depth = g.depth ? g.depth[ray] : 0.f;
+  float g_rgb[3];
+  ld3g(g.rgb, ray, g_rgb);
+  float sfx = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < kMaxChunksBwd; ++kk) {
+    const int k = nch - 1 - kk;
+    if (k < 0) break;
+    const int s = k * 32 + lane;
+    const bool ok = s < S;
+    const int64_t i = base + (ok ? s : S - 1);
+    const bool last = s >= S - 1;
+    const float z = a.zs[i];
+    const float d_s = last ? kLastDeltaStatic : a.zs[i + 1] - z;
+    const float* raw = a.raw + i * a.raw_ld;
+    const float c[3] = {raw[0], raw[1], raw[2]};
+    const float al = al_[k], T = T_[k];
+    float dw = (g.static_weights ? g.static_weights[i] : 0.f) + g_depth * z + dot3(g_rgb, c);
+    if (!ok) dw = 0.f;
+    const float S_after = warp_excl_suffix(ok ? dw * al * T : 0.f, sfx, lane);
+    const float dal = dw * T - safe_div(S_after, 1.f - al);
+    if (ok) {
+      float* o = g.d_raw + i * a.raw_ld;
+      const float w = al * T;
+      o[0] = g_rgb[0] * w; o[1] = g_rgb[1] * w; o[2] = g_rgb[2] * w;
+      o[3] = (dal * d_s * (1.f - al) + (g.static_sigmas ? g.static_sigmas[i] : 0.f)) * dsoftplus(x_[k]);
+    }
+  }
+}
+
 }  // namespace nsff
 
 using namespace nsff;
@@ -223,7 +280,12 @@ extern "C" int nsff_composite_backward(const nsff_composite_args* args, const ns
   if (a.R < 0 || a.S < 1) return NSFF_EINVAL;
   if (a.R == 0) return NSFF_OK;
   if (a.S > 32 * kMaxChunksBwd) return NSFF_EUNSUPPORTED;
-  if (!a.zs || !a.raw || !a.has_static_rgb || !a.has_transient) return NSFF_EUNSUPPORTED;   // training composites only
+  if (!a.zs || !a.raw || !a.has_static_rgb) return NSFF_EUNSUPPORTED;   // training composites only (not sigma-only)
+  if (!a.has_transient) {
+    if (!grads->d_raw || a.raw_ld < 4) return NSFF_EINVAL;
+    composite_bwd_static_kernel<<<(unsigned)cdiv64(a.R, 4), 128, 0, (cudaStream_t)stream>>>(a, *grads);
+    return after_launch();
+  }
   const bool warp = a.raw_fw != nullptr;
   if (warp && (!a.raw_bw || !a.has_flow || a.raw_w_ld != 7)) return NSFF_EINVAL;
   if (a.has_flow && (!a.xyz || a.raw_ld < 14)) return NSFF_EINVAL;

@@ -137,7 +137,9 @@ _DISOCC_OUT = ["disocc_fw", "disoccs_fw", "disocc_bw", "disoccs_bw"]
 _SHAPES = {"depth": (), "transient_alpha": (), "static_only_depth": (), "disocc_fw": (1,), "disocc_bw": (1,)}
 
 
-def composite_outputs(has_flow, warp, disocc):
+def composite_outputs(has_flow, warp, disocc, transient=True):
+    if not transient:
+        return ["static_sigmas", "static_weights", "depth", "rgb"]
     names = list(_SAMPLE_OUT)
     if warp:
         names += _WARP_SAMPLE_OUT
@@ -156,10 +158,12 @@ def _composite_args(cfg, zs, xyz, noises, raw, raw_fw, raw_bw, xyz_fw, xyz_bw):
     a = _cabi.CompositeArgs()
     a.R, a.S = R, S
     a.zs, a.xyz, a.raw, a.raw_ld = zs.data_ptr(), xyz.data_ptr(), raw.data_ptr(), raw.shape[-1]
-    a.has_static_rgb, a.has_transient, a.has_flow = 1, 1, int(cfg["has_flow"])
+    a.has_static_rgb, a.has_transient, a.has_flow = 1, int(cfg.get("transient", True)), int(cfg["has_flow"])
     a.noise_std = float(cfg["noise_std"])
     if cfg["noise_std"] > 0:
-        a.noise_static, a.noise_trans = noises[0].data_ptr(), noises[1].data_ptr()
+        a.noise_static = noises[0].data_ptr()
+        if cfg.get("transient", True):
+            a.noise_trans = noises[1].data_ptr()
     if cfg["warp"]:
         a.raw_fw, a.raw_bw, a.raw_w_ld = raw_fw.data_ptr(), raw_bw.data_ptr(), 7
         a.xyz_fw, a.xyz_bw = xyz_fw.data_ptr(), xyz_bw.data_ptr()
@@ -175,7 +179,7 @@ class CompositeFn(torch.autograd.Function):
     def forward(ctx, cfg, zs, xyz, n_s, n_t, n_fw, n_bw, raw, raw_fw, raw_bw, xyz_fw, xyz_bw):
         R, S = zs.shape
         dev = zs.device
-        names = composite_outputs(cfg["has_flow"], cfg["warp"], cfg["disocc"])
+        names = composite_outputs(cfg["has_flow"], cfg["warp"], cfg["disocc"], cfg.get("transient", True))
         a = _composite_args(cfg, zs, xyz, (n_s, n_t, n_fw, n_bw), raw, raw_fw, raw_bw, xyz_fw, xyz_bw)
         outs = []
         for nm in names:
@@ -227,9 +231,6 @@ def field_pass_train(results, model, embeddings, xyz, zs, dirs, ts, max_t, want_
                      t_embedded, a_embedded):
     """Differentiable counterpart of rendering._field_pass for test_time=False (same keys, same order)."""
     from .nerf import NeRF
-    if not want_transient:
-        raise NotImplementedError("nsff_pl_b200: training a field without the transient branch is not built yet "
-                                  "(composite backward covers the static+transient composite)")
     typ = model.typ
     R, S = zs.shape
     B = R * S
@@ -239,6 +240,20 @@ def field_pass_train(results, model, embeddings, xyz, zs, dirs, ts, max_t, want_
     results[f"zs_{typ}"] = zs
     results[f"xyzs_{typ}"] = xyz
     zs_flat = zs.reshape(B)
+
+    if not want_transient:                                                 # static-only field (rendering.py:297-298)
+        mask = NeRF.out_mask(False, True, False, [])
+        raw = FieldFn.apply(model, mask, S, xyz.reshape(B, 3), None, a_embedded, dirs, zs_flat, *params).view(R, S, 4)
+        results[f"static_rgbs_{typ}"] = raw[..., :3]
+        n_s = torch.randn(R, S, **f32)
+        cfg = dict(has_flow=False, warp=False, disocc=False, noise_std=float(noise_std), transient=False)
+        o = dict(zip(composite_outputs(False, False, False, False),
+                     CompositeFn.apply(cfg, zs, xyz, n_s, None, None, None, raw.contiguous(), None, None, None, None)))
+        results[f"static_sigmas_{typ}"] = o["static_sigmas"]
+        results[f"static_weights_{typ}"] = o["static_weights"]
+        results[f"depth_{typ}"] = o["depth"]
+        results[f"rgb_{typ}"] = o["rgb"]
+        return
 
     def t_rows(shift):
         if shift == 0 and t_embedded is not None:

@@ -115,6 +115,26 @@ def test_no_flow_and_hierarchical_gradients_fp32():
     _check_grads(models, emb, specs, enc, tol=0.15)
 
 
+def test_static_only_field_gradients_fp32():
+    """A NeRF without the transient branch (reference config 1 in training mode): rgb / depth / weights / sigmas."""
+    from nsff_pl_b200.models.rendering import render_rays
+    models, emb, specs, enc = build_fields(W=256, transient=False, seed=9, precision="fp32")
+    models["fine"].requires_grad_(True)
+    rays, _ = synthetic_rays(10, seed=4)
+    res = render_rays(models, emb, rays.cuda(), None, 0, N_samples=40, test_time=False)
+    _loss(res).backward()
+    for k in specs["fine"].params:
+        specs["fine"].params[k] = specs["fine"].params[k].clone().requires_grad_(True)
+    want = O.render_rays(specs, enc, rays, None, 0, N_samples=40, test_time=False)
+    assert list(want.keys()) == list(res.keys())
+    _loss(want).backward()
+    for name, p in models["fine"].named_parameters():
+        ref = specs["fine"].params[name].grad.double()
+        got = p.grad.detach().cpu().double()
+        err = float((got - ref).norm() / (ref.norm() + 1e-12))
+        assert err <= 1e-2, f"{name}: {err:.3e}"
+
+
 def test_full_nsff_gradients_bf16_forward():
     models, emb, specs, enc, loss, loss_ref, _, _ = _run("bf16", 16, 64, TRAIN_KW, energise=False)
     assert abs(loss - loss_ref) <= 2e-2 * max(1.0, abs(loss_ref))
@@ -140,5 +160,5 @@ def test_training_step_reduces_the_loss():
         loss = ((res["rgb_fine"] - target) ** 2).mean() + 0.1 * ((res["rgb_fw"] - target) ** 2).mean()
         loss.backward()
         opt.step()                                   # bumps parameter versions -> the bf16 pack is rebuilt
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     assert losses[-1] < losses[0], losses
