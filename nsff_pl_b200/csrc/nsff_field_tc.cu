@@ -38,7 +38,7 @@ using namespace sm100;
 // ---------------------------------------------------------------------------------------------
 // pack layout (shared by nsff_field_pack_bytes / nsff_field_pack / the forward launcher)
 // ---------------------------------------------------------------------------------------------
-enum ChunkId : uint8_t { CH_H0 = 0, CH_H1, CH_H2, CH_H3, CH_PE, CH_T, CH_DIR, CH_NONE = 255 };
+enum ChunkId : uint8_t { CH_H0 = 0, CH_H1, CH_H2, CH_H3, CH_PE, CH_T, CH_DIR, CH_A, CH_NONE = 255 };
 enum LayerId {
   L_S1 = 0, L_S2, L_S3, L_S4, L_S5, L_S6, L_S7, L_S8, L_SSIG, L_SFIN, L_SDIR, L_SRGB,
   L_T1, L_T2, L_T3, L_T4, L_T5, L_T6, L_T7, L_T8, L_TFIN, L_THEAD, L_COUNT
@@ -68,7 +68,7 @@ struct PackLayout {
 static int build_layout(const nsff_field_desc& d, PackLayout& L) {
   if (d.W != 256 || d.D != 8 || d.skip != 4 || d.in_xyz != 63) return NSFF_EUNSUPPORTED;
   if (d.use_viewdir && d.in_dir != 27) return NSFF_EUNSUPPORTED;
-  if (d.in_a != 0) return NSFF_EUNSUPPORTED;   // appearance code: fp32 path only (for now)
+  if (d.in_a != 0 && (d.in_a != 48 || !d.use_viewdir)) return NSFF_EUNSUPPORTED;   // NeRF-W appearance code: 48 wide
   if (d.has_transient && d.in_t != 48) return NSFF_EUNSUPPORTED;
   memset(&L, 0, sizeof(L));
   uint32_t off = 0, boff = 0;
@@ -79,7 +79,7 @@ static int build_layout(const nsff_field_desc& d, PackLayout& L) {
     p.nchunks = 0;
     for (uint8_t c : chunks) {
       p.chunk[p.nchunks] = c;
-      p.kcnt[p.nchunks] = (c == CH_T) ? 3 : (c == CH_DIR) ? 2 : 4;
+      p.kcnt[p.nchunks] = (c == CH_T || c == CH_A) ? 3 : (c == CH_DIR) ? 2 : 4;
       ++p.nchunks;
     }
     p.w_off = off;
@@ -95,7 +95,10 @@ static int build_layout(const nsff_field_desc& d, PackLayout& L) {
   }
   add(L_SSIG, 16, {CH_H0, CH_H1, CH_H2, CH_H3});
   add(L_SFIN, 256, {CH_H0, CH_H1, CH_H2, CH_H3});
-  if (d.use_viewdir) add(L_SDIR, 256, {CH_DIR, CH_H0, CH_H1, CH_H2, CH_H3});
+  if (d.use_viewdir) {
+    if (d.in_a > 0) add(L_SDIR, 256, {CH_DIR, CH_A, CH_H0, CH_H1, CH_H2, CH_H3});
+    else add(L_SDIR, 256, {CH_DIR, CH_H0, CH_H1, CH_H2, CH_H3});
+  }
   add(L_SRGB, 16, {CH_H0, CH_H1, CH_H2, CH_H3});
   if (d.has_transient) {
     add(L_T1, 256, {CH_PE, CH_T});
@@ -157,7 +160,6 @@ constexpr int kEpiWarps = 16;        // 4 TMEM lane quadrants x 4 column parts: 
                                      // the TMEM-load / st.shared / proxy-fence latencies of the epilogue
 constexpr int kThreads = (kEpiWarps + 2) * 32;
 constexpr uint32_t kChunkBytes = 128 * 128;          // 128 rows x 64 bf16
-constexpr uint32_t kSmemA = 7 * kChunkBytes;         // 4 hidden + PE + T + DIR
 constexpr int kBiasSlots = 4;
 constexpr uint32_t kSmemBias = kBiasSlots * 1024;    // fp32 bias rows of the steps in flight
 constexpr uint32_t kSmemBar = 512;
@@ -168,10 +170,13 @@ constexpr int kMaxStages = 6;
 // kCtas = 2: CTA pair (cluster of 2, one TPC), cta_group::2 MMAs (M=256 = two tiles): each CTA stages only
 //            its half of every weight block (N/2 rows), so the L2->SM weight stream and the B-operand smem
 //            traffic halve and the ring holds twice as many K-chunks (6 stages of 16 KB).
-template <int kCtas>
+// kAppear: one more prologue chunk (the 48-wide NeRF-W appearance code feeding the dir layer), paid for with one
+//          ring stage.
+template <int kCtas, bool kAppear>
 struct Cfg {
-  static constexpr int kStages = kCtas == 1 ? 3 : 6;
+  static constexpr int kStages = kCtas == 1 ? (kAppear ? 2 : 3) : (kAppear ? 5 : 6);
   static constexpr uint32_t kStageBytes = (256 / kCtas) * 128;     // (N/kCtas) rows x 64 bf16
+  static constexpr uint32_t kSmemA = (kAppear ? 8 : 7) * kChunkBytes;   // 4 hidden + PE + T + DIR (+ A)
   static constexpr uint32_t kSmemB = kStages * kStageBytes;
   static constexpr uint32_t kSmemTotal = kSmemA + kSmemB + kSmemBias + kSmemBar + 1024;   // + alignment slack
 };
@@ -200,7 +205,7 @@ struct FwdParams {
   int32_t out_ld;
   int32_t n_steps;
   int32_t n_tiles;
-  int32_t need_t, need_dir;
+  int32_t need_t, need_dir, need_a, c_a;
   int32_t last_extra_step;  // last step whose K-chunks include PE / time code / PE(dir): after its MMAs the three
                             // prologue chunks are dead and the NEXT tile's prologue can be written early
   float flow_scale;
@@ -333,6 +338,16 @@ __device__ __forceinline__ void encode_tile_row(const FwdParams& P, uint32_t sA,
         store_unit(chT, row, part * 2 + u, v);
       }
     }
+    if (P.need_a && part < 3) {
+      const int64_t arow = P.pts.a_index ? P.pts.a_index[ray] : ray;
+      const float4* ap = reinterpret_cast<const float4*>(P.pts.a_table + arow * 48) + part * 4;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        float4 a = __ldg(ap + 2 * u), b = __ldg(ap + 2 * u + 1);
+        float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        store_unit(sA + CH_A * kChunkBytes, row, part * 2 + u, v);
+      }
+    }
     if (P.need_dir && part == 3) {
       float d[3] = {P.pts.dirs[ray * 3 + 0], P.pts.dirs[ray * 3 + 1], P.pts.dirs[ray * 3 + 2]};
       float sn[4][3], cs[4][3];
@@ -370,6 +385,15 @@ __device__ __forceinline__ void encode_tile_row(const FwdParams& P, uint32_t sA,
         store_unit(chT, row, part * 2 + u, v);
       }
     }
+    if (P.need_a && part < 3) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = xr[P.c_a + (part * 2 + u) * 8 + i];
+        store_unit(sA + CH_A * kChunkBytes, row, part * 2 + u, v);
+      }
+    }
     if (P.need_dir && part == 3) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -382,15 +406,15 @@ __device__ __forceinline__ void encode_tile_row(const FwdParams& P, uint32_t sA,
   }
 }
 
-template <int kCtas>
+template <int kCtas, bool kAppear>
 __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid_constant__ FwdParams P) {
-  using C = Cfg<kCtas>;
+  using C = Cfg<kCtas, kAppear>;
   constexpr int kStages = C::kStages;
   constexpr uint32_t kStageBytes = C::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;                       // 7 chunks
-  const uint32_t sB = smem_base + kSmemA;              // ring
+  const uint32_t sB = smem_base + C::kSmemA;           // ring
   const uint32_t sBias = sB + C::kSmemB;
   const uint32_t sBar = sBias + kSmemBias;
   const uint32_t sTmemPtr = sBar + BAR_COUNT * 8;
@@ -769,7 +793,11 @@ extern "C" int nsff_field_pack(const nsff_field_desc* desc, const nsff_field_par
   for (int h = 0; h < 4; ++h) wjob(L_SSIG, h, prm->static_sigma_w, 256, 0, 1, h * 64, 64);
   bjob(L_SSIG, 0, prm->static_sigma_b, 1);
   trunk_layer(L_SFIN, prm->static_final_w, prm->static_final_b, 256, 0, 0, nullptr);
-  if (desc->use_viewdir) trunk_layer(L_SDIR, prm->static_dir_w, prm->static_dir_b, 283, 0, 1, pre_dir);
+  const int pre_dir_a[2][2] = {{256, 27}, {283, 48}};
+  if (desc->use_viewdir) {
+    if (desc->in_a > 0) trunk_layer(L_SDIR, prm->static_dir_w, prm->static_dir_b, 283 + 48, 0, 2, pre_dir_a);
+    else trunk_layer(L_SDIR, prm->static_dir_w, prm->static_dir_b, 283, 0, 1, pre_dir);
+  }
   for (int h = 0; h < 4; ++h) wjob(L_SRGB, h, prm->static_rgb_w, 256, 0, 3, h * 64, 64);
   bjob(L_SRGB, 0, prm->static_rgb_b, 3);
   if (desc->has_transient) {   // nerf.py:93-116
@@ -832,6 +860,7 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
   };
   P.need_dir = 0;
   P.need_t = 0;
+  P.need_a = 0;
   if (want_s) {
     for (int i = L_S1; i <= L_S8; ++i) push(i, EPI_RELU_HID);
     if (sigma_only) {
@@ -845,6 +874,7 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
       if (d.use_viewdir) {
         push(L_SDIR, EPI_RELU_HID);
         P.need_dir = 1;
+        P.need_a = d.in_a > 0;
       }
       Step& rg = push(L_SRGB, EPI_HEAD);
       for (int i = 0; i < 3; ++i) rg.head_dst[i] = (int8_t)(col + i), rg.head_act[i] = HA_SIGMOID;
@@ -928,14 +958,15 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
     P.dbg = tl_dev;
   }
 #endif
-  if (ctas == 1) {
-    NSFF_CUDA_TRY(cudaFuncSetAttribute(field_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)Cfg<1>::kSmemTotal));
+  const bool appear = P.need_a != 0;
+  auto launch_single = [&](auto kern, uint32_t smem) -> int {
+    NSFF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = P.n_tiles < max_ctas ? P.n_tiles : max_ctas;
-    field_forward_kernel<1><<<grid, kThreads, Cfg<1>::kSmemTotal, st>>>(P);
-  } else {
-    NSFF_CUDA_TRY(cudaFuncSetAttribute(field_forward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)Cfg<2>::kSmemTotal));
+    kern<<<grid, kThreads, smem, st>>>(P);
+    return NSFF_OK;
+  };
+  auto launch_pair = [&](auto kern, uint32_t smem) -> int {
+    NSFF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int n_pairs = (P.n_tiles + 1) / 2;
     int clusters = max_ctas / 2;
     if (clusters < 1) clusters = 1;
@@ -943,7 +974,7 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters);
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = Cfg<2>::kSmemTotal;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -952,8 +983,18 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    NSFF_CUDA_TRY(cudaLaunchKernelEx(&cfg, field_forward_kernel<2>, P));
+    NSFF_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, P));
+    return NSFF_OK;
+  };
+  int lrc;
+  if (ctas == 1) {
+    lrc = appear ? launch_single(field_forward_kernel<1, true>, Cfg<1, true>::kSmemTotal)
+                 : launch_single(field_forward_kernel<1, false>, Cfg<1, false>::kSmemTotal);
+  } else {
+    lrc = appear ? launch_pair(field_forward_kernel<2, true>, Cfg<2, true>::kSmemTotal)
+                 : launch_pair(field_forward_kernel<2, false>, Cfg<2, false>::kSmemTotal);
   }
+  if (lrc != NSFF_OK) return lrc;
 #ifdef NSFF_TIMELINE
   if (tl_dev) {
     static int tl_seq = 0;
@@ -981,6 +1022,9 @@ extern "C" int nsff_field_forward(const nsff_field_desc* desc, const void* pack,
   if ((out_mask & NSFF_OUT_STATIC) && !(out_mask & NSFF_OUT_SIGMA_ONLY) && desc->use_viewdir && !pts->dirs)
     return NSFF_EINVAL;
   if (pts->t_table && ((uintptr_t)pts->t_table & 15u)) return NSFF_EINVAL;
+  if ((out_mask & NSFF_OUT_STATIC) && !(out_mask & NSFF_OUT_SIGMA_ONLY) && desc->use_viewdir && desc->in_a > 0 &&
+      (!pts->a_table || ((uintptr_t)pts->a_table & 15u)))
+    return NSFF_EINVAL;
   FwdParams P;
   memset(&P, 0, sizeof(P));
   P.pts = *pts;
@@ -1005,6 +1049,7 @@ extern "C" int nsff_field_forward_embedded(const nsff_field_desc* desc, const vo
     if (x_ld < desc->in_xyz + ((out_mask & NSFF_OUT_TRANSIENT) ? desc->in_t : 0)) return NSFF_EINVAL;
   } else {
     P.c_dir = desc->in_xyz;
+    P.c_a = desc->in_xyz + desc->in_dir;
     P.c_t = desc->in_xyz + desc->in_dir + desc->in_a;
     if (x_ld < desc->in_xyz + desc->in_dir + desc->in_a + ((out_mask & NSFF_OUT_TRANSIENT) ? desc->in_t : 0))
       return NSFF_EINVAL;

@@ -419,3 +419,17 @@ def test_interpolate_matches_oracle_and_reference_fixture():
     rgb_o, depth_o = O.interpolate(cpu(gt), cpu(gp), 0.4, K, c2w, (w, h))
     assert rgb.shape == (h, w, 3) and depth.shape == (h, w)
     assert max_abs(rgb, rgb_o) <= 2e-5 and max_abs(depth, depth_o) <= 2e-5
+
+
+def test_render_appearance_code_bf16_and_fp32():
+    """NeRF-W appearance code (encode_appearance=True, nerf.py:85-87): a 48-wide per-frame code joins the dir layer;
+    on the tensor-core path it is a fourth prologue chunk."""
+    for precision, tol, default in (("fp32", FP32_WARP_TOL, FP32_TOL), ("bf16", BF16_TOL, None)):
+        models, emb, specs, enc = build_fields(W=256, appearance=True, seed=19, precision=precision, n_frames=8)
+        rays, ts = synthetic_rays(40, n_frames=8, seed=6)
+        got, want = _run_both(models, emb, specs, enc, rays, ts, 7, N_samples=48, test_time=False,
+                              output_transient_flow=["fw", "bw", "disocc"])
+        compare_dicts(got, want, tol, default_tol=default)
+        got, want = _run_both(models, emb, specs, enc, rays, ts, 7, N_samples=48, test_time=True,
+                              a_embedded=torch.randn(40, 48))
+        compare_dicts(got, want, tol, default_tol=default)
