@@ -293,6 +293,17 @@ NSFF_API size_t nsff_interpolate_scratch_floats(int64_t R, int S);
 NSFF_API int nsff_interpolate(const nsff_interpolate_args* args /*host*/, float* scratch, float* rgb /*(h,w,3)*/,
                               float* depth /*(h,w)*/, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * f4  on-device ray generation                    datasets/ray_utils.py:7-106, monocular.py:268-276
+ *     nsff_frame_rays: all H*W NDC rays (o,d) of a pinhole frame in pixel order = get_ray_directions ->
+ *     get_rays (normalised) -> get_ndc_rays.  K4 = {fx, fy, cx, cy} and c2w12 = row-major 3x4, both HOST.
+ *     nsff_ndc_rays: get_ndc_rays alone on caller-provided world rays (near / shift_near scalars).
+ */
+NSFF_API int nsff_frame_rays(const float* K4 /*host*/, const float* c2w12 /*host*/, float near, float shift_near,
+                             int H, int W, float* rays /*(H*W,6)*/, void* stream);
+NSFF_API int nsff_ndc_rays(const float* K4 /*host*/, float near, float shift_near, const float* rays_o,
+                           const float* rays_d, int64_t n, float* out_o, float* out_d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

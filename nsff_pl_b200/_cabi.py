@@ -120,6 +120,10 @@ PROTOTYPES = {
     "nsff_composite_backward": (C.c_int, [C.POINTER(CompositeArgs), C.POINTER(CompositeGrads), C.c_void_p]),
     "nsff_interpolate_scratch_floats": (C.c_size_t, [C.c_int64, C.c_int]),
     "nsff_interpolate": (C.c_int, [C.POINTER(InterpolateArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsff_frame_rays": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_void_p]),
+    "nsff_ndc_rays": (C.c_int, [C.POINTER(C.c_float), C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int64,
+                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsff_visibility": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.c_void_p, C.c_int, C.c_int,
                                   C.c_int, C.c_void_p, C.c_void_p]),
     "nsff_composite": (C.c_int, [C.POINTER(CompositeArgs), C.c_void_p]),

@@ -167,3 +167,81 @@ int nsff_visibility(const float* xyz, int64_t B, const float* K, const float* w2
 }
 
 }  // extern "C"
+
+// ---- f4: on-device ray generation ----------------------------------------------------------------
+// datasets/ray_utils.py:7-106 (get_ray_directions -> get_rays -> get_ndc_rays) as used for a test frame by
+// datasets/monocular.py:268-276: pixel (i, j) -> camera direction ((i-cx)/fx, -(j-cy)/fy, -1) -> world ray
+// (normalised) from the camera centre -> NDC ray.  One thread per pixel, 24 B written per ray.
+namespace nsff {
+struct FrameCam {
+  float fx, fy, cx, cy;
+  float c2w[12];
+  float near, shift_near;
+};
+
+__device__ __forceinline__ void ndc_ray(const FrameCam& c, const float (&o_in)[3], const float (&d)[3], float* out) {
+  // ray_utils.py:85-104
+  const float t = -(c.shift_near + o_in[2]) / d[2];
+  const float o[3] = {o_in[0] + t * d[0], o_in[1] + t * d[1], o_in[2] + t * d[2]};
+  const float ox_oz = o[0] / o[2], oy_oz = o[1] / o[2];
+  const float sx = -1.f / (c.cx / c.fx), sy = -1.f / (c.cy / c.fy);
+  const float o2 = 1.f + 2.f * c.near / o[2];
+  out[0] = sx * ox_oz;
+  out[1] = sy * oy_oz;
+  out[2] = o2;
+  out[3] = sx * (d[0] / d[2] - ox_oz);
+  out[4] = sy * (d[1] / d[2] - oy_oz);
+  out[5] = 1.f - o2;
+}
+
+__global__ void frame_rays_kernel(FrameCam c, int H, int W, float* __restrict__ rays) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)H * W) return;
+  const int j = (int)(idx / W), i = (int)(idx - (int64_t)j * W);
+  const float dc[3] = {((float)i - c.cx) / c.fx, -((float)j - c.cy) / c.fy, -1.f};
+  float d[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) d[r] = dc[0] * c.c2w[r * 4 + 0] + dc[1] * c.c2w[r * 4 + 1] + dc[2] * c.c2w[r * 4 + 2];
+  const float inv = 1.f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  d[0] *= inv; d[1] *= inv; d[2] *= inv;
+  const float o[3] = {c.c2w[3], c.c2w[7], c.c2w[11]};
+  ndc_ray(c, o, d, rays + idx * 6);
+}
+
+__global__ void ndc_rays_kernel(FrameCam c, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                int64_t n, float* __restrict__ out_o, float* __restrict__ out_d) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const float o[3] = {rays_o[idx * 3], rays_o[idx * 3 + 1], rays_o[idx * 3 + 2]};
+  const float d[3] = {rays_d[idx * 3], rays_d[idx * 3 + 1], rays_d[idx * 3 + 2]};
+  float r[6];
+  ndc_ray(c, o, d, r);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    out_o[idx * 3 + k] = r[k];
+    out_d[idx * 3 + k] = r[3 + k];
+  }
+}
+}  // namespace nsff
+
+extern "C" int nsff_frame_rays(const float* K4, const float* c2w12, float near, float shift_near, int H, int W,
+                               float* rays, void* stream) {
+  if (!K4 || !c2w12 || !rays || H < 1 || W < 1) return NSFF_EINVAL;
+  nsff::FrameCam c;
+  c.fx = K4[0]; c.fy = K4[1]; c.cx = K4[2]; c.cy = K4[3];
+  for (int i = 0; i < 12; ++i) c.c2w[i] = c2w12[i];
+  c.near = near; c.shift_near = shift_near;
+  nsff::frame_rays_kernel<<<(unsigned)nsff::cdiv64((int64_t)H * W, 256), 256, 0, (cudaStream_t)stream>>>(c, H, W, rays);
+  return nsff::after_launch();
+}
+
+extern "C" int nsff_ndc_rays(const float* K4, float near, float shift_near, const float* rays_o, const float* rays_d,
+                             int64_t n, float* out_o, float* out_d, void* stream) {
+  if (!K4 || n < 0 || (n > 0 && (!rays_o || !rays_d || !out_o || !out_d))) return NSFF_EINVAL;
+  if (n == 0) return NSFF_OK;
+  nsff::FrameCam c = {};
+  c.fx = K4[0]; c.fy = K4[1]; c.cx = K4[2]; c.cy = K4[3];
+  c.near = near; c.shift_near = shift_near;
+  nsff::ndc_rays_kernel<<<(unsigned)nsff::cdiv64(n, 256), 256, 0, (cudaStream_t)stream>>>(c, rays_o, rays_d, n, out_o, out_d);
+  return nsff::after_launch();
+}

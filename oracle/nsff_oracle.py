@@ -491,3 +491,24 @@ def interpolate(results_t, results_tp1, dt, K, c2w, img_wh):
         depth += (1 - acc[..., 3]) * c_a[..., 0] * zs[..., s]
         acc[..., 3:] += (1 - acc[..., 3:]) * c_a
     return acc[..., :3], depth
+
+
+# --------------------------------------------------------------------------
+# ray generation for a test frame (datasets/ray_utils.py:7-106, monocular.py:268-276)
+# --------------------------------------------------------------------------
+def frame_rays(H: int, W: int, K: torch.Tensor, c2w: torch.Tensor, near: float = 1.0) -> torch.Tensor:
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    dirs = torch.stack([(xs - cx) / fx, -(ys - cy) / fy, -torch.ones_like(xs)], -1).reshape(-1, 3)   # :27-29
+    rays_d = dirs @ c2w[:, :3].T                                                                       # :50-54
+    rays_d = rays_d / torch.norm(rays_d, dim=-1, keepdim=True)
+    rays_o = c2w[:, 3].expand_as(rays_d)
+    shift_near = -min(-1.0, float(c2w[2, 3]))                                                          # monocular.py:270
+    t = -(shift_near + rays_o[..., 2]) / rays_d[..., 2]                                                # :88-104
+    rays_o = rays_o + t[..., None] * rays_d
+    ox_oz, oy_oz = rays_o[..., 0] / rays_o[..., 2], rays_o[..., 1] / rays_o[..., 2]
+    o0, o1 = -1. / (cx / fx) * ox_oz, -1. / (cy / fy) * oy_oz
+    o2 = 1. + 2. * near / rays_o[..., 2]
+    d0 = -1. / (cx / fx) * (rays_d[..., 0] / rays_d[..., 2] - ox_oz)
+    d1 = -1. / (cy / fy) * (rays_d[..., 1] / rays_d[..., 2] - oy_oz)
+    return torch.cat([torch.stack([o0, o1, o2], -1), torch.stack([d0, d1, 1 - o2], -1)], 1)

@@ -291,6 +291,22 @@ def main():
     arrays["K"], arrays["c2w"] = K_i.numpy(), c2w_i.numpy()
     save("interpolate_w64", dict(img_wh=[wi, hi], dts=[0.0, 0.3, 0.75], keys=list(keys)), arrays)
 
+    # ---- 2d. test-frame ray generation (ray_utils.py:7-106 composed as monocular.py:268-276 does) ----------
+    from datasets import ray_utils as ref_ru
+    wr, hr = 16, 9
+    ds_r = FakeDataset(n_frames=N_FRAMES, n_cams=1, img_wh=(wr, hr), seed=5)
+    arrays = {"K": ds_r.Ks[0].numpy()}
+    for pi in range(3):
+        c2w_r = torch.tensor(ds_r.poses[pi]).clone()
+        if pi == 2:
+            c2w_r[2, 3] = -1.7                                  # camera behind z=-1: shift_near = 1.7 branch
+        dirs = ref_ru.get_ray_directions(hr, wr, ds_r.Ks[0])
+        ro, rd = ref_ru.get_rays(dirs, c2w_r)
+        shift_near = -min(-1.0, float(c2w_r[2, 3]))
+        ro, rd = ref_ru.get_ndc_rays(ds_r.Ks[0], 1.0, shift_near, ro, rd)
+        arrays[f"c2w.{pi}"], arrays[f"rays.{pi}"] = c2w_r.numpy(), torch.cat([ro, rd], 1).numpy()
+    save("frame_rays", dict(img_wh=[wr, hr], n=3, near=1.0), arrays)
+
     # ---- 3. full-width network (the shape the CUDA path is built for) ----------
     # weights are NOT stored (4.9 MB each); they are re-created from the seed and
     # guarded by a checksum so a different torch RNG is detected, not mis-compared.

@@ -433,3 +433,35 @@ def test_render_appearance_code_bf16_and_fp32():
         got, want = _run_both(models, emb, specs, enc, rays, ts, 7, N_samples=48, test_time=True,
                               a_embedded=torch.randn(40, 48))
         compare_dicts(got, want, tol, default_tol=default)
+
+
+@pytest.mark.gpu
+def test_frame_rays_on_device_match_reference_fixture_and_oracle():
+    """f4: rays built on the device (one kernel) vs the reference's CPU ray_utils output (fixture) and, at the
+    benchmark frame size, vs the oracle; the NDC invariant o_z + d_z == 1 holds for every ray."""
+    from nsff_pl_b200.datasets import ray_utils as RU
+    meta, a = golden_io.load("frame_rays")
+    w, h = meta["img_wh"]
+    K = torch.as_tensor(a["K"])
+    for i in range(meta["n"]):
+        got = RU.frame_rays(h, w, K, a[f"c2w.{i}"], near=meta["near"]).cpu()
+        ref = torch.as_tensor(a[f"rays.{i}"])
+        assert max_abs(got, ref) <= 2e-6 * float(ref.abs().max()), (i, max_abs(got, ref))
+    ds = FakeDataset(n_frames=4, n_cams=1, img_wh=(512, 288), seed=3)
+    c2w = torch.tensor(ds.poses[1])
+    got = RU.frame_rays(288, 512, ds.Ks[0], c2w)
+    ref = O.frame_rays(288, 512, ds.Ks[0], c2w)
+    assert got.shape == (288 * 512, 6)
+    assert max_abs(got.cpu(), ref) <= 2e-6 * float(ref.abs().max())
+    assert float((got[:, 2] + got[:, 5] - 1).abs().max()) < 1e-6
+    # get_ndc_rays alone on arbitrary world rays
+    g = torch.Generator().manual_seed(4)
+    ro = torch.randn(1000, 3, generator=g) * 0.1
+    rd = torch.nn.functional.normalize(torch.randn(1000, 3, generator=g) * 0.3 + torch.tensor([0., 0., -1.]), dim=-1)
+    o_d, d_d = RU.get_ndc_rays(ds.Ks[0], 1.0, 1.0, ro.cuda(), rd.cuda())
+    fx, fy, cx, cy = ds.Ks[0][0, 0], ds.Ks[0][1, 1], ds.Ks[0][0, 2], ds.Ks[0][1, 2]
+    t = -(1.0 + ro[:, 2]) / rd[:, 2]
+    o = ro + t[:, None] * rd
+    o_ref = torch.stack([-1 / (cx / fx) * o[:, 0] / o[:, 2], -1 / (cy / fy) * o[:, 1] / o[:, 2], 1 + 2 / o[:, 2]], -1)
+    assert max_abs(o_d.cpu(), o_ref) < 1e-5
+    assert float((o_d[:, 2] + d_d[:, 2] - 1).abs().max()) < 1e-6

@@ -166,3 +166,12 @@ def test_full_width_seeded_case():
     assert list(got.keys()) == meta["result_keys"]
     for k, v in golden_io.expected(a).items():
         _close(k, got[k], v)
+
+
+def test_frame_rays_matches_reference():
+    """ray_utils.py get_ray_directions -> get_rays -> get_ndc_rays, composed as monocular.py:268-276 does."""
+    meta, a = golden_io.load("frame_rays")
+    w, h = meta["img_wh"]
+    for i in range(meta["n"]):
+        got = O.frame_rays(h, w, torch.as_tensor(a["K"]), torch.as_tensor(a[f"c2w.{i}"]), near=meta["near"])
+        assert torch.equal(got, torch.as_tensor(a[f"rays.{i}"])), i
