@@ -191,6 +191,50 @@ NSFF_API int nsff_field_backward_fp32(const nsff_field_desc* desc /*host*/, cons
                                       float* d_pos, float* d_t, float* d_a, float* scratch, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * b   tensor-core backward of the field           torch autograd of models/nerf.py:118-213 (train.py:178-198)
+ *     Same contract as nsff_field_backward_fp32 (gradients ACCUMULATE into `grads`; d_pos / d_t / d_a are overwritten),
+ *     but every GEMM (forward recompute, dgrad, wgrad) runs as bf16 tcgen05 MMAs with fp32 accumulation over
+ *     activations kept in HBM as 128-byte-swizzled "tile images" ([128-point tile][64-column chunk][128 x 128 B]).
+ *     `pack` = nsff_field_bwd_tc_pack of the CURRENT parameters (W and W^T blocks); `params` supplies the fp32 biases.
+ */
+NSFF_API size_t nsff_field_bwd_tc_pack_bytes(const nsff_field_desc* desc /*host*/);
+NSFF_API int nsff_field_bwd_tc_pack(const nsff_field_desc* desc /*host*/, const nsff_field_params* params /*host*/,
+                                    void* pack, void* stream);
+NSFF_API size_t nsff_field_bwd_tc_scratch_bytes(const nsff_field_desc* desc /*host*/, int64_t B);
+NSFF_API int nsff_field_backward_tc(const nsff_field_desc* desc /*host*/, const nsff_field_params* params /*host*/,
+                                    const void* pack, const nsff_points* pts /*host*/, int out_mask, const float* out,
+                                    const float* d_out, int32_t out_ld, const nsff_field_grads* grads /*host*/,
+                                    float* d_pos, float* d_t, float* d_a, void* scratch, void* stream);
+
+/* The two GEMM kernels of that backward, exposed for hosts that keep their own tile images (and for the unit tests).
+ * Image = [ceil(n_rows/128) tiles][chunks][128 rows x 64 bf16, 128B swizzle]; weight block = [N rows x 64 bf16], same
+ * swizzle (nsff_img_pack_weight: blk[n][k] = transpose ? src[(k0+k)*ld + n0+n] : src[(n0+n)*ld + k0+k], zero padded). */
+NSFF_API size_t nsff_img_bytes(int64_t n_rows, int n_chunks);
+NSFF_API int nsff_img_from_rows(const float* src, int32_t ld, int32_t col0, int32_t ncols, int64_t n_rows, void* img,
+                                int32_t img_chunks, int32_t chunk, void* stream);
+NSFF_API int nsff_img_to_rows(const void* img, int32_t img_chunks, int32_t chunk, float* dst, int32_t ld, int32_t col0,
+                              int32_t ncols, int64_t n_rows, void* stream);
+NSFF_API int nsff_img_pack_weight(const float* src, int32_t ld, int32_t transpose, int32_t n0, int32_t k0,
+                                  int32_t n_valid, int32_t k_valid, int32_t N, void* block, void* stream);
+typedef struct {
+  const void* a_img; int32_t a_chunks;   /* A: (n_rows, 64*a_chunks), every chunk is a K chunk                    */
+  const void* b_blocks; int32_t N;       /* a_chunks weight blocks of N x 64 (N = 64, 128 or 256)                 */
+  const float* bias;                     /* N floats or NULL                                                      */
+  int32_t epi;                           /* 0 relu->image, 1 linear->image, 2 relu-mask->image, 3 fp32 rows       */
+  void* out_img; const void* mask_img;   /* N/64 chunks per tile                                                  */
+  float* out_rows; int32_t ld, ncols, beta; /* epi 3: out_rows[r*ld + c] (+)= acc, c < ncols                       */
+  int64_t n_rows;
+} nsff_img_gemm_args;
+NSFF_API int nsff_img_gemm(const nsff_img_gemm_args* args /*host*/, void* stream);
+typedef struct {
+  const void* a_img;                     /* (n_rows, 256): 4 chunks                                               */
+  const void* b_img; int32_t b_chunks;   /* (n_rows, 64*b_chunks), 1..4 chunks                                    */
+  int64_t n_rows;
+  float* acc_t;                          /* (64*b_chunks, 256) fp32: acc_t[n*256 + m] += sum_r B[r,n] A[r,m]      */
+} nsff_img_wgrad_args;
+NSFF_API int nsff_img_wgrad(const nsff_img_wgrad_args* args /*host*/, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * a8  eval-only camera visibility                rendering.py:190-200, ray_utils.py:127-181
  *     vis[p] = number of cameras whose image contains the world-space projection of NDC point p.
  *     w2c: (n_cams, 12) row-major 3x4 world-to-camera matrices (inverse of the c2w poses).

@@ -92,6 +92,18 @@ class InterpolateArgs(C.Structure):
                 ("rgb_tp1", C.c_void_p), ("alpha_tp1", C.c_void_p), ("flow_bw", C.c_void_p), ("ld_tp1", C.c_int32)]
 
 
+class ImgGemmArgs(C.Structure):
+    _fields_ = [("a_img", C.c_void_p), ("a_chunks", C.c_int32), ("b_blocks", C.c_void_p), ("N", C.c_int32),
+                ("bias", C.c_void_p), ("epi", C.c_int32), ("out_img", C.c_void_p), ("mask_img", C.c_void_p),
+                ("out_rows", C.c_void_p), ("ld", C.c_int32), ("ncols", C.c_int32), ("beta", C.c_int32),
+                ("n_rows", C.c_int64)]
+
+
+class ImgWgradArgs(C.Structure):
+    _fields_ = [("a_img", C.c_void_p), ("b_img", C.c_void_p), ("b_chunks", C.c_int32), ("n_rows", C.c_int64),
+                ("acc_t", C.c_void_p)]
+
+
 # name -> (restype, argtypes); also the list tests/test_cabi_symbols.py checks against the header
 PROTOTYPES = {
     "nsff_abi_version": (C.c_int, []),
@@ -117,6 +129,21 @@ PROTOTYPES = {
     "nsff_field_backward_fp32": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(FieldParams), C.POINTER(Points), C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(FieldGrads), C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsff_field_bwd_tc_pack_bytes": (C.c_size_t, [C.POINTER(FieldDesc)]),
+    "nsff_field_bwd_tc_pack": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(FieldParams), C.c_void_p, C.c_void_p]),
+    "nsff_field_bwd_tc_scratch_bytes": (C.c_size_t, [C.POINTER(FieldDesc), C.c_int64]),
+    "nsff_field_backward_tc": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(FieldParams), C.c_void_p, C.POINTER(Points),
+                                         C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(FieldGrads), C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsff_img_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
+    "nsff_img_from_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int32,
+                                     C.c_int32, C.c_void_p]),
+    "nsff_img_to_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_int64, C.c_void_p]),
+    "nsff_img_pack_weight": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_int32, C.c_void_p, C.c_void_p]),
+    "nsff_img_gemm": (C.c_int, [C.POINTER(ImgGemmArgs), C.c_void_p]),
+    "nsff_img_wgrad": (C.c_int, [C.POINTER(ImgWgradArgs), C.c_void_p]),
     "nsff_composite_backward": (C.c_int, [C.POINTER(CompositeArgs), C.POINTER(CompositeGrads), C.c_void_p]),
     "nsff_interpolate_scratch_floats": (C.c_size_t, [C.c_int64, C.c_int]),
     "nsff_interpolate": (C.c_int, [C.POINTER(InterpolateArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -1,0 +1,1151 @@
+// Tensor-core backward of the NeRF field (autograd of models/nerf.py:118-213, reference train.py:178-198).
+//
+// Layer-wise bf16 GEMMs on tcgen05 with fp32 accumulation in TMEM.  Every activation / gradient plane lives in HBM
+// as a "tile image": [tile of 128 points][64-column chunk][128 rows x 128 B, 128-byte swizzled] - the exact shared
+// memory operand layout - so every operand load is ONE 1-D bulk copy (cp.async.bulk + mbarrier complete_tx), and the
+// SAME bytes serve both GEMM flavours:
+//   * img_gemm_kernel   out[P, N]   = epi( A[P, K] . B[N, K]^T )      A, B K-major   (forward recompute, dgrad)
+//   * img_wgrad_kernel  dW^T[N, M] += sum_p B[p, n] . A[p, m]         A, B MN-major  (wgrad: K = points)
+// The point tile that is a K-major A operand of the dgrad ([128 pts x 64 ch], rows = points) is, read as
+// "MN-major with K = points", exactly the canonical SWIZZLE_128B MN-major atom (64 MN elements contiguous, 8 K rows of
+// 128 B per 1024-B group): no transposed copy of any activation is ever made.
+//
+// Both kernels are HBM-bound at this shape (a 256x256 layer moves 134-200 MB per 131k points = 20-30 us, its MMAs take
+// 8 us), so they are written for streaming: weights resident in smem (img_gemm), deep bulk-copy rings, accumulators
+// double-buffered in TMEM so the epilogue of tile i overlaps the loads/MMAs of tile i+1.
+#include <cuda_bf16.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "nsff_common.cuh"
+#include "nsff_field_host.cuh"
+#include "nsff_sm100.cuh"
+
+#define TRY(expr)                   \
+  do {                              \
+    int _rc = (expr);               \
+    if (_rc != NSFF_OK) return _rc; \
+  } while (0)
+
+namespace nsff {
+namespace bwd {
+using namespace sm100;
+
+constexpr uint32_t kChunkBytes = 128 * 128;   // 128 rows x 64 bf16
+constexpr uint32_t kSmemLimit = 232448;       // 227 KB opt-in
+constexpr int kMaxK = 6;                      // K chunks of one GEMM
+
+__device__ __forceinline__ uint32_t row_off(int row) { return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128); }
+
+// ------------------------------------------------------------------------------------------------------------------
+// small image kernels
+// ------------------------------------------------------------------------------------------------------------------
+// fp32 row-major columns [col0, col0+ncols) -> one chunk of an image (zero padded to 64 columns / 128-row tiles)
+__global__ void rows_to_img_kernel(const float* __restrict__ src, int ld, int col0, int ncols, int64_t n_rows,
+                                   uint8_t* __restrict__ img, uint32_t tile_stride, int n_tiles) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // one thread per (row, 16-byte unit)
+  if (idx >= (int64_t)n_tiles * 128 * 8) return;
+  const int unit = (int)(idx & 7);
+  const int64_t r = idx >> 3;
+  const int row = (int)(r & 127);
+  const int64_t tile = r >> 7;
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float v[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = unit * 8 + i * 2 + j;
+      v[j] = (r < n_rows && c < ncols) ? src[r * ld + col0 + c] : 0.f;
+    }
+    w[i] = pack_bf16x2(v[0], v[1]);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(img + tile * tile_stride + row_off(row) + (((unit ^ row) & 7) << 4));
+  *dst = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__global__ void img_to_rows_kernel(const uint8_t* __restrict__ img, uint32_t tile_stride, float* __restrict__ dst,
+                                   int ld, int col0, int ncols, int64_t n_rows) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_rows * 64) return;
+  const int c = (int)(idx & 63);
+  const int64_t r = idx >> 6;
+  if (c >= ncols) return;
+  const int row = (int)(r & 127);
+  const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(img + (r >> 7) * tile_stride + row_off(row) +
+                                                                  ((((c >> 3) ^ row) & 7) << 4)) + (c & 7);
+  dst[r * ld + col0 + c] = __bfloat162float(*p);
+}
+
+// weight block [N rows x 64 cols] bf16, 128B-swizzled: blk[n][dk0 + k] = T ? src[(k0+k)*ld + n0+n] : src[(n0+n)*ld + k0+k]
+struct PackJob {
+  const float* src;
+  uint8_t* dst;
+  int32_t ld, transpose, n0, k0, n_valid, k_valid, dk0, dn0;
+};
+constexpr int kPackJobsPerLaunch = 64;
+struct PackJobs {
+  PackJob job[kPackJobsPerLaunch];
+};
+__global__ void pack_blocks_kernel(const __grid_constant__ PackJobs J) {
+  const PackJob& j = J.job[blockIdx.x];
+  const int total = j.n_valid * j.k_valid;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    int n, k;
+    if (j.transpose) n = e % j.n_valid, k = e / j.n_valid;     // consecutive threads walk the contiguous source dim
+    else k = e % j.k_valid, n = e / j.k_valid;
+    const float v = j.transpose ? j.src[(int64_t)(j.k0 + k) * j.ld + j.n0 + n] : j.src[(int64_t)(j.n0 + n) * j.ld + j.k0 + k];
+    const int row = j.dn0 + n, col = j.dk0 + k;
+    *reinterpret_cast<__nv_bfloat16*>(j.dst + row_off(row) + ((((col >> 3) ^ row) & 7) << 4) + (col & 7) * 2) =
+        __float2bfloat16_rn(v);
+  }
+}
+
+// column sums of an image -> db[c] += sum_rows   (bias gradients; pad rows are zero by construction)
+__global__ void __launch_bounds__(256) img_colsum_kernel(const uint8_t* __restrict__ img, uint32_t tile_stride,
+                                                         int n_chunks, int n_tiles, float* __restrict__ db) {
+  __shared__ float acc_s[64];
+  const int chunk = blockIdx.y;
+  if (threadIdx.x < 64) acc_s[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int unit = threadIdx.x & 7, rr = threadIdx.x >> 3;            // rr 0..31: (row & 7) is fixed per thread
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint8_t* base = img + (size_t)tile * tile_stride + (size_t)chunk * kChunkBytes;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int row = it * 32 + rr;
+      const uint4 q = *reinterpret_cast<const uint4*>(base + row_off(row) + (unit << 4));
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[2 * i] += __uint_as_float(w[i] << 16);
+        acc[2 * i + 1] += __uint_as_float(w[i] & 0xFFFF0000u);
+      }
+    }
+  }
+  const int logical = (unit ^ rr) & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) atomicAdd(&acc_s[logical * 8 + i], acc[i]);
+  __syncthreads();
+  if (threadIdx.x < 64 && chunk * 64 + threadIdx.x < n_chunks * 64) atomicAdd(db + chunk * 64 + threadIdx.x, acc_s[threadIdx.x]);
+}
+
+// pre-activation gradients of all head columns of one branch: fp32 (B,16) is not kept, only the bf16 image chunk
+// (columns >= n and rows >= B are zero) and the bias gradients.
+struct HeadSpec {
+  int8_t src[16];        // image column i <- column src[i] of out / d_out (-1: zero column)
+  uint8_t act[16];       // 0 identity, 1 sigmoid, 2 flow
+  float* db[16];         // where the bias gradient of column i accumulates (NULL = none)
+};
+__global__ void __launch_bounds__(128) heads_dpre_kernel(const float* __restrict__ d_out, const float* __restrict__ out,
+                                                         int ld, const __grid_constant__ HeadSpec H,
+                                                         const float* __restrict__ zs, float scale, int64_t B,
+                                                         uint8_t* __restrict__ img, uint32_t tile_stride) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per image row (incl. pad rows)
+  const int row = (int)(r & 127);
+  float g[16];
+  const bool valid = r < B;
+  const bool far = valid && zs && zs[r] > kZFar;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float v = 0.f;
+    if (valid && H.src[i] >= 0) {
+      const float go = d_out[r * ld + H.src[i]], y = out[r * ld + H.src[i]];
+      if (H.act[i] == 1) v = go * y * (1.f - y);
+      else if (H.act[i] == 2) {
+        const float t = y / scale;
+        v = far ? 0.f : go * scale * (1.f - t * t);
+      } else v = go;
+    }
+    g[i] = v;
+  }
+  uint8_t* rowp = img + (r >> 7) * tile_stride + row_off(row);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (u < 2) q = make_uint4(pack_bf16x2(g[u * 8], g[u * 8 + 1]), pack_bf16x2(g[u * 8 + 2], g[u * 8 + 3]),
+                              pack_bf16x2(g[u * 8 + 4], g[u * 8 + 5]), pack_bf16x2(g[u * 8 + 6], g[u * 8 + 7]));
+    *reinterpret_cast<uint4*>(rowp + (((u ^ row) & 7) << 4)) = q;
+  }
+  // bias gradients: warp reduce, one atomic per warp and column
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if (H.src[i] < 0) continue;      // uniform across the block
+    float s = g[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && H.db[i]) atomicAdd(H.db[i], s);
+  }
+}
+
+// scatter of a wgrad result: acc_t is [(64*nb) x 256] fp32 with acc_t[n*256 + m] = sum_p B[p,n] A[p,m].
+//   transposed mode (layers): dW[m*ldw + dcol0[j] + c] += acc_t[(64j + c)*256 + m]   for c < ncols[j]
+//   direct mode (heads, operands swapped): row n of acc_t is the gradient of head row n: dst[n][m] += acc_t[n*256 + m]
+struct FinishJob {
+  const float* acc_t;
+  float* dW;
+  int32_t ldw, nb, direct;
+  int32_t dcol0[4], ncols[4];
+  float* drow[16];           // direct mode: destination of acc_t row n (256 floats) or NULL
+};
+__global__ void wgrad_finish_kernel(const __grid_constant__ FinishJob J) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = idx >> 8, m = idx & 255;
+  if (J.direct) {
+    if (n < 16 && J.drow[n]) J.drow[n][m] += J.acc_t[n * 256 + m];
+    return;
+  }
+  if (n >= J.nb * 64) return;
+  const int j = n >> 6, c = n & 63;
+  if (c < J.ncols[j]) J.dW[(int64_t)m * J.ldw + J.dcol0[j] + c] += J.acc_t[n * 256 + m];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// img_gemm_kernel: K-major GEMM, weights resident in shared memory
+// ------------------------------------------------------------------------------------------------------------------
+enum GemmEpi : int32_t { GE_RELU_IMG = 0, GE_LIN_IMG = 1, GE_MASK_IMG = 2, GE_F32_ROWS = 3 };
+
+struct GemmParams {
+  const uint8_t* a_base[kMaxK];   // chunk c of tile t: a_base[c] + t * a_stride[c]
+  uint32_t a_stride[kMaxK];
+  uint8_t kcnt[8];                // K=16 MMAs issued from chunk c (1..4)
+  int32_t n_tiles, n_chunks, N, stages, epi;
+  const uint8_t* b_blocks;        // n_chunks blocks of N x 64 bf16
+  const float* bias;              // N floats or NULL
+  uint8_t* out_img;               // N/64 chunks per tile
+  uint32_t out_stride;
+  const uint8_t* mask_img;        // same geometry as out_img (GE_MASK_IMG): out = acc where mask > 0 else 0
+  uint32_t mask_stride;
+  float* out_f32;                 // GE_F32_ROWS: (n_rows, ld), columns [0, ncols)
+  int32_t ld, ncols, beta;
+  int64_t n_rows;
+};
+
+constexpr int kGemmEpiWarps = 8;
+constexpr int kGemmThreads = (kGemmEpiWarps + 2) * 32;
+constexpr int kGemmMaxStages = 8;
+enum { GB_B_FULL = 0, GB_A_FULL = 1, GB_A_EMPTY = GB_A_FULL + kGemmMaxStages, GB_ACC_FULL = GB_A_EMPTY + kGemmMaxStages,
+       GB_ACC_EMPTY = GB_ACC_FULL + 2, GB_COUNT = GB_ACC_EMPTY + 2 };
+constexpr uint32_t kGemmAux = 1024 /*bias*/ + 256 /*barriers + tmem ptr*/;
+
+__global__ void __launch_bounds__(kGemmThreads, 1) img_gemm_kernel(const __grid_constant__ GemmParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t blk_bytes = (uint32_t)P.N * 128u;
+  const uint32_t sB = base;
+  const uint32_t sA = sB + (uint32_t)P.n_chunks * blk_bytes;
+  const uint32_t sBias = sA + (uint32_t)P.stages * kChunkBytes;
+  const uint32_t sBar = sBias + 1024;
+  const uint32_t sTmemPtr = sBar + GB_COUNT * 8;
+  auto bar = [&](int i) { return sBar + (uint32_t)i * 8u; };
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (sBias - raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar(GB_B_FULL), 1);
+    for (int i = 0; i < kGemmMaxStages; ++i) {
+      mbar_init(bar(GB_A_FULL + i), 1);
+      mbar_init(bar(GB_A_EMPTY + i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(GB_ACC_FULL + i), 1);
+      mbar_init(bar(GB_ACC_EMPTY + i), kGemmEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kGemmEpiWarps + 1) tmem_alloc(sTmemPtr, 512);
+  for (int i = threadIdx.x; i < P.N; i += blockDim.x) bias_s[i] = P.bias ? P.bias[i] : 0.f;
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sTmemPtr));
+
+  if (warp == kGemmEpiWarps) {
+    // ===== producer: weights once, then the A chunks of this CTA's tiles through the ring =====
+    if (elect_one()) {
+      mbar_arrive_expect_tx(bar(GB_B_FULL), (uint32_t)P.n_chunks * blk_bytes);
+      for (int c = 0; c < P.n_chunks; ++c)
+        bulk_g2s(sB + (uint32_t)c * blk_bytes, P.b_blocks + (size_t)c * blk_bytes, blk_bytes, bar(GB_B_FULL));
+      uint32_t stage = 0, par = 1;
+      for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        for (int c = 0; c < P.n_chunks; ++c) {
+          mbar_wait(bar(GB_A_EMPTY + stage), par);
+          mbar_arrive_expect_tx(bar(GB_A_FULL + stage), kChunkBytes);
+          bulk_g2s(sA + stage * kChunkBytes, P.a_base[c] + (size_t)tile * P.a_stride[c], kChunkBytes,
+                   bar(GB_A_FULL + stage));
+          if (++stage == (uint32_t)P.stages) stage = 0, par ^= 1u;
+        }
+      }
+    }
+  } else if (warp == kGemmEpiWarps + 1) {
+    // ===== MMA issuer =====
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(128, (uint32_t)P.N);
+      mbar_wait(bar(GB_B_FULL), 0);
+      uint32_t stage = 0, par = 0, local = 0;
+      for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++local) {
+        const uint32_t slot = local & 1u, use = local >> 1;
+        mbar_wait(bar(GB_ACC_EMPTY + slot), (use & 1u) ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + slot * 256u;
+        for (int c = 0; c < P.n_chunks; ++c) {
+          mbar_wait(bar(GB_A_FULL + stage), par);
+          tc_fence_after_sync();
+          const uint32_t a0 = sA + stage * kChunkBytes, b0 = sB + (uint32_t)c * blk_bytes;
+          const int kc = P.kcnt[c];
+          for (int k = 0; k < kc; ++k)
+            mma_bf16_ss(d_tmem, make_desc_k128(a0 + (uint32_t)k * 32u), make_desc_k128(b0 + (uint32_t)k * 32u), idesc,
+                        (c | k) != 0);
+          mma_commit(bar(GB_A_EMPTY + stage));
+          if (++stage == (uint32_t)P.stages) stage = 0, par ^= 1u;
+        }
+        mma_commit(bar(GB_ACC_FULL + slot));
+      }
+    }
+  } else {
+    // ===== epilogue: warp (q, half) drains rows 32q.. of columns [half*N/2, (half+1)*N/2) =====
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t roff = row_off(row);
+    const int rsw = row & 7;
+    const int c_begin = half * (P.N / 2), c_end = c_begin + P.N / 2;
+    uint32_t local = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++local) {
+      const uint32_t slot = local & 1u, use = local >> 1;
+      mbar_wait(bar(GB_ACC_FULL + slot), use & 1u);
+      tc_fence_after_sync();
+      const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 256u;
+      const int64_t p = (int64_t)tile * 128 + row;
+      for (int cb = c_begin; cb < c_end; cb += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_acc + (uint32_t)cb, v);
+        tmem_ld_wait();
+        if (P.epi == GE_F32_ROWS) {
+          if (p < P.n_rows) {
+            float* o = P.out_f32 + p * P.ld;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int col = cb + i;
+              if (col < P.ncols) {
+                const float x = __uint_as_float(v[i]) + bias_s[col];
+                o[col] = P.beta ? o[col] + x : x;
+              }
+            }
+          }
+        } else {
+          const size_t off = (size_t)tile * P.out_stride + (size_t)(cb >> 6) * kChunkBytes + roff;
+          const int unit0 = (cb & 63) >> 3;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[u * 8 + i]) + bias_s[cb + u * 8 + i];
+            const uint32_t uo = (uint32_t)(((unit0 + u) ^ rsw) & 7) << 4;
+            uint4 w;
+            if (P.epi == GE_RELU_IMG) {
+              w = make_uint4(pack_bf16x2_relu(f[0], f[1]), pack_bf16x2_relu(f[2], f[3]), pack_bf16x2_relu(f[4], f[5]),
+                             pack_bf16x2_relu(f[6], f[7]));
+            } else {
+              w = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                             pack_bf16x2(f[6], f[7]));
+              if (P.epi == GE_MASK_IMG) {
+                // ReLU mask: the stored activation is max(x,0) in bf16, so "> 0" == "any magnitude bit set"
+                const uint4 mk = *reinterpret_cast<const uint4*>(P.mask_img + (size_t)tile * P.mask_stride +
+                                                                 (size_t)(cb >> 6) * kChunkBytes + roff + uo);
+                auto sel = [](uint32_t x, uint32_t m) {
+                  return x & (((m & 0x7FFFu) ? 0xFFFFu : 0u) | ((m & 0x7FFF0000u) ? 0xFFFF0000u : 0u));
+                };
+                w.x = sel(w.x, mk.x); w.y = sel(w.y, mk.y); w.z = sel(w.z, mk.z); w.w = sel(w.w, mk.w);
+              }
+            }
+            *reinterpret_cast<uint4*>(P.out_img + off + uo) = w;
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(GB_ACC_EMPTY + slot));
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kGemmEpiWarps + 1) {
+    tc_fence_after_sync();
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// img_wgrad_kernel: both operands MN-major (K = points), split over the point range, fp32 RED into acc_t
+// ------------------------------------------------------------------------------------------------------------------
+struct WgradParams {
+  const uint8_t* a_base;          // 4 chunks (M = 256 channels)
+  uint32_t a_stride;
+  const uint8_t* b_base[4];       // nb chunks (N = 64*nb channels)
+  uint32_t b_stride[4];
+  int32_t nb, n_tiles, variant;
+  float* acc_t;                   // [(64*nb) x 256]
+};
+constexpr int kWgEpiWarps = 8;
+constexpr int kWgThreads = (kWgEpiWarps + 2) * 32;
+constexpr int kWgStages = 3;
+constexpr uint32_t kHalfChunk = 8192;                 // 64 points x 128 B
+constexpr uint32_t kWgStageBytes = 8 * kHalfChunk;    // 4 A + up to 4 B half chunks
+enum { WB_FULL = 0, WB_EMPTY = WB_FULL + kWgStages, WB_ACC = WB_EMPTY + kWgStages, WB_COUNT };
+constexpr uint32_t kWgSmem = kWgStages * kWgStageBytes + 256 + 1024;
+
+// Shared-memory descriptor, MN-major operand, 128-byte swizzle (canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in
+// 16-byte units): 64 MN elements contiguous; LBO = byte distance between 64-element MN groups; SBO = byte distance
+// between groups of 8 K rows.
+__device__ __forceinline__ uint64_t make_desc_mn128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1u << 46;
+  d |= (uint64_t)2u << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1) img_wgrad_kernel(const __grid_constant__ WgradParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sBar = base + kWgStages * kWgStageBytes;
+  const uint32_t sTmemPtr = sBar + WB_COUNT * 8;
+  auto bar = [&](int i) { return sBar + (uint32_t)i * 8u; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // contiguous tile range of this CTA
+  const int t0 = (int)((int64_t)P.n_tiles * blockIdx.x / gridDim.x);
+  const int t1 = (int)((int64_t)P.n_tiles * (blockIdx.x + 1) / gridDim.x);
+  const int n_half = (t1 - t0) * 2;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWgStages; ++i) {
+      mbar_init(bar(WB_FULL + i), 1);
+      mbar_init(bar(WB_EMPTY + i), 1);
+    }
+    mbar_init(bar(WB_ACC), 1);
+    fence_mbar_init();
+  }
+  if (warp == kWgEpiWarps + 1) tmem_alloc(sTmemPtr, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sTmemPtr));
+  const uint32_t N = (uint32_t)P.nb * 64u;
+
+  if (n_half > 0) {
+    if (warp == kWgEpiWarps) {
+      if (elect_one()) {
+        uint32_t stage = 0, par = 1;
+        const uint32_t bytes = (4u + (uint32_t)P.nb) * kHalfChunk;
+        for (int h = 0; h < n_half; ++h) {
+          const size_t tile = (size_t)(t0 + (h >> 1));
+          const size_t hoff = (size_t)(h & 1) * kHalfChunk;
+          mbar_wait(bar(WB_EMPTY + stage), par);
+          mbar_arrive_expect_tx(bar(WB_FULL + stage), bytes);
+          const uint32_t s0 = base + stage * kWgStageBytes;
+          for (int c = 0; c < 4; ++c)
+            bulk_g2s(s0 + (uint32_t)c * kHalfChunk, P.a_base + tile * P.a_stride + (size_t)c * kChunkBytes + hoff,
+                     kHalfChunk, bar(WB_FULL + stage));
+          for (int j = 0; j < P.nb; ++j)
+            bulk_g2s(s0 + (uint32_t)(4 + j) * kHalfChunk, P.b_base[j] + tile * P.b_stride[j] + hoff, kHalfChunk,
+                     bar(WB_FULL + stage));
+          if (++stage == kWgStages) stage = 0, par ^= 1u;
+        }
+      }
+    } else if (warp == kWgEpiWarps + 1) {
+      if (elect_one()) {
+        // M = 128 channels of A per MMA, N = 64*nb channels of B, K = 16 points; both MN-major (bits 15, 16)
+        const uint32_t idesc = make_idesc_bf16(128, N) | (1u << 15) | (1u << 16);
+        const uint32_t lbo = P.variant == 1 ? 1024u : kHalfChunk, sbo = P.variant == 1 ? kHalfChunk : 1024u;
+        uint32_t stage = 0, par = 0;
+        for (int h = 0; h < n_half; ++h) {
+          mbar_wait(bar(WB_FULL + stage), par);
+          tc_fence_after_sync();
+          const uint32_t s0 = base + stage * kWgStageBytes;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t bdesc = make_desc_mn128(s0 + 4u * kHalfChunk + (uint32_t)kk * 2048u, lbo, sbo);
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+              const uint64_t adesc = make_desc_mn128(s0 + (uint32_t)(2 * m) * kHalfChunk + (uint32_t)kk * 2048u, lbo, sbo);
+              mma_bf16_ss(tmem_base + (uint32_t)m * 256u, adesc, bdesc, idesc, (h | kk) != 0);
+            }
+          }
+          mma_commit(bar(WB_EMPTY + stage));
+          if (++stage == kWgStages) stage = 0, par ^= 1u;
+        }
+        mma_commit(bar(WB_ACC));
+      }
+    } else {
+      const int q = warp & 3, mh = warp >> 2;
+      mbar_wait(bar(WB_ACC), 0);
+      tc_fence_after_sync();
+      const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)mh * 256u;
+      float* dst = P.acc_t + mh * 128 + q * 32 + lane;
+      for (uint32_t cb = 0; cb < N; cb += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_acc + cb, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) atomicAdd(dst + (size_t)(cb + i) * 256, __uint_as_float(v[i]));
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kWgEpiWarps + 1) {
+    tc_fence_after_sync();
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+static int g_sm_count = 0;
+static int sm_count() {
+  if (!g_sm_count) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      return 148;
+    g_sm_count = n;
+  }
+  return g_sm_count;
+}
+
+static int check_arch() {
+  int dev = 0, major = 0;
+  NSFF_CUDA_TRY(cudaGetDevice(&dev));
+  NSFF_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  return major == 10 ? NSFF_OK : NSFF_EARCH;
+}
+
+static int launch_gemm(GemmParams& P, cudaStream_t st) {
+  if (P.n_tiles <= 0) return NSFF_OK;
+  if (P.n_chunks < 1 || P.n_chunks > kMaxK || (P.N != 256 && P.N != 128 && P.N != 64)) return NSFF_EINVAL;
+  const uint32_t fixed = (uint32_t)P.n_chunks * (uint32_t)P.N * 128u + kGemmAux + 1024u;
+  int stages = (int)((kSmemLimit - fixed) / kChunkBytes);
+  if (stages > kGemmMaxStages) stages = kGemmMaxStages;
+  if (stages < 2) return NSFF_EUNSUPPORTED;
+  P.stages = stages;
+  const uint32_t smem = fixed + (uint32_t)stages * kChunkBytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NSFF_CUDA_TRY(cudaFuncSetAttribute(img_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    attr_set = true;
+  }
+  int grid = sm_count();
+  if (grid > P.n_tiles) grid = P.n_tiles;
+  img_gemm_kernel<<<grid, kGemmThreads, smem, st>>>(P);
+  return after_launch();
+}
+
+static int launch_wgrad(WgradParams& P, cudaStream_t st) {
+  if (P.n_tiles <= 0) return NSFF_OK;
+  if (P.nb < 1 || P.nb > 4) return NSFF_EINVAL;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NSFF_CUDA_TRY(cudaFuncSetAttribute(img_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem));
+    attr_set = true;
+  }
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("NSFF_WG_DESC");
+    variant = e ? atoi(e) : 0;
+  }
+  P.variant = variant;
+  int grid = sm_count();
+  if (grid > P.n_tiles) grid = P.n_tiles;
+  img_wgrad_kernel<<<grid, kWgThreads, kWgSmem, st>>>(P);
+  return after_launch();
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- weight pack of the backward ----------------------------------------------------------------------------------
+// All blocks are N x 64 bf16 (N = 256, or 128 for the "trunk input" extras), zero where no weight maps.
+struct Blk {
+  uint32_t off;
+  int n;        // number of consecutive blocks
+  int N;
+};
+struct BwdPack {
+  // forward (recompute): W blocks, K chunks in the order the GEMM consumes them
+  Blk s_fwd[8], s_fin, s_dir, t_fwd[8], t_fin;
+  // dgrad: W^T blocks, K chunks = output-channel chunks of the layer
+  Blk s_hidT[8], s_finT /*4 + sigma-head block*/, s_dirT /*4: feat part*/, s_dirxT /*4, N=128: [dir|a] part*/, s_rgbT /*1*/;
+  Blk t_hidT[8], t_finT, t_headT /*1*/, t_in1T /*4, N=128*/, t_in5T /*4, N=128*/;
+  size_t bytes;
+};
+
+struct PackBuilder {
+  std::vector<PackJob> jobs;   // only filled when dst != nullptr
+  uint8_t* dst = nullptr;
+  uint32_t off = 0;
+  Blk alloc(int n, int N) {
+    Blk b{off, n, N};
+    off += (uint32_t)n * (uint32_t)N * 128u;
+    return b;
+  }
+  void job(const Blk& b, int idx, const float* src, int ld, bool T, int n0, int k0, int n_valid, int k_valid, int dk0 = 0,
+           int dn0 = 0) {
+    if (!dst || !src || n_valid <= 0 || k_valid <= 0) return;
+    PackJob j{src, dst + b.off + (size_t)idx * b.N * 128, ld, T ? 1 : 0, n0, k0, n_valid, k_valid, dk0, dn0};
+    jobs.push_back(j);
+  }
+};
+
+static int flush_pack_jobs(PackBuilder& pb, cudaStream_t st) {
+  for (size_t i = 0; i < pb.jobs.size(); i += kPackJobsPerLaunch) {
+    PackJobs J;
+    memset(&J, 0, sizeof(J));
+    const int n = (int)std::min<size_t>(kPackJobsPerLaunch, pb.jobs.size() - i);
+    for (int k = 0; k < n; ++k) J.job[k] = pb.jobs[i + k];
+    pack_blocks_kernel<<<n, 256, 0, st>>>(J);
+    TRY(after_launch());
+  }
+  pb.jobs.clear();
+  return NSFF_OK;
+}
+
+static int supported(const nsff_field_desc* d) {
+  if (d->W != 256 || d->D != 8 || d->skip != 4 || d->in_xyz != 63) return NSFF_EUNSUPPORTED;
+  if (d->use_viewdir && d->in_dir != 27) return NSFF_EUNSUPPORTED;
+  if (d->in_a != 0 && (d->in_a != 48 || !d->use_viewdir)) return NSFF_EUNSUPPORTED;
+  if (d->has_transient && d->in_t != 48) return NSFF_EUNSUPPORTED;
+  return NSFF_OK;
+}
+
+// Lays the blocks out (always) and, when pb.dst is set, emits the pack jobs reading `p`.
+static void build_pack(const nsff_field_desc* d, const nsff_field_params* p, BwdPack& L, PackBuilder& pb) {
+  const int W = 256, nx = d->in_xyz, nt = d->in_t, sk = d->skip;
+  auto trunk = [&](bool trans, Blk* fwd, Blk* hidT) {
+    const int n_in = trans ? nx + nt : nx;
+    const float* const* w = p ? (trans ? p->trans_w : p->static_w) : nullptr;
+    for (int i = 0; i < 8; ++i) {
+      const bool first = i == 0, skip = i == sk;
+      const int ld = first ? n_in : (skip ? n_in + W : W);
+      const int n_extra = (first || skip) ? (trans ? 2 : 1) : 0;
+      const int n_hid = first ? 0 : 4;
+      fwd[i] = pb.alloc(n_extra + n_hid, 256);
+      const float* src = w ? w[i] : nullptr;
+      if (n_extra) {
+        pb.job(fwd[i], 0, src, ld, false, 0, 0, 256, nx);
+        if (trans) pb.job(fwd[i], 1, src, ld, false, 0, nx, 256, nt);
+      }
+      for (int j = 0; j < n_hid; ++j) pb.job(fwd[i], n_extra + j, src, ld, false, 0, (skip ? n_in : 0) + 64 * j, 256, 64);
+      if (!first) {
+        hidT[i] = pb.alloc(4, 256);
+        for (int j = 0; j < 4; ++j) pb.job(hidT[i], j, src, ld, true, skip ? n_in : 0, 64 * j, 256, 64);
+      } else {
+        hidT[i] = Blk{0, 0, 0};
+      }
+    }
+  };
+  trunk(false, L.s_fwd, L.s_hidT);
+  L.s_fin = pb.alloc(4, 256);
+  L.s_finT = pb.alloc(5, 256);
+  for (int j = 0; j < 4; ++j) {
+    pb.job(L.s_fin, j, p ? p->static_final_w : nullptr, W, false, 0, 64 * j, 256, 64);
+    pb.job(L.s_finT, j, p ? p->static_final_w : nullptr, W, true, 0, 64 * j, 256, 64);
+  }
+  pb.job(L.s_finT, 4, p ? p->static_sigma_w : nullptr, W, true, 0, 0, 256, 1, /*dk0=*/3);
+  L.s_rgbT = pb.alloc(1, 256);
+  pb.job(L.s_rgbT, 0, p ? p->static_rgb_w : nullptr, W, true, 0, 0, 256, 3, 0);
+  if (d->use_viewdir) {
+    const int ldd = W + d->in_dir + d->in_a;
+    const float* wd = p ? p->static_dir_w : nullptr;
+    L.s_dir = pb.alloc(4 + 1 + (d->in_a > 0 ? 1 : 0), 256);
+    L.s_dirT = pb.alloc(4, 256);
+    for (int j = 0; j < 4; ++j) {
+      pb.job(L.s_dir, j, wd, ldd, false, 0, 64 * j, 256, 64);
+      pb.job(L.s_dirT, j, wd, ldd, true, 0, 64 * j, 256, 64);
+    }
+    pb.job(L.s_dir, 4, wd, ldd, false, 0, W, 256, d->in_dir);
+    if (d->in_a > 0) {
+      pb.job(L.s_dir, 5, wd, ldd, false, 0, W + d->in_dir, 256, d->in_a);
+      L.s_dirxT = pb.alloc(4, 128);
+      for (int j = 0; j < 4; ++j) pb.job(L.s_dirxT, j, wd, ldd, true, W, 64 * j, d->in_dir + d->in_a, 64);
+    }
+  }
+  if (d->has_transient) {
+    trunk(true, L.t_fwd, L.t_hidT);
+    L.t_fin = pb.alloc(4, 256);
+    L.t_finT = pb.alloc(4, 256);
+    for (int j = 0; j < 4; ++j) {
+      pb.job(L.t_fin, j, p ? p->trans_final_w : nullptr, W, false, 0, 64 * j, 256, 64);
+      pb.job(L.t_finT, j, p ? p->trans_final_w : nullptr, W, true, 0, 64 * j, 256, 64);
+    }
+    L.t_headT = pb.alloc(1, 256);
+    pb.job(L.t_headT, 0, p ? p->trans_rgb_w : nullptr, W, true, 0, 0, 256, 3, 0);
+    pb.job(L.t_headT, 0, p ? p->trans_sigma_w : nullptr, W, true, 0, 0, 256, 1, 3);
+    pb.job(L.t_headT, 0, p ? p->trans_fw_w : nullptr, W, true, 0, 0, 256, 3, 4);
+    pb.job(L.t_headT, 0, p ? p->trans_bw_w : nullptr, W, true, 0, 0, 256, 3, 7);
+    L.t_in1T = pb.alloc(4, 128);
+    L.t_in5T = pb.alloc(4, 128);
+    for (int j = 0; j < 4; ++j) {
+      pb.job(L.t_in1T, j, p ? p->trans_w[0] : nullptr, nx + nt, true, 0, 64 * j, nx + nt, 64);
+      pb.job(L.t_in5T, j, p ? p->trans_w[sk] : nullptr, nx + nt + W, true, 0, 64 * j, nx + nt, 64);
+    }
+  }
+  L.bytes = pb.off;
+}
+
+// ---- scratch --------------------------------------------------------------------------------------------------------
+struct Scratch {
+  float* X;
+  uint8_t *PE, *T, *DIR, *A, *SH[8], *SFEAT, *SDIRO, *TH[8], *TFEAT, *G0, *G1, *DP;
+  float *DIN, *ACC;
+  size_t acc_bytes, total;
+};
+constexpr size_t kAccSlots = 96;          // 64-row x 256 fp32 wgrad result slots per call
+static Scratch carve(const nsff_field_desc* d, int64_t B, uint8_t* base) {
+  Scratch s;
+  const size_t nt = (size_t)cdiv64(B, 128);
+  const size_t one = nt * kChunkBytes, four = 4 * one;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    uint8_t* p = base ? base + o : nullptr;
+    o += align_up(bytes, 1024);
+    return p;
+  };
+  const int cin = d->in_xyz + d->in_dir + d->in_a + d->in_t;
+  s.X = reinterpret_cast<float*>(take((size_t)B * cin * sizeof(float)));
+  s.PE = take(one); s.T = take(one); s.DIR = take(one); s.A = take(one);
+  for (int i = 0; i < 8; ++i) s.SH[i] = take(four);
+  s.SFEAT = take(four); s.SDIRO = take(four);
+  for (int i = 0; i < 8; ++i) s.TH[i] = take(d->has_transient ? four : 0);
+  s.TFEAT = take(d->has_transient ? four : 0);
+  s.G0 = take(four); s.G1 = take(four); s.DP = take(one);
+  s.DIN = reinterpret_cast<float*>(take((size_t)B * 128 * sizeof(float)));
+  s.acc_bytes = kAccSlots * 64 * 256 * sizeof(float);
+  s.ACC = reinterpret_cast<float*>(take(s.acc_bytes));
+  s.total = o;
+  return s;
+}
+
+// ---- orchestration helpers --------------------------------------------------------------------------------------------
+struct Src {
+  const uint8_t* p;
+  uint32_t stride;
+  int kcnt;
+};
+static inline Src chunk_of(const uint8_t* img, int chunks_per_tile, int c, int kcnt = 4) {
+  return Src{img + (size_t)c * kChunkBytes, (uint32_t)chunks_per_tile * kChunkBytes, kcnt};
+}
+struct Ctx {
+  cudaStream_t st;
+  int n_tiles;
+  int64_t B;
+  const uint8_t* pack;
+  float* acc;
+  size_t acc_used, acc_cap;   // in floats
+};
+
+static int gemm_img(Ctx& c, const std::vector<Src>& a, const Blk& blk, const float* bias, int epi, uint8_t* out_img,
+                    const uint8_t* mask_img) {
+  if ((int)a.size() != blk.n) return NSFF_EINVAL;
+  GemmParams P;
+  memset(&P, 0, sizeof(P));
+  for (size_t i = 0; i < a.size(); ++i) P.a_base[i] = a[i].p, P.a_stride[i] = a[i].stride, P.kcnt[i] = (uint8_t)a[i].kcnt;
+  P.n_tiles = c.n_tiles; P.n_chunks = blk.n; P.N = blk.N; P.epi = epi;
+  P.b_blocks = c.pack + blk.off; P.bias = bias;
+  P.out_img = out_img; P.out_stride = (uint32_t)(blk.N / 64) * kChunkBytes;
+  P.mask_img = mask_img; P.mask_stride = P.out_stride;
+  P.n_rows = c.B;
+  return launch_gemm(P, c.st);
+}
+static int gemm_rows(Ctx& c, const std::vector<Src>& a, const Blk& blk, float* out, int ld, int ncols, int beta) {
+  if ((int)a.size() != blk.n) return NSFF_EINVAL;
+  GemmParams P;
+  memset(&P, 0, sizeof(P));
+  for (size_t i = 0; i < a.size(); ++i) P.a_base[i] = a[i].p, P.a_stride[i] = a[i].stride, P.kcnt[i] = (uint8_t)a[i].kcnt;
+  P.n_tiles = c.n_tiles; P.n_chunks = blk.n; P.N = blk.N; P.epi = GE_F32_ROWS;
+  P.b_blocks = c.pack + blk.off;
+  P.out_f32 = out; P.ld = ld; P.ncols = ncols; P.beta = beta; P.n_rows = c.B;
+  return launch_gemm(P, c.st);
+}
+static std::vector<Src> four(const uint8_t* img) {
+  return {chunk_of(img, 4, 0), chunk_of(img, 4, 1), chunk_of(img, 4, 2), chunk_of(img, 4, 3)};
+}
+// acc_t rows = channels of the B chunks, columns = the 256 channels of `a_img`
+static int wgrad_img(Ctx& c, const uint8_t* a_img, const std::vector<Src>& b, float** acc_out) {
+  const size_t need = b.size() * 64 * 256;
+  if (b.empty() || b.size() > 4 || c.acc_used + need > c.acc_cap) return NSFF_EINVAL;
+  WgradParams P;
+  memset(&P, 0, sizeof(P));
+  P.a_base = a_img; P.a_stride = 4 * kChunkBytes;
+  for (size_t j = 0; j < b.size(); ++j) P.b_base[j] = b[j].p, P.b_stride[j] = b[j].stride;
+  P.nb = (int)b.size(); P.n_tiles = c.n_tiles;
+  P.acc_t = c.acc + c.acc_used;
+  c.acc_used += need;
+  *acc_out = P.acc_t;
+  return launch_wgrad(P, c.st);
+}
+static int finish_cols(Ctx& c, const float* acc, float* dW, int ldw, std::initializer_list<int> dcol0,
+                       std::initializer_list<int> ncols) {
+  if (!dW) return NSFF_EINVAL;
+  FinishJob J;
+  memset(&J, 0, sizeof(J));
+  J.acc_t = acc; J.dW = dW; J.ldw = ldw; J.nb = (int)dcol0.size();
+  int i = 0;
+  for (int v : dcol0) J.dcol0[i++] = v;
+  i = 0;
+  for (int v : ncols) J.ncols[i++] = v;
+  wgrad_finish_kernel<<<J.nb * 64, 256, 0, c.st>>>(J);
+  return after_launch();
+}
+static int finish_rows(Ctx& c, const float* acc, float* const (&drow)[16]) {
+  FinishJob J;
+  memset(&J, 0, sizeof(J));
+  J.acc_t = acc; J.direct = 1;
+  for (int i = 0; i < 16; ++i) J.drow[i] = drow[i];
+  wgrad_finish_kernel<<<16, 256, 0, c.st>>>(J);
+  return after_launch();
+}
+static int colsum(Ctx& c, const uint8_t* img4, float* db) {
+  if (!db) return NSFF_EINVAL;
+  int gx = c.n_tiles < 64 ? c.n_tiles : 64;
+  img_colsum_kernel<<<dim3((unsigned)gx, 4), 256, 0, c.st>>>(img4, 4 * kChunkBytes, 4, c.n_tiles, db);
+  return after_launch();
+}
+static int rows_to_img(Ctx& c, const float* src, int ld, int col0, int ncols, uint8_t* img) {
+  const int64_t n = (int64_t)c.n_tiles * 128 * 8;
+  rows_to_img_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, c.st>>>(src, ld, col0, ncols, c.B, img, kChunkBytes, c.n_tiles);
+  return after_launch();
+}
+
+struct Trunk {
+  bool trans;
+  const Blk* fwd;
+  const Blk* hidT;
+  const float* const* b;
+  float* const* gw;
+  float* const* gb;
+  uint8_t* const* H;
+  std::vector<Src> in;     // trunk input chunks ([PE] or [PE, T])
+  int n_in;
+};
+
+static int trunk_forward(Ctx& c, const nsff_field_desc* d, const Trunk& t) {
+  for (int i = 0; i < 8; ++i) {
+    std::vector<Src> a;
+    if (i == 0 || i == d->skip) a = t.in;
+    if (i > 0) {
+      auto h = four(t.H[i - 1]);
+      a.insert(a.end(), h.begin(), h.end());
+    }
+    TRY(gemm_img(c, a, t.fwd[i], t.b[i], GE_RELU_IMG, t.H[i], nullptr));
+  }
+  return NSFF_OK;
+}
+
+// g_cur holds dZ_8 (gradient w.r.t. the pre-activation of the last trunk layer).  d_in (fp32 (B,128)) receives the
+// gradient w.r.t. the trunk input columns [PE | t], accumulated over the skip layer and layer 1.
+static int trunk_backward(Ctx& c, const nsff_field_desc* d, const Trunk& t, uint8_t* g_cur, uint8_t* g_next,
+                          const Blk* in1T, const Blk* in5T, float* d_in) {
+  const int W = 256;
+  for (int i = 7; i >= 0; --i) {
+    const bool first = i == 0, skip = i == d->skip;
+    const int in_k = first ? t.n_in : (skip ? t.n_in + W : W);
+    if (!t.gw[i] || !t.gb[i]) return NSFF_EINVAL;
+    TRY(colsum(c, g_cur, t.gb[i]));
+    float* acc;
+    if (!first) {
+      TRY(wgrad_img(c, g_cur, four(t.H[i - 1]), &acc));
+      const int h0 = skip ? t.n_in : 0;
+      TRY(finish_cols(c, acc, t.gw[i], in_k, {h0, h0 + 64, h0 + 128, h0 + 192}, {64, 64, 64, 64}));
+    }
+    if (first || skip) {
+      TRY(wgrad_img(c, g_cur, t.in, &acc));
+      if (t.trans) TRY(finish_cols(c, acc, t.gw[i], in_k, {0, d->in_xyz}, {d->in_xyz, d->in_t}));
+      else TRY(finish_cols(c, acc, t.gw[i], in_k, {0}, {d->in_xyz}));
+      if (d_in) TRY(gemm_rows(c, four(g_cur), first ? *in1T : *in5T, d_in, 128, t.n_in, first ? 1 : 0));
+    }
+    if (!first) {
+      TRY(gemm_img(c, four(g_cur), t.hidT[i], nullptr, GE_MASK_IMG, g_next, t.H[i - 1]));
+      uint8_t* tmp = g_cur; g_cur = g_next; g_next = tmp;
+    }
+  }
+  return NSFF_OK;
+}
+
+}  // namespace bwd
+}  // namespace nsff
+
+using namespace nsff;
+using namespace nsff::bwd;
+
+extern "C" {
+
+size_t nsff_field_bwd_tc_pack_bytes(const nsff_field_desc* d) {
+  if (!d || supported(d) != NSFF_OK) return 0;
+  BwdPack L;
+  PackBuilder pb;
+  build_pack(d, nullptr, L, pb);
+  return L.bytes;
+}
+
+int nsff_field_bwd_tc_pack(const nsff_field_desc* d, const nsff_field_params* p, void* pack, void* stream) {
+  if (!d || !p || !pack) return NSFF_EINVAL;
+  TRY(supported(d));
+  cudaStream_t st = (cudaStream_t)stream;
+  BwdPack L;
+  PackBuilder pb;
+  pb.dst = reinterpret_cast<uint8_t*>(pack);
+  build_pack(d, p, L, pb);
+  NSFF_CUDA_TRY(cudaMemsetAsync(pack, 0, L.bytes, st));
+  return flush_pack_jobs(pb, st);
+}
+
+size_t nsff_field_bwd_tc_scratch_bytes(const nsff_field_desc* d, int64_t B) {
+  if (!d || B < 0 || supported(d) != NSFF_OK) return 0;
+  return carve(d, B, nullptr).total;
+}
+
+int nsff_field_backward_tc(const nsff_field_desc* d, const nsff_field_params* p, const void* pack,
+                           const nsff_points* pts, int out_mask,
+                           const float* out, const float* d_out, int32_t out_ld, const nsff_field_grads* g,
+                           float* d_pos, float* d_t, float* d_a, void* scratch, void* stream) {
+  if (!d || !p || !pack || !pts || !out || !d_out || !g || !scratch) return NSFF_EINVAL;
+  TRY(supported(d));
+  if (out_mask & NSFF_OUT_SIGMA_ONLY) return NSFF_EUNSUPPORTED;
+  if (pts->t_index || pts->a_index || pts->offset) return NSFF_EINVAL;   // per-ray code rows, final positions
+  const bool want_s = out_mask & NSFF_OUT_STATIC, want_t = out_mask & NSFF_OUT_TRANSIENT;
+  const bool want_fw = out_mask & NSFF_OUT_FLOW_FW, want_bw = out_mask & NSFF_OUT_FLOW_BW;
+  if (!want_s && !want_t) return NSFF_EINVAL;
+  if (want_t && !d->has_transient) return NSFF_EINVAL;
+  const int64_t B = pts->B;
+  if (B <= 0 || pts->S < 1 || B % pts->S) return B == 0 ? NSFF_OK : NSFF_EINVAL;
+  if (want_t && d->in_t > 0 && !pts->t_table) return NSFF_EINVAL;
+  TRY(check_arch());
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t R = B / pts->S;
+  const int W = 256;
+  BwdPack L;
+  {
+    PackBuilder pb;
+    build_pack(d, nullptr, L, pb);
+  }
+  Scratch s = carve(d, B, reinterpret_cast<uint8_t*>(scratch));
+  Ctx c{st, (int)cdiv64(B, 128), B, reinterpret_cast<const uint8_t*>(pack), s.ACC, 0, s.acc_bytes / sizeof(float)};
+  NSFF_CUDA_TRY(cudaMemsetAsync(s.ACC, 0, s.acc_bytes, st));
+  if (d_pos) NSFF_CUDA_TRY(cudaMemsetAsync(d_pos, 0, (size_t)B * 3 * sizeof(float), st));
+  if (d_t) NSFF_CUDA_TRY(cudaMemsetAsync(d_t, 0, (size_t)R * d->in_t * sizeof(float), st));
+  if (d_a) NSFF_CUDA_TRY(cudaMemsetAsync(d_a, 0, (size_t)R * d->in_a * sizeof(float), st));
+
+  // ---- inputs: embedded row (fp32, shared with the fp32 path) -> bf16 chunk images ----
+  const int cin = d->in_xyz + d->in_dir + d->in_a + d->in_t;
+  TRY(launch_embed_rows(d, pts, s.X, cin, st));
+  TRY(rows_to_img(c, s.X, cin, 0, d->in_xyz, s.PE));
+  if (d->use_viewdir) TRY(rows_to_img(c, s.X, cin, d->in_xyz, d->in_dir, s.DIR));
+  if (d->in_a > 0) TRY(rows_to_img(c, s.X, cin, d->in_xyz + d->in_dir, d->in_a, s.A));
+  if (want_t) TRY(rows_to_img(c, s.X, cin, d->in_xyz + d->in_dir + d->in_a, d->in_t, s.T));
+  const Src pe = chunk_of(s.PE, 1, 0, 4), tc = chunk_of(s.T, 1, 0, 3), dirc = chunk_of(s.DIR, 1, 0, 2),
+            ac = chunk_of(s.A, 1, 0, 3), dp = chunk_of(s.DP, 1, 0, 1);
+  int col = 0;
+  auto heads = [&](const HeadSpec& H) {
+    heads_dpre_kernel<<<(unsigned)c.n_tiles, 128, 0, st>>>(d_out, out, out_ld, H, pts->zs, d->flow_scale, B, s.DP,
+                                                           kChunkBytes);
+    return after_launch();
+  };
+  float* acc;
+
+  if (want_s) {
+    Trunk t{false, L.s_fwd, L.s_hidT, p->static_b, g->static_w, g->static_b, s.SH, {pe}, d->in_xyz};
+    // ---- recompute, keeping every layer ----
+    TRY(trunk_forward(c, d, t));
+    TRY(gemm_img(c, four(s.SH[7]), L.s_fin, p->static_final_b, GE_LIN_IMG, s.SFEAT, nullptr));
+    const uint8_t* rgb_in = s.SFEAT;
+    if (d->use_viewdir) {
+      std::vector<Src> a = four(s.SFEAT);
+      a.push_back(dirc);
+      if (d->in_a > 0) a.push_back(ac);
+      TRY(gemm_img(c, a, L.s_dir, p->static_dir_b, GE_RELU_IMG, s.SDIRO, nullptr));
+      rgb_in = s.SDIRO;
+    }
+    // ---- heads: image columns 0..2 = rgb (sigmoid), 3 = sigma ----
+    HeadSpec H;
+    memset(&H, 0, sizeof(H));
+    for (int i = 0; i < 16; ++i) H.src[i] = -1;
+    for (int i = 0; i < 3; ++i) H.src[i] = (int8_t)(col + i), H.act[i] = 1, H.db[i] = g->static_rgb_b ? g->static_rgb_b + i : nullptr;
+    H.src[3] = (int8_t)(col + 3), H.act[3] = 0, H.db[3] = g->static_sigma_b;
+    TRY(heads(H));
+    if (!g->static_rgb_w || !g->static_sigma_w) return NSFF_EINVAL;
+    {
+      float* rows[16] = {g->static_rgb_w, g->static_rgb_w + W, g->static_rgb_w + 2 * W};
+      TRY(wgrad_img(c, rgb_in, {dp}, &acc));
+      TRY(finish_rows(c, acc, rows));
+      float* rows2[16] = {nullptr, nullptr, nullptr, g->static_sigma_w};
+      TRY(wgrad_img(c, s.SH[7], {dp}, &acc));
+      TRY(finish_rows(c, acc, rows2));
+    }
+    uint8_t *g_fin, *other;
+    if (d->use_viewdir) {
+      const int kd = W + d->in_dir + d->in_a;
+      TRY(gemm_img(c, {dp}, L.s_rgbT, nullptr, GE_MASK_IMG, s.G0, s.SDIRO));          // dZ_dir
+      TRY(colsum(c, s.G0, g->static_dir_b));
+      TRY(wgrad_img(c, s.G0, four(s.SFEAT), &acc));
+      TRY(finish_cols(c, acc, g->static_dir_w, kd, {0, 64, 128, 192}, {64, 64, 64, 64}));
+      if (d->in_a > 0) {
+        TRY(wgrad_img(c, s.G0, {dirc, ac}, &acc));
+        TRY(finish_cols(c, acc, g->static_dir_w, kd, {W, W + d->in_dir}, {d->in_dir, d->in_a}));
+        if (d_a) {
+          TRY(gemm_rows(c, four(s.G0), L.s_dirxT, s.DIN, 128, d->in_dir + d->in_a, 0));
+          TRY(launch_ray_reduce(s.DIN, 128, d->in_dir, d->in_a, pts->S, R, d_a, st));
+        }
+      } else {
+        TRY(wgrad_img(c, s.G0, {dirc}, &acc));
+        TRY(finish_cols(c, acc, g->static_dir_w, kd, {W}, {d->in_dir}));
+      }
+      TRY(gemm_img(c, four(s.G0), L.s_dirT, nullptr, GE_LIN_IMG, s.G1, nullptr));       // dFEAT = dZ_final
+      g_fin = s.G1, other = s.G0;
+    } else {
+      TRY(gemm_img(c, {dp}, L.s_rgbT, nullptr, GE_LIN_IMG, s.G0, nullptr));
+      g_fin = s.G0, other = s.G1;
+    }
+    TRY(colsum(c, g_fin, g->static_final_b));
+    TRY(wgrad_img(c, g_fin, four(s.SH[7]), &acc));
+    TRY(finish_cols(c, acc, g->static_final_w, W, {0, 64, 128, 192}, {64, 64, 64, 64}));
+    {
+      std::vector<Src> a = four(g_fin);
+      a.push_back(dp);
+      TRY(gemm_img(c, a, L.s_finT, nullptr, GE_MASK_IMG, other, s.SH[7]));              // dZ_8 (incl. sigma head)
+    }
+    // static positions never carry gradient (the warped passes evaluate the dynamic branch only)
+    TRY(trunk_backward(c, d, t, other, g_fin, nullptr, nullptr, nullptr));
+    col += 4;
+  }
+  if (want_t) {
+    Trunk t{true, L.t_fwd, L.t_hidT, p->trans_b, g->trans_w, g->trans_b, s.TH, {pe, tc}, d->in_xyz + d->in_t};
+    TRY(trunk_forward(c, d, t));
+    TRY(gemm_img(c, four(s.TH[7]), L.t_fin, p->trans_final_b, GE_LIN_IMG, s.TFEAT, nullptr));
+    // ---- heads: image columns 0..2 rgb, 3 sigma, 4..6 flow fw, 7..9 flow bw (fixed, whatever the mask) ----
+    HeadSpec H;
+    memset(&H, 0, sizeof(H));
+    for (int i = 0; i < 16; ++i) H.src[i] = -1;
+    for (int i = 0; i < 3; ++i) H.src[i] = (int8_t)(col + i), H.act[i] = 1, H.db[i] = g->trans_rgb_b ? g->trans_rgb_b + i : nullptr;
+    H.src[3] = (int8_t)(col + 3), H.act[3] = 0, H.db[3] = g->trans_sigma_b;
+    float* rows[16] = {g->trans_rgb_w, g->trans_rgb_w + W, g->trans_rgb_w + 2 * W, g->trans_sigma_w};
+    if (!g->trans_rgb_w || !g->trans_sigma_w) return NSFF_EINVAL;
+    int cc = col + 4;
+    if (want_fw) {
+      if (!g->trans_fw_w) return NSFF_EINVAL;
+      for (int i = 0; i < 3; ++i) {
+        H.src[4 + i] = (int8_t)(cc + i), H.act[4 + i] = 2, H.db[4 + i] = g->trans_fw_b ? g->trans_fw_b + i : nullptr;
+        rows[4 + i] = g->trans_fw_w + i * W;
+      }
+      cc += 3;
+    }
+    if (want_bw) {
+      if (!g->trans_bw_w) return NSFF_EINVAL;
+      for (int i = 0; i < 3; ++i) {
+        H.src[7 + i] = (int8_t)(cc + i), H.act[7 + i] = 2, H.db[7 + i] = g->trans_bw_b ? g->trans_bw_b + i : nullptr;
+        rows[7 + i] = g->trans_bw_w + i * W;
+      }
+      cc += 3;
+    }
+    TRY(heads(H));
+    TRY(wgrad_img(c, s.TFEAT, {dp}, &acc));
+    TRY(finish_rows(c, acc, rows));
+    TRY(gemm_img(c, {dp}, L.t_headT, nullptr, GE_LIN_IMG, s.G0, nullptr));               // dTFEAT = dZ_final
+    TRY(colsum(c, s.G0, g->trans_final_b));
+    TRY(wgrad_img(c, s.G0, four(s.TH[7]), &acc));
+    TRY(finish_cols(c, acc, g->trans_final_w, W, {0, 64, 128, 192}, {64, 64, 64, 64}));
+    TRY(gemm_img(c, four(s.G0), L.t_finT, nullptr, GE_MASK_IMG, s.G1, s.TH[7]));          // dZ_8
+    float* d_in = (d_pos || d_t) ? s.DIN : nullptr;
+    TRY(trunk_backward(c, d, t, s.G1, s.G0, &L.t_in1T, &L.t_in5T, d_in));
+    if (d_t && d->in_t > 0) TRY(launch_ray_reduce(d_in, 128, d->in_xyz, d->in_t, pts->S, R, d_t, st));
+    if (d_pos) TRY(launch_pe_bwd(d_in, 128, pts->xyz, (d->in_xyz - 3) / 6, d_pos, B, st));
+  }
+  return NSFF_OK;
+}
+
+// ---- generic entry points (unit tests; hosts that keep their own bf16 tile images) -------------------------------
+size_t nsff_img_bytes(int64_t n_rows, int n_chunks) {
+  if (n_rows < 0 || n_chunks < 1) return 0;
+  return (size_t)cdiv64(n_rows, 128) * (size_t)n_chunks * kChunkBytes;
+}
+
+int nsff_img_from_rows(const float* src, int32_t ld, int32_t col0, int32_t ncols, int64_t n_rows, void* img,
+                       int32_t img_chunks, int32_t chunk, void* stream) {
+  if (!src || !img || ncols < 0 || ncols > 64 || chunk < 0 || chunk >= img_chunks || n_rows < 0) return NSFF_EINVAL;
+  const int n_tiles = (int)cdiv64(n_rows, 128);
+  if (!n_tiles) return NSFF_OK;
+  const int64_t n = (int64_t)n_tiles * 128 * 8;
+  rows_to_img_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      src, ld, col0, ncols, n_rows, reinterpret_cast<uint8_t*>(img) + (size_t)chunk * kChunkBytes,
+      (uint32_t)img_chunks * kChunkBytes, n_tiles);
+  return after_launch();
+}
+
+int nsff_img_to_rows(const void* img, int32_t img_chunks, int32_t chunk, float* dst, int32_t ld, int32_t col0,
+                     int32_t ncols, int64_t n_rows, void* stream) {
+  if (!dst || !img || ncols < 0 || ncols > 64 || chunk < 0 || chunk >= img_chunks || n_rows < 0) return NSFF_EINVAL;
+  if (!n_rows) return NSFF_OK;
+  img_to_rows_kernel<<<(unsigned)cdiv64(n_rows * 64, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint8_t*>(img) + (size_t)chunk * kChunkBytes, (uint32_t)img_chunks * kChunkBytes, dst, ld,
+      col0, ncols, n_rows);
+  return after_launch();
+}
+
+int nsff_img_pack_weight(const float* src, int32_t ld, int32_t transpose, int32_t n0, int32_t k0, int32_t n_valid,
+                         int32_t k_valid, int32_t N, void* block, void* stream) {
+  if (!src || !block || (N != 256 && N != 128 && N != 64) || n_valid < 0 || n_valid > N || k_valid < 0 || k_valid > 64)
+    return NSFF_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  NSFF_CUDA_TRY(cudaMemsetAsync(block, 0, (size_t)N * 128, st));
+  if (!n_valid || !k_valid) return NSFF_OK;
+  PackJobs J;
+  memset(&J, 0, sizeof(J));
+  J.job[0] = PackJob{src, reinterpret_cast<uint8_t*>(block), ld, transpose ? 1 : 0, n0, k0, n_valid, k_valid, 0, 0};
+  pack_blocks_kernel<<<1, 256, 0, st>>>(J);
+  return after_launch();
+}
+
+int nsff_img_gemm(const nsff_img_gemm_args* a, void* stream) {
+  if (!a || !a->a_img || !a->b_blocks || a->a_chunks < 1 || a->a_chunks > kMaxK || a->n_rows < 0) return NSFF_EINVAL;
+  if (a->epi < 0 || a->epi > 3) return NSFF_EINVAL;
+  if (a->epi == GE_F32_ROWS ? !a->out_rows : !a->out_img) return NSFF_EINVAL;
+  if (a->epi == GE_MASK_IMG && !a->mask_img) return NSFF_EINVAL;
+  TRY(check_arch());
+  GemmParams P;
+  memset(&P, 0, sizeof(P));
+  for (int i = 0; i < a->a_chunks; ++i) {
+    P.a_base[i] = reinterpret_cast<const uint8_t*>(a->a_img) + (size_t)i * kChunkBytes;
+    P.a_stride[i] = (uint32_t)a->a_chunks * kChunkBytes;
+    P.kcnt[i] = 4;
+  }
+  P.n_tiles = (int)cdiv64(a->n_rows, 128); P.n_chunks = a->a_chunks; P.N = a->N; P.epi = a->epi;
+  P.b_blocks = reinterpret_cast<const uint8_t*>(a->b_blocks); P.bias = a->bias;
+  P.out_img = reinterpret_cast<uint8_t*>(a->out_img); P.out_stride = (uint32_t)(a->N / 64) * kChunkBytes;
+  P.mask_img = reinterpret_cast<const uint8_t*>(a->mask_img); P.mask_stride = P.out_stride;
+  P.out_f32 = a->out_rows; P.ld = a->ld; P.ncols = a->ncols; P.beta = a->beta; P.n_rows = a->n_rows;
+  return launch_gemm(P, (cudaStream_t)stream);
+}
+
+int nsff_img_wgrad(const nsff_img_wgrad_args* a, void* stream) {
+  if (!a || !a->a_img || !a->b_img || a->b_chunks < 1 || a->b_chunks > 4 || !a->acc_t || a->n_rows < 0) return NSFF_EINVAL;
+  TRY(check_arch());
+  WgradParams P;
+  memset(&P, 0, sizeof(P));
+  P.a_base = reinterpret_cast<const uint8_t*>(a->a_img); P.a_stride = 4 * kChunkBytes;
+  for (int j = 0; j < a->b_chunks; ++j) {
+    P.b_base[j] = reinterpret_cast<const uint8_t*>(a->b_img) + (size_t)j * kChunkBytes;
+    P.b_stride[j] = (uint32_t)a->b_chunks * kChunkBytes;
+  }
+  P.nb = a->b_chunks; P.n_tiles = (int)cdiv64(a->n_rows, 128); P.acc_t = a->acc_t;
+  return launch_wgrad(P, (cudaStream_t)stream);
+}
+}

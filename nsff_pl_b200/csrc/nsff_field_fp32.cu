@@ -4,6 +4,7 @@
 // the oracle to ~1e-6 on the GPU, independently of bf16 rounding.  It is NOT a fallback: the
 // renderer only takes it when the caller selects precision='fp32'.
 #include "nsff_common.cuh"
+#include "nsff_field_host.cuh"
 
 namespace nsff {
 
@@ -489,6 +490,22 @@ static int relu_bwd(float* dY, int ldd, const float* Y, int ldy, int64_t M, int 
 static int head_bwd(const float* d_out, const float* out, int ld, int col0, int n, int act, const float* zs,
                     float scale, float* dpre, int64_t M, cudaStream_t st) {
   head_bwd_kernel<<<(unsigned)cdiv64(M * n, 256), 256, 0, st>>>(d_out, out, ld, col0, n, act, zs, scale, dpre, M);
+  return after_launch();
+}
+
+int launch_embed_rows(const nsff_field_desc* d, const nsff_points* pts, float* X, int ld, cudaStream_t st) {
+  EmbedArgs e{*pts, d->in_xyz, d->in_dir, d->in_a, d->in_t, X, ld};
+  e.p.xyz_out = nullptr;
+  const int cin = d->in_xyz + d->in_dir + d->in_a + d->in_t;
+  embed_points_kernel<<<(unsigned)cdiv64(pts->B * cin, 256), 256, 0, st>>>(e);
+  return after_launch();
+}
+int launch_ray_reduce(const float* dX, int ld, int col0, int n, int S, int64_t R, float* d_code, cudaStream_t st) {
+  ray_reduce_kernel<<<(unsigned)cdiv64(R * n, 256), 256, 0, st>>>(dX, ld, col0, n, S, R, d_code);
+  return after_launch();
+}
+int launch_pe_bwd(const float* dX, int ld, const float* pos, int n_freqs, float* d_pos, int64_t M, cudaStream_t st) {
+  pe_bwd_kernel<<<(unsigned)cdiv64(M * 3, 256), 256, 0, st>>>(dX, ld, pos, n_freqs, d_pos, M);
   return after_launch();
 }
 

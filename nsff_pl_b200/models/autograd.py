@@ -3,7 +3,8 @@
 The reference gets its backward from torch autograd over ~25 nn.Linear layers and the einops/cumprod composite
 (train.py:178-198 -> rendering.py:83-300).  Here the forward is the same pair of kernels as inference
 (tcgen05 field kernel + composite) and the backward is hand-written:
-    FieldFn      -> nsff_field_backward_fp32   (recompute + dgrad/wgrad per layer, PE and code gradients)
+    FieldFn      -> nsff_field_backward_tc (bf16 tcgen05 GEMMs) or nsff_field_backward_fp32 (verification):
+                    recompute + dgrad/wgrad per layer, PE and code gradients
     CompositeFn  -> nsff_composite_backward    (reverse transmittance scans)
 Only cheap glue stays in torch (xyz + flow, embedding-table gathers), so their gradients come for free.
 """
@@ -102,7 +103,9 @@ class FieldFn(torch.autograd.Function):
         d_a = torch.empty(R, a_code.shape[1], device=dev) if need_a else None
         _cabi.select_device(pos)
         st = _cabi.stream_ptr(dev)
-        rays_per = max(1, 32768 // S)
+        tc = model.backward_precision() == "bf16"
+        bwd_pack = model.field_bwd_pack() if tc else None
+        rays_per = max(1, (262144 if tc else 32768) // S)
         ld = out.stride(0)
         for r0 in range(0, R, rays_per):
             nr = min(rays_per, R - r0)
@@ -114,15 +117,23 @@ class FieldFn(torch.autograd.Function):
             pts.t_table = None if t_code is None else t_code.data_ptr() + r0 * t_code.shape[1] * 4
             pts.a_table = None if a_code is None else a_code.data_ptr() + r0 * a_code.shape[1] * 4
             pts.B, pts.S = nb, S
-            scratch = torch.empty(L.nsff_field_bwd_scratch_floats(C.byref(desc), nb), device=dev, dtype=torch.float32)
-            rc = L.nsff_field_backward_fp32(
-                C.byref(desc), C.byref(fp), C.byref(pts), mask, C.c_void_p(out.data_ptr() + b0 * ld * 4),
-                C.c_void_p(d_out.data_ptr() + b0 * ld * 4), ld, C.byref(fg),
-                None if d_pos is None else C.c_void_p(d_pos.data_ptr() + b0 * 12),
-                None if d_t is None else C.c_void_p(d_t.data_ptr() + r0 * d_t.shape[1] * 4),
-                None if d_a is None else C.c_void_p(d_a.data_ptr() + r0 * d_a.shape[1] * 4),
-                _cabi.ptr(scratch), st)
-            _cabi.check(rc, "nsff_field_backward_fp32")
+            tail = (C.c_void_p(out.data_ptr() + b0 * ld * 4), C.c_void_p(d_out.data_ptr() + b0 * ld * 4), ld,
+                    C.byref(fg),
+                    None if d_pos is None else C.c_void_p(d_pos.data_ptr() + b0 * 12),
+                    None if d_t is None else C.c_void_p(d_t.data_ptr() + r0 * d_t.shape[1] * 4),
+                    None if d_a is None else C.c_void_p(d_a.data_ptr() + r0 * d_a.shape[1] * 4))
+            if tc:
+                scratch = torch.empty(L.nsff_field_bwd_tc_scratch_bytes(C.byref(desc), nb), device=dev,
+                                      dtype=torch.uint8)
+                rc = L.nsff_field_backward_tc(C.byref(desc), C.byref(fp), _cabi.ptr(bwd_pack), C.byref(pts), mask,
+                                              *tail, _cabi.ptr(scratch), st)
+                _cabi.check(rc, "nsff_field_backward_tc")
+            else:
+                scratch = torch.empty(L.nsff_field_bwd_scratch_floats(C.byref(desc), nb), device=dev,
+                                      dtype=torch.float32)
+                rc = L.nsff_field_backward_fp32(C.byref(desc), C.byref(fp), C.byref(pts), mask, *tail,
+                                                _cabi.ptr(scratch), st)
+                _cabi.check(rc, "nsff_field_backward_fp32")
         del keep
         return (None, None, None, d_pos, d_t, d_a, None, None, *grads)
 

@@ -180,6 +180,34 @@ class NeRF(nn.Module):
             self._pack_key = key
         return self._pack
 
+    def field_bwd_pack(self):
+        """W and W^T bf16 blocks for the tensor-core backward (nsff_field_backward_tc); same cache rule."""
+        params = list(self.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if getattr(self, "_bwd_pack", None) is None or key != self._bwd_pack_key:
+            desc = self.field_desc()
+            fp, keep = self.field_params()
+            L = _cabi.lib()
+            nbytes = L.nsff_field_bwd_tc_pack_bytes(C.byref(desc))
+            if nbytes == 0:
+                raise NotImplementedError("tensor-core backward needs the 8x256 / skip-4 NSFF field shape")
+            dev = params[0].device
+            self._bwd_pack = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            _cabi.select_device(self._bwd_pack)
+            _cabi.check(L.nsff_field_bwd_tc_pack(C.byref(desc), C.byref(fp), _cabi.ptr(self._bwd_pack),
+                                                 _cabi.stream_ptr(dev)), "nsff_field_bwd_tc_pack")
+            del keep
+            self._bwd_pack_key = key
+        return self._bwd_pack
+
+    def backward_precision(self):
+        """'bf16' (tcgen05 backward) or 'fp32' (CUDA-core verification backward); follows ``precision`` unless
+        ``grad_precision`` is set on the module."""
+        gp = getattr(self, "grad_precision", None) or self.precision
+        if gp not in ("bf16", "fp32"):
+            raise ValueError(f"unknown grad_precision {gp!r} (use 'bf16' or 'fp32')")
+        return gp
+
     @staticmethod
     def out_mask(sigma_only, output_static, output_transient, output_transient_flow):
         m = 0

@@ -162,3 +162,55 @@ def test_training_step_reduces_the_loss():
         opt.step()                                   # bumps parameter versions -> the bf16 pack is rebuilt
         losses.append(float(loss.detach()))
     assert losses[-1] < losses[0], losses
+
+
+def _grads_with(grad_precision, R, S, kw, transient=True, appearance=False, seed=3):
+    from nsff_pl_b200.models.rendering import render_rays
+    models, emb, _, _ = build_fields(W=256, seed=seed, precision="bf16", n_frames=8, transient=transient,
+                                     appearance=appearance)
+    for m in models.values():
+        m.requires_grad_(True)
+        m.grad_precision = grad_precision
+    for e in ("t", "a"):
+        if e in emb:
+            emb[e].weight.requires_grad_(True)
+    rays, ts = synthetic_rays(R, n_frames=8, seed=R)
+    res = render_rays(models, emb, rays.cuda(), ts.cuda() if transient or appearance else None, 7, N_samples=S, **kw)
+    _loss(res).backward()
+    torch.cuda.synchronize()
+    out = {n: p.grad.detach().double().cpu() for n, p in models["fine"].named_parameters() if p.grad is not None}
+    for e in ("t", "a"):
+        if e in emb and emb[e].weight.grad is not None:
+            out["embedding_" + e] = emb[e].weight.grad.detach().double().cpu()
+    return out
+
+
+@pytest.mark.parametrize("R,S", [(24, 48), (7, 33)])
+def test_tensor_core_backward_matches_fp32_backward(R, S):
+    """Same bf16 forward; gradients through nsff_field_backward_tc (bf16 tcgen05 GEMMs over tile images) against
+    nsff_field_backward_fp32 (itself pinned to the oracle's autograd above).  bf16 operands: 2e-2 of each norm."""
+    ref = _grads_with("fp32", R, S, TRAIN_KW)
+    got = _grads_with("bf16", R, S, TRAIN_KW)
+    assert set(ref) == set(got)
+    for k in ref:
+        err = float((got[k] - ref[k]).norm() / (ref[k].norm() + 1e-30))
+        assert err <= 2e-2, f"{k}: relative error {err:.3e} (|ref| {float(ref[k].norm()):.3e})"
+
+
+def test_tensor_core_backward_static_only_model():
+    kw = dict(perturb=0, noise_std=0, N_importance=0, test_time=False)
+    ref = _grads_with("fp32", 10, 40, kw, transient=False, seed=9)
+    got = _grads_with("bf16", 10, 40, kw, transient=False, seed=9)
+    assert set(ref) == set(got)
+    for k in ref:
+        err = float((got[k] - ref[k]).norm() / (ref[k].norm() + 1e-30))
+        assert err <= 2e-2, f"{k}: relative error {err:.3e}"
+
+
+def test_tensor_core_backward_appearance_code():
+    ref = _grads_with("fp32", 9, 40, TRAIN_KW, appearance=True, seed=5)
+    got = _grads_with("bf16", 9, 40, TRAIN_KW, appearance=True, seed=5)
+    assert set(ref) == set(got) and "embedding_a" in ref
+    for k in ref:
+        err = float((got[k] - ref[k]).norm() / (ref[k].norm() + 1e-30))
+        assert err <= 2e-2, f"{k}: relative error {err:.3e}"
