@@ -172,16 +172,25 @@ def run_train(args, rank, local_rank, world):
     import scenes
     for m in models.values():
         m.requires_grad_(True)
+        m.grad_precision = args.grad_precision
     emb["t"].weight.requires_grad_(True)
     params = [p for m in models.values() for p in m.parameters()] + [emb["t"].weight]
     opt = torch.optim.Adam(params, lr=5e-4)
+    phase = {}
     rays, ts = synthetic_rays(R, n_frames=N_FRAMES, seed=100 + rank)
     rays, ts = rays.to(dev), ts.to(dev)
     target = torch.rand(R, 3, device=dev)
     kw = dict(N_samples=S, perturb=1.0, noise_std=1.0, N_importance=0, test_time=False,
               output_transient_flow=["fw", "bw", "disocc"])
 
+    def mark(name):
+        if phase is not None and "on" in phase:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            phase.setdefault("ev", []).append((name, ev))
+
     def step():
+        mark("start")
         opt.zero_grad(set_to_none=True)
         res = render_rays(models, emb, rays, ts, N_FRAMES - 1, **kw)
         loss = ((res["rgb_fine"] - target) ** 2).mean()
@@ -190,7 +199,9 @@ def run_train(args, rank, local_rank, world):
         loss = loss + (res["disoccs_bw"] * (res["xyzs_bw_fw"] - res["xyzs_fine"]).abs()).mean()
         loss = loss + 0.1 * (res["transient_flows_fw"].abs().mean() + res["transient_flows_bw"].abs().mean())
         loss = loss + 0.01 * (res["transient_weights_fine"] * res["static_weights_fine"]).mean()
+        mark("forward+loss")
         loss.backward()
+        mark("backward")
         if world > 1:
             flat = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
             dist.all_reduce(flat)
@@ -202,6 +213,7 @@ def run_train(args, rank, local_rank, world):
                     p.grad.copy_(flat[o:o + n].view_as(p.grad))
                     o += n
         opt.step()
+        mark("allreduce+adam")
         return loss
 
     for _ in range(max(3, args.warmup)):
@@ -223,15 +235,25 @@ def run_train(args, rank, local_rank, world):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    # one more instrumented step for the phase split (not part of the timed region)
+    phase["on"] = True
+    step()
+    torch.cuda.synchronize()
+    evs = phase["ev"]
+    split = {evs[i][0]: round(evs[i - 1][1].elapsed_time(evs[i][1]), 3) for i in range(1, len(evs))}
     if rank == 0:
         value = R * S * world * args.steps / (ms * 1e-3)
+        tc = args.grad_precision == "bf16"
         print(json.dumps({"metric": "ray-samples/sec (training step fwd+bwd+Adam)", "value": value, "unit": "ray-samples/s",
                           "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                          "dtype": "bf16 fwd / f32 bwd", "data": "synthetic",
+                          "dtype": "bf16" if tc else "bf16 fwd / f32 bwd", "data": "synthetic",
                           "config": {"workload": "training step, 1024 rays x 128 samples per GPU, full NSFF + warp, surrogate "
                                                  "photometric/cycle/flow loss, Adam (BASELINE.json configs[2])",
-                                     "backward": "fp32 CUDA-core kernels (recompute); tensor-core backward is round-2 work"},
+                                     "backward": ("bf16 tcgen05 GEMMs over tile images (recompute + dgrad + wgrad per layer)"
+                                                  if tc else "fp32 CUDA-core kernels (verification path)")},
+                          "phase_ms": split,
+                          "algorithmic_tflop_per_step": round(R * S * 14.28e6 / 1e12, 3),
                           "gpu_launches": int(_cabi.launch_count() - n0), "final_loss": float(loss)}), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -255,6 +277,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--precision", default="bf16", choices=["bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--grad-precision", default="bf16", choices=["bf16", "fp32"],
+                    help="train workload: tensor-core backward (default) or the fp32 verification backward")
     ap.add_argument("--workload", default="render", choices=["render", "train"],
                     help="render = BASELINE.json metric (default, what the driver runs); train = configs[2] step")
     args = ap.parse_args()

@@ -220,10 +220,15 @@ typedef struct {
   const void* a_img; int32_t a_chunks;   /* A: (n_rows, 64*a_chunks), every chunk is a K chunk                    */
   const void* b_blocks; int32_t N;       /* a_chunks weight blocks of N x 64 (N = 64, 128 or 256)                 */
   const float* bias;                     /* N floats or NULL                                                      */
-  int32_t epi;                           /* 0 relu->image, 1 linear->image, 2 relu-mask->image, 3 fp32 rows       */
-  void* out_img; const void* mask_img;   /* N/64 chunks per tile                                                  */
+  int32_t epi;                           /* 0 relu->image, 1 linear->image, 2 mask(image)->image, 3 fp32 rows,
+                                            4 mask(bit plane)->image                                              */
+  void* out_img; const void* mask_img;   /* N/64 chunks per tile; epi 2: out = acc where mask_img > 0             */
   float* out_rows; int32_t ld, ncols, beta; /* epi 3: out_rows[r*ld + c] (+)= acc, c < ncols                       */
   int64_t n_rows;
+  uint32_t* relu_bits;                   /* optional (image epilogues): bit plane of (out > 0), per tile
+                                            [8 words][128 rows] uint32, bit i of word w = column 32w+i            */
+  const uint32_t* mask_bits;             /* epi 4: out = acc where the bit is set                                 */
+  float* colsum;                         /* optional (image epilogues): colsum[c] += sum_r out[r, c] (fp32)       */
 } nsff_img_gemm_args;
 NSFF_API int nsff_img_gemm(const nsff_img_gemm_args* args /*host*/, void* stream);
 typedef struct {

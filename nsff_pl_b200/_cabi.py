@@ -96,7 +96,7 @@ class ImgGemmArgs(C.Structure):
     _fields_ = [("a_img", C.c_void_p), ("a_chunks", C.c_int32), ("b_blocks", C.c_void_p), ("N", C.c_int32),
                 ("bias", C.c_void_p), ("epi", C.c_int32), ("out_img", C.c_void_p), ("mask_img", C.c_void_p),
                 ("out_rows", C.c_void_p), ("ld", C.c_int32), ("ncols", C.c_int32), ("beta", C.c_int32),
-                ("n_rows", C.c_int64)]
+                ("n_rows", C.c_int64), ("relu_bits", C.c_void_p), ("mask_bits", C.c_void_p), ("colsum", C.c_void_p)]
 
 
 class ImgWgradArgs(C.Structure):

@@ -37,6 +37,20 @@ constexpr uint32_t kChunkBytes = 128 * 128;   // 128 rows x 64 bf16
 constexpr uint32_t kSmemLimit = 232448;       // 227 KB opt-in
 constexpr int kMaxK = 6;                      // K chunks of one GEMM
 
+// bulk copy with an L2 evict-first policy: operand tiles are consumed once per kernel, the output of the kernel should
+// be what stays in the 126 MB L2 for the next launch
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+      "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+      : "memory");
+}
+
 __device__ __forceinline__ uint32_t row_off(int row) { return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128); }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -103,36 +117,6 @@ __global__ void pack_blocks_kernel(const __grid_constant__ PackJobs J) {
   }
 }
 
-// column sums of an image -> db[c] += sum_rows   (bias gradients; pad rows are zero by construction)
-__global__ void __launch_bounds__(256) img_colsum_kernel(const uint8_t* __restrict__ img, uint32_t tile_stride,
-                                                         int n_chunks, int n_tiles, float* __restrict__ db) {
-  __shared__ float acc_s[64];
-  const int chunk = blockIdx.y;
-  if (threadIdx.x < 64) acc_s[threadIdx.x] = 0.f;
-  __syncthreads();
-  const int unit = threadIdx.x & 7, rr = threadIdx.x >> 3;            // rr 0..31: (row & 7) is fixed per thread
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const uint8_t* base = img + (size_t)tile * tile_stride + (size_t)chunk * kChunkBytes;
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int row = it * 32 + rr;
-      const uint4 q = *reinterpret_cast<const uint4*>(base + row_off(row) + (unit << 4));
-      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        acc[2 * i] += __uint_as_float(w[i] << 16);
-        acc[2 * i + 1] += __uint_as_float(w[i] & 0xFFFF0000u);
-      }
-    }
-  }
-  const int logical = (unit ^ rr) & 7;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) atomicAdd(&acc_s[logical * 8 + i], acc[i]);
-  __syncthreads();
-  if (threadIdx.x < 64 && chunk * 64 + threadIdx.x < n_chunks * 64) atomicAdd(db + chunk * 64 + threadIdx.x, acc_s[threadIdx.x]);
-}
-
 // pre-activation gradients of all head columns of one branch: fp32 (B,16) is not kept, only the bf16 image chunk
 // (columns >= n and rows >= B are zero) and the bias gradients.
 struct HeadSpec {
@@ -181,6 +165,67 @@ __global__ void __launch_bounds__(128) heads_dpre_kernel(const float* __restrict
   }
 }
 
+// The MLP input row of every point (rendering.py:164-173) as bf16 chunk images, one launch: PE(xyz) (63 -> 64 columns),
+// time code (48), PE(dir) (27), appearance code (48).  One thread per (row, kind): a full 128-byte image row each.
+struct EmbedImgArgs {
+  const float* xyz;       // (B,3)
+  const float* dirs;      // (R,3)
+  const float* t_table;   // (R,in_t) per-ray rows or NULL
+  const float* a_table;   // (R,in_a) per-ray rows or NULL
+  int64_t B;
+  int32_t S, n_tiles, in_xyz, in_dir, in_t, in_a;
+  uint8_t* img[4];        // PE, T, DIR, A (NULL = skip)
+};
+// sin/cos of one frequency for the three components, written to columns 3+6f .. 3+6f+5 of a 64-wide row buffer
+template <int kNFreq>
+__device__ __forceinline__ void pe_row(const float (&b)[3], float (&row)[64]) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) row[c] = b[c];
+#pragma unroll
+  for (int f = 0; f < kNFreq; ++f) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float sn, cs;
+      sincosf(__fmul_rn(exp2f((float)f), b[c]), &sn, &cs);       // freqs = 2^linspace(0, N-1, N)  (nerf.py:13)
+      row[3 + 6 * f + c] = sn;
+      row[3 + 6 * f + 3 + c] = cs;
+    }
+  }
+}
+__global__ void __launch_bounds__(128) embed_img_kernel(const __grid_constant__ EmbedImgArgs E) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // one thread per (row, kind)
+  if (idx >= (int64_t)E.n_tiles * 128 * 4) return;
+  const int kind = (int)(idx & 3);
+  const int64_t r = idx >> 2;
+  if (!E.img[kind]) return;
+  const int row = (int)(r & 127);
+  float v[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) v[i] = 0.f;
+  if (r < E.B) {
+    const int64_t ray = r / E.S;
+    if (kind == 0) {
+      const float b[3] = {E.xyz[r * 3], E.xyz[r * 3 + 1], E.xyz[r * 3 + 2]};
+      pe_row<10>(b, v);
+    } else if (kind == 2) {
+      const float b[3] = {E.dirs[ray * 3], E.dirs[ray * 3 + 1], E.dirs[ray * 3 + 2]};
+      pe_row<4>(b, v);
+    } else {
+      const float* tab = kind == 1 ? E.t_table : E.a_table;
+      if (tab) {
+#pragma unroll
+        for (int i = 0; i < 48; ++i) v[i] = tab[ray * 48 + i];
+      }
+    }
+  }
+  uint8_t* rowp = E.img[kind] + (r >> 7) * kChunkBytes + row_off(row);
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    *reinterpret_cast<uint4*>(rowp + (((u ^ row) & 7) << 4)) =
+        make_uint4(pack_bf16x2(v[u * 8], v[u * 8 + 1]), pack_bf16x2(v[u * 8 + 2], v[u * 8 + 3]),
+                   pack_bf16x2(v[u * 8 + 4], v[u * 8 + 5]), pack_bf16x2(v[u * 8 + 6], v[u * 8 + 7]));
+}
+
 // scatter of a wgrad result: acc_t is [(64*nb) x 256] fp32 with acc_t[n*256 + m] = sum_p B[p,n] A[p,m].
 //   transposed mode (layers): dW[m*ldw + dcol0[j] + c] += acc_t[(64j + c)*256 + m]   for c < ncols[j]
 //   direct mode (heads, operands swapped): row n of acc_t is the gradient of head row n: dst[n][m] += acc_t[n*256 + m]
@@ -206,7 +251,10 @@ __global__ void wgrad_finish_kernel(const __grid_constant__ FinishJob J) {
 // ------------------------------------------------------------------------------------------------------------------
 // img_gemm_kernel: K-major GEMM, weights resident in shared memory
 // ------------------------------------------------------------------------------------------------------------------
-enum GemmEpi : int32_t { GE_RELU_IMG = 0, GE_LIN_IMG = 1, GE_MASK_IMG = 2, GE_F32_ROWS = 3 };
+enum GemmEpi : int32_t { GE_RELU_IMG = 0, GE_LIN_IMG = 1, GE_MASK_IMG = 2, GE_F32_ROWS = 3, GE_MASK_BITS = 4 };
+// ReLU bit planes: per 128-row tile [8 words][128 rows] uint32, bit i of word w = (activation[row][32w + i] > 0).
+// The recompute writes them next to each activation image; the dgrad epilogue reads 16 B per row instead of 512 B.
+constexpr uint32_t kBitsPerTile = 8 * 128;   // uint32 per tile
 
 struct GemmParams {
   const uint8_t* a_base[kMaxK];   // chunk c of tile t: a_base[c] + t * a_stride[c]
@@ -222,6 +270,11 @@ struct GemmParams {
   float* out_f32;                 // GE_F32_ROWS: (n_rows, ld), columns [0, ncols)
   int32_t ld, ncols, beta;
   int64_t n_rows;
+  uint32_t* relu_bits_out;        // image epilogues, optional: bit plane of (out > 0)
+  const uint32_t* mask_bits;      // GE_MASK_BITS: out = acc where bit set else 0
+  float* colsum;                  // image epilogues, optional: colsum[c] += sum over rows of out[:, c]  (fp32, pre-rounding)
+  int32_t col0;                   // first output column of this launch inside the (<= 256 wide) output plane
+  int32_t l2_hint;                // 1: operand tiles are loaded with an L2 evict-first policy
 };
 
 constexpr int kGemmEpiWarps = 8;
@@ -272,12 +325,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) img_gemm_kernel(const __grid_
       for (int c = 0; c < P.n_chunks; ++c)
         bulk_g2s(sB + (uint32_t)c * blk_bytes, P.b_blocks + (size_t)c * blk_bytes, blk_bytes, bar(GB_B_FULL));
       uint32_t stage = 0, par = 1;
+      const uint64_t pol = policy_evict_first();
       for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
         for (int c = 0; c < P.n_chunks; ++c) {
           mbar_wait(bar(GB_A_EMPTY + stage), par);
           mbar_arrive_expect_tx(bar(GB_A_FULL + stage), kChunkBytes);
-          bulk_g2s(sA + stage * kChunkBytes, P.a_base[c] + (size_t)tile * P.a_stride[c], kChunkBytes,
-                   bar(GB_A_FULL + stage));
+          if (P.l2_hint)
+            bulk_g2s_hint(sA + stage * kChunkBytes, P.a_base[c] + (size_t)tile * P.a_stride[c], kChunkBytes,
+                          bar(GB_A_FULL + stage), pol);
+          else
+            bulk_g2s(sA + stage * kChunkBytes, P.a_base[c] + (size_t)tile * P.a_stride[c], kChunkBytes,
+                     bar(GB_A_FULL + stage));
           if (++stage == (uint32_t)P.stages) stage = 0, par ^= 1u;
         }
       }
@@ -313,63 +371,119 @@ __global__ void __launch_bounds__(kGemmThreads, 1) img_gemm_kernel(const __grid_
     const int row = q * 32 + lane;
     const uint32_t roff = row_off(row);
     const int rsw = row & 7;
-    const int c_begin = half * (P.N / 2), c_end = c_begin + P.N / 2;
+    const int c_begin = half * (P.N / 2);
+    const int n_batches = P.N / 64;                         // 32-column batches of this warp: 1, 2 or 4
+    const int word0 = (P.col0 + c_begin) >> 5;
+    float colacc[4] = {0.f, 0.f, 0.f, 0.f};
     uint32_t local = 0;
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++local) {
       const uint32_t slot = local & 1u, use = local >> 1;
+      // the ReLU bits of this row are fetched before the accumulator is awaited: off the critical path
+      uint32_t mbits[4] = {~0u, ~0u, ~0u, ~0u};
+      if (P.epi == GE_MASK_BITS) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (b < n_batches) mbits[b] = P.mask_bits[(size_t)tile * kBitsPerTile + (size_t)(word0 + b) * 128 + row];
+      }
       mbar_wait(bar(GB_ACC_FULL + slot), use & 1u);
       tc_fence_after_sync();
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 256u;
       const int64_t p = (int64_t)tile * 128 + row;
-      for (int cb = c_begin; cb < c_end; cb += 32) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (b >= n_batches) break;
+        const int cb = c_begin + 32 * b;
         uint32_t v[32];
         tmem_ld32(t_acc + (uint32_t)cb, v);
         tmem_ld_wait();
         if (P.epi == GE_F32_ROWS) {
           if (p < P.n_rows) {
-            float* o = P.out_f32 + p * P.ld;
+            float* o = P.out_f32 + p * P.ld + cb;
+            const bool vec = ((P.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.out_f32) & 15) == 0);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int col = cb + i;
-              if (col < P.ncols) {
-                const float x = __uint_as_float(v[i]) + bias_s[col];
-                o[col] = P.beta ? o[col] + x : x;
+            for (int i = 0; i < 32; i += 4) {
+              if (vec && cb + i + 4 <= P.ncols) {
+                float4 x = make_float4(__uint_as_float(v[i]) + bias_s[cb + i], __uint_as_float(v[i + 1]) + bias_s[cb + i + 1],
+                                       __uint_as_float(v[i + 2]) + bias_s[cb + i + 2], __uint_as_float(v[i + 3]) + bias_s[cb + i + 3]);
+                if (P.beta) {
+                  const float4 y = *reinterpret_cast<const float4*>(o + i);
+                  x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+                }
+                *reinterpret_cast<float4*>(o + i) = x;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  if (cb + i + j < P.ncols) {
+                    const float x = __uint_as_float(v[i + j]) + bias_s[cb + i + j];
+                    o[i + j] = P.beta ? o[i + j] + x : x;
+                  }
+                }
               }
             }
           }
         } else {
-          const size_t off = (size_t)tile * P.out_stride + (size_t)(cb >> 6) * kChunkBytes + roff;
-          const int unit0 = (cb & 63) >> 3;
+          const int gc = P.col0 + cb;                                   // column inside the output plane
+          const size_t off = (size_t)tile * P.out_stride + (size_t)(gc >> 6) * kChunkBytes + roff;
+          const int unit0 = (gc & 63) >> 3;
+          uint32_t mb = mbits[b];
+          if (P.epi == GE_MASK_IMG) {
+            // ReLU mask given as an activation image: max(x,0) in bf16, so "> 0" == "any magnitude bit set"
+            mb = 0;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float f[8];
+            for (int u = 0; u < 4; ++u) {
+              const uint4 mk = *reinterpret_cast<const uint4*>(P.mask_img + (size_t)tile * P.mask_stride +
+                                                               (size_t)(gc >> 6) * kChunkBytes + roff +
+                                                               ((uint32_t)(((unit0 + u) ^ rsw) & 7) << 4));
+              const uint32_t w4[4] = {mk.x, mk.y, mk.z, mk.w};
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[u * 8 + i]) + bias_s[cb + u * 8 + i];
-            const uint32_t uo = (uint32_t)(((unit0 + u) ^ rsw) & 7) << 4;
-            uint4 w;
-            if (P.epi == GE_RELU_IMG) {
-              w = make_uint4(pack_bf16x2_relu(f[0], f[1]), pack_bf16x2_relu(f[2], f[3]), pack_bf16x2_relu(f[4], f[5]),
-                             pack_bf16x2_relu(f[6], f[7]));
-            } else {
-              w = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                             pack_bf16x2(f[6], f[7]));
-              if (P.epi == GE_MASK_IMG) {
-                // ReLU mask: the stored activation is max(x,0) in bf16, so "> 0" == "any magnitude bit set"
-                const uint4 mk = *reinterpret_cast<const uint4*>(P.mask_img + (size_t)tile * P.mask_stride +
-                                                                 (size_t)(cb >> 6) * kChunkBytes + roff + uo);
-                auto sel = [](uint32_t x, uint32_t m) {
-                  return x & (((m & 0x7FFFu) ? 0xFFFFu : 0u) | ((m & 0x7FFF0000u) ? 0xFFFF0000u : 0u));
-                };
-                w.x = sel(w.x, mk.x); w.y = sel(w.y, mk.y); w.z = sel(w.z, mk.z); w.w = sel(w.w, mk.w);
+              for (int k = 0; k < 4; ++k) {
+                mb |= ((w4[k] & 0x7FFFu) ? 1u : 0u) << (u * 8 + 2 * k);
+                mb |= ((w4[k] & 0x7FFF0000u) ? 1u : 0u) << (u * 8 + 2 * k + 1);
               }
             }
-            *reinterpret_cast<uint4*>(P.out_img + off + uo) = w;
+          }
+          float f[32];
+          uint32_t pos_bits = 0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float x = __uint_as_float(v[i]) + bias_s[cb + i];
+            if (P.epi == GE_RELU_IMG) x = fmaxf(x, 0.f);
+            if (P.epi == GE_MASK_IMG || P.epi == GE_MASK_BITS) x = ((mb >> i) & 1u) ? x : 0.f;
+            pos_bits |= (x > 0.f ? 1u : 0u) << i;
+            f[i] = x;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t uo = (uint32_t)(((unit0 + u) ^ rsw) & 7) << 4;
+            *reinterpret_cast<uint4*>(P.out_img + off + uo) =
+                make_uint4(pack_bf16x2(f[u * 8], f[u * 8 + 1]), pack_bf16x2(f[u * 8 + 2], f[u * 8 + 3]),
+                           pack_bf16x2(f[u * 8 + 4], f[u * 8 + 5]), pack_bf16x2(f[u * 8 + 6], f[u * 8 + 7]));
+          }
+          if (P.relu_bits_out) P.relu_bits_out[(size_t)tile * kBitsPerTile + (size_t)(gc >> 5) * 128 + row] = pos_bits;
+          if (P.colsum) {
+            // transpose-reduce over the warp's 32 rows: after the butterfly lane L holds the sum of column cb + L
+#pragma unroll
+            for (int o2 = 16; o2 >= 1; o2 >>= 1) {
+              const bool upper = (lane & o2) != 0;
+#pragma unroll
+              for (int i = 0; i < o2; ++i) {
+                const float keep = upper ? f[i + o2] : f[i];
+                const float send = upper ? f[i] : f[i + o2];
+                f[i] = keep + __shfl_xor_sync(0xffffffffu, send, o2);
+              }
+            }
+            colacc[b] += f[0];
           }
         }
       }
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(GB_ACC_EMPTY + slot));
+    }
+    if (P.colsum && P.epi != GE_F32_ROWS) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (b < n_batches) atomicAdd(P.colsum + c_begin + 32 * b + lane, colacc[b]);
     }
   }
 
@@ -390,7 +504,7 @@ struct WgradParams {
   uint32_t a_stride;
   const uint8_t* b_base[4];       // nb chunks (N = 64*nb channels)
   uint32_t b_stride[4];
-  int32_t nb, n_tiles, variant;
+  int32_t nb, n_tiles, l2_hint;
   float* acc_t;                   // [(64*nb) x 256]
 };
 constexpr int kWgEpiWarps = 8;
@@ -446,6 +560,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) img_wgrad_kernel(const __grid_c
     if (warp == kWgEpiWarps) {
       if (elect_one()) {
         uint32_t stage = 0, par = 1;
+        const uint64_t pol = policy_evict_first();
         const uint32_t bytes = (4u + (uint32_t)P.nb) * kHalfChunk;
         for (int h = 0; h < n_half; ++h) {
           const size_t tile = (size_t)(t0 + (h >> 1));
@@ -453,12 +568,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) img_wgrad_kernel(const __grid_c
           mbar_wait(bar(WB_EMPTY + stage), par);
           mbar_arrive_expect_tx(bar(WB_FULL + stage), bytes);
           const uint32_t s0 = base + stage * kWgStageBytes;
-          for (int c = 0; c < 4; ++c)
-            bulk_g2s(s0 + (uint32_t)c * kHalfChunk, P.a_base + tile * P.a_stride + (size_t)c * kChunkBytes + hoff,
-                     kHalfChunk, bar(WB_FULL + stage));
-          for (int j = 0; j < P.nb; ++j)
-            bulk_g2s(s0 + (uint32_t)(4 + j) * kHalfChunk, P.b_base[j] + tile * P.b_stride[j] + hoff, kHalfChunk,
-                     bar(WB_FULL + stage));
+          for (int c = 0; c < 4 + P.nb; ++c) {
+            const uint8_t* src = c < 4 ? P.a_base + tile * P.a_stride + (size_t)c * kChunkBytes + hoff
+                                       : P.b_base[c - 4] + tile * P.b_stride[c - 4] + hoff;
+            if (P.l2_hint) bulk_g2s_hint(s0 + (uint32_t)c * kHalfChunk, src, kHalfChunk, bar(WB_FULL + stage), pol);
+            else bulk_g2s(s0 + (uint32_t)c * kHalfChunk, src, kHalfChunk, bar(WB_FULL + stage));
+          }
           if (++stage == kWgStages) stage = 0, par ^= 1u;
         }
       }
@@ -466,7 +581,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) img_wgrad_kernel(const __grid_c
       if (elect_one()) {
         // M = 128 channels of A per MMA, N = 64*nb channels of B, K = 16 points; both MN-major (bits 15, 16)
         const uint32_t idesc = make_idesc_bf16(128, N) | (1u << 15) | (1u << 16);
-        const uint32_t lbo = P.variant == 1 ? 1024u : kHalfChunk, sbo = P.variant == 1 ? kHalfChunk : 1024u;
+        const uint32_t lbo = kHalfChunk, sbo = 1024u;     // MN groups (64 channels) 8 KB apart, K groups (8 points) 1 KB apart
         uint32_t stage = 0, par = 0;
         for (int h = 0; h < n_half; ++h) {
           mbar_wait(bar(WB_FULL + stage), par);
@@ -531,6 +646,15 @@ static int check_arch() {
   return major == 10 ? NSFF_OK : NSFF_EARCH;
 }
 
+static int l2_hint_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NSFF_BWD_L2HINT");     // A/B knob; measured 6.97 -> 6.82 ms per training step
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
 static int launch_gemm(GemmParams& P, cudaStream_t st) {
   if (P.n_tiles <= 0) return NSFF_OK;
   if (P.n_chunks < 1 || P.n_chunks > kMaxK || (P.N != 256 && P.N != 128 && P.N != 64)) return NSFF_EINVAL;
@@ -539,6 +663,7 @@ static int launch_gemm(GemmParams& P, cudaStream_t st) {
   if (stages > kGemmMaxStages) stages = kGemmMaxStages;
   if (stages < 2) return NSFF_EUNSUPPORTED;
   P.stages = stages;
+  P.l2_hint = l2_hint_enabled();
   const uint32_t smem = fixed + (uint32_t)stages * kChunkBytes;
   static bool attr_set = false;
   if (!attr_set) {
@@ -559,12 +684,7 @@ static int launch_wgrad(WgradParams& P, cudaStream_t st) {
     NSFF_CUDA_TRY(cudaFuncSetAttribute(img_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem));
     attr_set = true;
   }
-  static int variant = -1;
-  if (variant < 0) {
-    const char* e = getenv("NSFF_WG_DESC");
-    variant = e ? atoi(e) : 0;
-  }
-  P.variant = variant;
+  P.l2_hint = l2_hint_enabled();
   int grid = sm_count();
   if (grid > P.n_tiles) grid = P.n_tiles;
   img_wgrad_kernel<<<grid, kWgThreads, kWgSmem, st>>>(P);
@@ -577,8 +697,10 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 // All blocks are N x 64 bf16 (N = 256, or 128 for the "trunk input" extras), zero where no weight maps.
 struct Blk {
   uint32_t off;
-  int n;        // number of consecutive blocks
+  int n;        // number of consecutive blocks (per half when split)
   int N;
+  int split;    // 1: the 256 output columns are packed as two halves of n blocks of 128 x 64 each (two launches): used
+                // for 6-chunk layers, whose 192 KB of resident weights would leave only a 2-deep A ring
 };
 struct BwdPack {
   // forward (recompute): W blocks, K chunks in the order the GEMM consumes them
@@ -593,8 +715,8 @@ struct PackBuilder {
   std::vector<PackJob> jobs;   // only filled when dst != nullptr
   uint8_t* dst = nullptr;
   uint32_t off = 0;
-  Blk alloc(int n, int N) {
-    Blk b{off, n, N};
+  Blk alloc(int n, int N, bool split = false) {
+    Blk b{off, n, split ? 128 : N, split ? 1 : 0};
     off += (uint32_t)n * (uint32_t)N * 128u;
     return b;
   }
@@ -603,6 +725,11 @@ struct PackBuilder {
     if (!dst || !src || n_valid <= 0 || k_valid <= 0) return;
     PackJob j{src, dst + b.off + (size_t)idx * b.N * 128, ld, T ? 1 : 0, n0, k0, n_valid, k_valid, dk0, dn0};
     jobs.push_back(j);
+  }
+  // forward-type block idx (K chunk) of a possibly split layer: rows [0,256) of src, columns [k0, k0+k_valid)
+  void job_fwd(const Blk& b, int idx, const float* src, int ld, int k0, int k_valid) {
+    if (!b.split) return job(b, idx, src, ld, false, 0, k0, 256, k_valid);
+    for (int h = 0; h < 2; ++h) job(b, h * b.n + idx, src, ld, false, 128 * h, k0, 128, k_valid);
   }
 };
 
@@ -629,6 +756,7 @@ static int supported(const nsff_field_desc* d) {
 
 // Lays the blocks out (always) and, when pb.dst is set, emits the pack jobs reading `p`.
 static void build_pack(const nsff_field_desc* d, const nsff_field_params* p, BwdPack& L, PackBuilder& pb) {
+  memset(&L, 0, sizeof(L));
   const int W = 256, nx = d->in_xyz, nt = d->in_t, sk = d->skip;
   auto trunk = [&](bool trans, Blk* fwd, Blk* hidT) {
     const int n_in = trans ? nx + nt : nx;
@@ -638,18 +766,18 @@ static void build_pack(const nsff_field_desc* d, const nsff_field_params* p, Bwd
       const int ld = first ? n_in : (skip ? n_in + W : W);
       const int n_extra = (first || skip) ? (trans ? 2 : 1) : 0;
       const int n_hid = first ? 0 : 4;
-      fwd[i] = pb.alloc(n_extra + n_hid, 256);
+      fwd[i] = pb.alloc(n_extra + n_hid, 256, n_extra + n_hid > 5);
       const float* src = w ? w[i] : nullptr;
       if (n_extra) {
-        pb.job(fwd[i], 0, src, ld, false, 0, 0, 256, nx);
-        if (trans) pb.job(fwd[i], 1, src, ld, false, 0, nx, 256, nt);
+        pb.job_fwd(fwd[i], 0, src, ld, 0, nx);
+        if (trans) pb.job_fwd(fwd[i], 1, src, ld, nx, nt);
       }
-      for (int j = 0; j < n_hid; ++j) pb.job(fwd[i], n_extra + j, src, ld, false, 0, (skip ? n_in : 0) + 64 * j, 256, 64);
+      for (int j = 0; j < n_hid; ++j) pb.job_fwd(fwd[i], n_extra + j, src, ld, (skip ? n_in : 0) + 64 * j, 64);
       if (!first) {
         hidT[i] = pb.alloc(4, 256);
         for (int j = 0; j < 4; ++j) pb.job(hidT[i], j, src, ld, true, skip ? n_in : 0, 64 * j, 256, 64);
       } else {
-        hidT[i] = Blk{0, 0, 0};
+        hidT[i] = Blk{0, 0, 0, 0};
       }
     }
   };
@@ -666,15 +794,15 @@ static void build_pack(const nsff_field_desc* d, const nsff_field_params* p, Bwd
   if (d->use_viewdir) {
     const int ldd = W + d->in_dir + d->in_a;
     const float* wd = p ? p->static_dir_w : nullptr;
-    L.s_dir = pb.alloc(4 + 1 + (d->in_a > 0 ? 1 : 0), 256);
+    L.s_dir = pb.alloc(4 + 1 + (d->in_a > 0 ? 1 : 0), 256, d->in_a > 0);
     L.s_dirT = pb.alloc(4, 256);
     for (int j = 0; j < 4; ++j) {
-      pb.job(L.s_dir, j, wd, ldd, false, 0, 64 * j, 256, 64);
+      pb.job_fwd(L.s_dir, j, wd, ldd, 64 * j, 64);
       pb.job(L.s_dirT, j, wd, ldd, true, 0, 64 * j, 256, 64);
     }
-    pb.job(L.s_dir, 4, wd, ldd, false, 0, W, 256, d->in_dir);
+    pb.job_fwd(L.s_dir, 4, wd, ldd, W, d->in_dir);
     if (d->in_a > 0) {
-      pb.job(L.s_dir, 5, wd, ldd, false, 0, W + d->in_dir, 256, d->in_a);
+      pb.job_fwd(L.s_dir, 5, wd, ldd, W + d->in_dir, d->in_a);
       L.s_dirxT = pb.alloc(4, 128);
       for (int j = 0; j < 4; ++j) pb.job(L.s_dirxT, j, wd, ldd, true, W, 64 * j, d->in_dir + d->in_a, 64);
     }
@@ -704,8 +832,8 @@ static void build_pack(const nsff_field_desc* d, const nsff_field_params* p, Bwd
 
 // ---- scratch --------------------------------------------------------------------------------------------------------
 struct Scratch {
-  float* X;
   uint8_t *PE, *T, *DIR, *A, *SH[8], *SFEAT, *SDIRO, *TH[8], *TFEAT, *G0, *G1, *DP;
+  uint32_t *SHB[8], *SDIROB, *THB[8];       // ReLU bit planes of the activations above
   float *DIN, *ACC;
   size_t acc_bytes, total;
 };
@@ -720,12 +848,14 @@ static Scratch carve(const nsff_field_desc* d, int64_t B, uint8_t* base) {
     o += align_up(bytes, 1024);
     return p;
   };
-  const int cin = d->in_xyz + d->in_dir + d->in_a + d->in_t;
-  s.X = reinterpret_cast<float*>(take((size_t)B * cin * sizeof(float)));
+  const size_t bits = nt * kBitsPerTile * sizeof(uint32_t);
   s.PE = take(one); s.T = take(one); s.DIR = take(one); s.A = take(one);
-  for (int i = 0; i < 8; ++i) s.SH[i] = take(four);
-  s.SFEAT = take(four); s.SDIRO = take(four);
-  for (int i = 0; i < 8; ++i) s.TH[i] = take(d->has_transient ? four : 0);
+  for (int i = 0; i < 8; ++i) s.SH[i] = take(four), s.SHB[i] = reinterpret_cast<uint32_t*>(take(bits));
+  s.SFEAT = take(four); s.SDIRO = take(four); s.SDIROB = reinterpret_cast<uint32_t*>(take(bits));
+  for (int i = 0; i < 8; ++i) {
+    s.TH[i] = take(d->has_transient ? four : 0);
+    s.THB[i] = reinterpret_cast<uint32_t*>(take(d->has_transient ? bits : 0));
+  }
   s.TFEAT = take(d->has_transient ? four : 0);
   s.G0 = take(four); s.G1 = take(four); s.DP = take(one);
   s.DIN = reinterpret_cast<float*>(take((size_t)B * 128 * sizeof(float)));
@@ -753,18 +883,31 @@ struct Ctx {
   size_t acc_used, acc_cap;   // in floats
 };
 
-static int gemm_img(Ctx& c, const std::vector<Src>& a, const Blk& blk, const float* bias, int epi, uint8_t* out_img,
-                    const uint8_t* mask_img) {
+struct GemmOut {
+  int epi;
+  uint8_t* out_img;                      // 4-chunk (or N/64-chunk) image
+  const float* bias = nullptr;
+  const uint32_t* mask_bits = nullptr;   // GE_MASK_BITS
+  uint32_t* relu_bits = nullptr;         // optional bit plane of (out > 0)
+  float* colsum = nullptr;               // optional column sums (bias gradient)
+};
+static int gemm_img(Ctx& c, const std::vector<Src>& a, const Blk& blk, const GemmOut& o) {
   if ((int)a.size() != blk.n) return NSFF_EINVAL;
   GemmParams P;
   memset(&P, 0, sizeof(P));
   for (size_t i = 0; i < a.size(); ++i) P.a_base[i] = a[i].p, P.a_stride[i] = a[i].stride, P.kcnt[i] = (uint8_t)a[i].kcnt;
-  P.n_tiles = c.n_tiles; P.n_chunks = blk.n; P.N = blk.N; P.epi = epi;
-  P.b_blocks = c.pack + blk.off; P.bias = bias;
-  P.out_img = out_img; P.out_stride = (uint32_t)(blk.N / 64) * kChunkBytes;
-  P.mask_img = mask_img; P.mask_stride = P.out_stride;
+  P.n_tiles = c.n_tiles; P.n_chunks = blk.n; P.N = blk.N; P.epi = o.epi;
+  P.out_img = o.out_img; P.out_stride = (uint32_t)(blk.split ? 4 : blk.N / 64) * kChunkBytes;
+  P.mask_bits = o.mask_bits; P.relu_bits_out = o.relu_bits;
   P.n_rows = c.B;
-  return launch_gemm(P, c.st);
+  for (int h = 0; h < (blk.split ? 2 : 1); ++h) {
+    P.b_blocks = c.pack + blk.off + (size_t)h * blk.n * blk.N * 128;
+    P.bias = o.bias ? o.bias + h * 128 : nullptr;
+    P.colsum = o.colsum ? o.colsum + h * 128 : nullptr;
+    P.col0 = h * 128;
+    TRY(launch_gemm(P, c.st));
+  }
+  return NSFF_OK;
 }
 static int gemm_rows(Ctx& c, const std::vector<Src>& a, const Blk& blk, float* out, int ld, int ncols, int beta) {
   if ((int)a.size() != blk.n) return NSFF_EINVAL;
@@ -814,18 +957,6 @@ static int finish_rows(Ctx& c, const float* acc, float* const (&drow)[16]) {
   wgrad_finish_kernel<<<16, 256, 0, c.st>>>(J);
   return after_launch();
 }
-static int colsum(Ctx& c, const uint8_t* img4, float* db) {
-  if (!db) return NSFF_EINVAL;
-  int gx = c.n_tiles < 64 ? c.n_tiles : 64;
-  img_colsum_kernel<<<dim3((unsigned)gx, 4), 256, 0, c.st>>>(img4, 4 * kChunkBytes, 4, c.n_tiles, db);
-  return after_launch();
-}
-static int rows_to_img(Ctx& c, const float* src, int ld, int col0, int ncols, uint8_t* img) {
-  const int64_t n = (int64_t)c.n_tiles * 128 * 8;
-  rows_to_img_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, c.st>>>(src, ld, col0, ncols, c.B, img, kChunkBytes, c.n_tiles);
-  return after_launch();
-}
-
 struct Trunk {
   bool trans;
   const Blk* fwd;
@@ -834,6 +965,7 @@ struct Trunk {
   float* const* gw;
   float* const* gb;
   uint8_t* const* H;
+  uint32_t* const* HB;     // ReLU bit planes of H
   std::vector<Src> in;     // trunk input chunks ([PE] or [PE, T])
   int n_in;
 };
@@ -846,12 +978,16 @@ static int trunk_forward(Ctx& c, const nsff_field_desc* d, const Trunk& t) {
       auto h = four(t.H[i - 1]);
       a.insert(a.end(), h.begin(), h.end());
     }
-    TRY(gemm_img(c, a, t.fwd[i], t.b[i], GE_RELU_IMG, t.H[i], nullptr));
+    GemmOut o{GE_RELU_IMG, t.H[i]};
+    o.bias = t.b[i];
+    o.relu_bits = t.HB[i];
+    TRY(gemm_img(c, a, t.fwd[i], o));
   }
   return NSFF_OK;
 }
 
-// g_cur holds dZ_8 (gradient w.r.t. the pre-activation of the last trunk layer).  d_in (fp32 (B,128)) receives the
+// g_cur holds dZ_8 (gradient w.r.t. the pre-activation of the last trunk layer; its column sums - the bias gradient
+// of layer 8 - were accumulated by the GEMM that produced it).  d_in (fp32 (B,128)) receives the
 // gradient w.r.t. the trunk input columns [PE | t], accumulated over the skip layer and layer 1.
 static int trunk_backward(Ctx& c, const nsff_field_desc* d, const Trunk& t, uint8_t* g_cur, uint8_t* g_next,
                           const Blk* in1T, const Blk* in5T, float* d_in) {
@@ -860,7 +996,6 @@ static int trunk_backward(Ctx& c, const nsff_field_desc* d, const Trunk& t, uint
     const bool first = i == 0, skip = i == d->skip;
     const int in_k = first ? t.n_in : (skip ? t.n_in + W : W);
     if (!t.gw[i] || !t.gb[i]) return NSFF_EINVAL;
-    TRY(colsum(c, g_cur, t.gb[i]));
     float* acc;
     if (!first) {
       TRY(wgrad_img(c, g_cur, four(t.H[i - 1]), &acc));
@@ -874,7 +1009,11 @@ static int trunk_backward(Ctx& c, const nsff_field_desc* d, const Trunk& t, uint
       if (d_in) TRY(gemm_rows(c, four(g_cur), first ? *in1T : *in5T, d_in, 128, t.n_in, first ? 1 : 0));
     }
     if (!first) {
-      TRY(gemm_img(c, four(g_cur), t.hidT[i], nullptr, GE_MASK_IMG, g_next, t.H[i - 1]));
+      if (!t.gb[i - 1]) return NSFF_EINVAL;
+      GemmOut o{GE_MASK_BITS, g_next};
+      o.mask_bits = t.HB[i - 1];
+      o.colsum = t.gb[i - 1];                                   // bias gradient of layer i-1 = column sums of dZ_{i-1}
+      TRY(gemm_img(c, four(g_cur), t.hidT[i], o));
       uint8_t* tmp = g_cur; g_cur = g_next; g_next = tmp;
     }
   }
@@ -945,13 +1084,21 @@ int nsff_field_backward_tc(const nsff_field_desc* d, const nsff_field_params* p,
   if (d_t) NSFF_CUDA_TRY(cudaMemsetAsync(d_t, 0, (size_t)R * d->in_t * sizeof(float), st));
   if (d_a) NSFF_CUDA_TRY(cudaMemsetAsync(d_a, 0, (size_t)R * d->in_a * sizeof(float), st));
 
-  // ---- inputs: embedded row (fp32, shared with the fp32 path) -> bf16 chunk images ----
-  const int cin = d->in_xyz + d->in_dir + d->in_a + d->in_t;
-  TRY(launch_embed_rows(d, pts, s.X, cin, st));
-  TRY(rows_to_img(c, s.X, cin, 0, d->in_xyz, s.PE));
-  if (d->use_viewdir) TRY(rows_to_img(c, s.X, cin, d->in_xyz, d->in_dir, s.DIR));
-  if (d->in_a > 0) TRY(rows_to_img(c, s.X, cin, d->in_xyz + d->in_dir, d->in_a, s.A));
-  if (want_t) TRY(rows_to_img(c, s.X, cin, d->in_xyz + d->in_dir + d->in_a, d->in_t, s.T));
+  // ---- inputs: the embedded row of every point as bf16 chunk images ----
+  {
+    EmbedImgArgs E;
+    memset(&E, 0, sizeof(E));
+    E.xyz = pts->xyz; E.dirs = pts->dirs; E.t_table = pts->t_table; E.a_table = pts->a_table;
+    E.B = B; E.S = pts->S; E.n_tiles = c.n_tiles;
+    E.in_xyz = d->in_xyz; E.in_dir = d->in_dir; E.in_t = d->in_t; E.in_a = d->in_a;
+    E.img[0] = s.PE;
+    E.img[1] = want_t ? s.T : nullptr;
+    E.img[2] = (want_s && d->use_viewdir) ? s.DIR : nullptr;
+    E.img[3] = (want_s && d->in_a > 0) ? s.A : nullptr;
+    if (E.img[2] && !pts->dirs) return NSFF_EINVAL;
+    embed_img_kernel<<<(unsigned)cdiv64((int64_t)c.n_tiles * 128 * 4, 128), 128, 0, st>>>(E);
+    TRY(after_launch());
+  }
   const Src pe = chunk_of(s.PE, 1, 0, 4), tc = chunk_of(s.T, 1, 0, 3), dirc = chunk_of(s.DIR, 1, 0, 2),
             ac = chunk_of(s.A, 1, 0, 3), dp = chunk_of(s.DP, 1, 0, 1);
   int col = 0;
@@ -963,16 +1110,23 @@ int nsff_field_backward_tc(const nsff_field_desc* d, const nsff_field_params* p,
   float* acc;
 
   if (want_s) {
-    Trunk t{false, L.s_fwd, L.s_hidT, p->static_b, g->static_w, g->static_b, s.SH, {pe}, d->in_xyz};
+    Trunk t{false, L.s_fwd, L.s_hidT, p->static_b, g->static_w, g->static_b, s.SH, s.SHB, {pe}, d->in_xyz};
     // ---- recompute, keeping every layer ----
     TRY(trunk_forward(c, d, t));
-    TRY(gemm_img(c, four(s.SH[7]), L.s_fin, p->static_final_b, GE_LIN_IMG, s.SFEAT, nullptr));
+    {
+      GemmOut o{GE_LIN_IMG, s.SFEAT};
+      o.bias = p->static_final_b;
+      TRY(gemm_img(c, four(s.SH[7]), L.s_fin, o));
+    }
     const uint8_t* rgb_in = s.SFEAT;
     if (d->use_viewdir) {
       std::vector<Src> a = four(s.SFEAT);
       a.push_back(dirc);
       if (d->in_a > 0) a.push_back(ac);
-      TRY(gemm_img(c, a, L.s_dir, p->static_dir_b, GE_RELU_IMG, s.SDIRO, nullptr));
+      GemmOut o{GE_RELU_IMG, s.SDIRO};
+      o.bias = p->static_dir_b;
+      o.relu_bits = s.SDIROB;
+      TRY(gemm_img(c, a, L.s_dir, o));
       rgb_in = s.SDIRO;
     }
     // ---- heads: image columns 0..2 = rgb (sigmoid), 3 = sigma ----
@@ -994,8 +1148,13 @@ int nsff_field_backward_tc(const nsff_field_desc* d, const nsff_field_params* p,
     uint8_t *g_fin, *other;
     if (d->use_viewdir) {
       const int kd = W + d->in_dir + d->in_a;
-      TRY(gemm_img(c, {dp}, L.s_rgbT, nullptr, GE_MASK_IMG, s.G0, s.SDIRO));          // dZ_dir
-      TRY(colsum(c, s.G0, g->static_dir_b));
+      if (!g->static_dir_w || !g->static_dir_b) return NSFF_EINVAL;
+      {
+        GemmOut o{GE_MASK_BITS, s.G0};                                                     // dZ_dir
+        o.mask_bits = s.SDIROB;
+        o.colsum = g->static_dir_b;
+        TRY(gemm_img(c, {dp}, L.s_rgbT, o));
+      }
       TRY(wgrad_img(c, s.G0, four(s.SFEAT), &acc));
       TRY(finish_cols(c, acc, g->static_dir_w, kd, {0, 64, 128, 192}, {64, 64, 64, 64}));
       if (d->in_a > 0) {
@@ -1009,28 +1168,41 @@ int nsff_field_backward_tc(const nsff_field_desc* d, const nsff_field_params* p,
         TRY(wgrad_img(c, s.G0, {dirc}, &acc));
         TRY(finish_cols(c, acc, g->static_dir_w, kd, {W}, {d->in_dir}));
       }
-      TRY(gemm_img(c, four(s.G0), L.s_dirT, nullptr, GE_LIN_IMG, s.G1, nullptr));       // dFEAT = dZ_final
+      {
+        GemmOut o{GE_LIN_IMG, s.G1};                                                       // dFEAT = dZ_final
+        o.colsum = g->static_final_b;
+        TRY(gemm_img(c, four(s.G0), L.s_dirT, o));
+      }
       g_fin = s.G1, other = s.G0;
     } else {
-      TRY(gemm_img(c, {dp}, L.s_rgbT, nullptr, GE_LIN_IMG, s.G0, nullptr));
+      GemmOut o{GE_LIN_IMG, s.G0};
+      o.colsum = g->static_final_b;
+      TRY(gemm_img(c, {dp}, L.s_rgbT, o));
       g_fin = s.G0, other = s.G1;
     }
-    TRY(colsum(c, g_fin, g->static_final_b));
+    if (!g->static_final_b || !g->static_final_w || !g->static_b[7]) return NSFF_EINVAL;
     TRY(wgrad_img(c, g_fin, four(s.SH[7]), &acc));
     TRY(finish_cols(c, acc, g->static_final_w, W, {0, 64, 128, 192}, {64, 64, 64, 64}));
     {
       std::vector<Src> a = four(g_fin);
       a.push_back(dp);
-      TRY(gemm_img(c, a, L.s_finT, nullptr, GE_MASK_IMG, other, s.SH[7]));              // dZ_8 (incl. sigma head)
+      GemmOut o{GE_MASK_BITS, other};                                                      // dZ_8 (incl. sigma head)
+      o.mask_bits = s.SHB[7];
+      o.colsum = g->static_b[7];
+      TRY(gemm_img(c, a, L.s_finT, o));
     }
     // static positions never carry gradient (the warped passes evaluate the dynamic branch only)
     TRY(trunk_backward(c, d, t, other, g_fin, nullptr, nullptr, nullptr));
     col += 4;
   }
   if (want_t) {
-    Trunk t{true, L.t_fwd, L.t_hidT, p->trans_b, g->trans_w, g->trans_b, s.TH, {pe, tc}, d->in_xyz + d->in_t};
+    Trunk t{true, L.t_fwd, L.t_hidT, p->trans_b, g->trans_w, g->trans_b, s.TH, s.THB, {pe, tc}, d->in_xyz + d->in_t};
     TRY(trunk_forward(c, d, t));
-    TRY(gemm_img(c, four(s.TH[7]), L.t_fin, p->trans_final_b, GE_LIN_IMG, s.TFEAT, nullptr));
+    {
+      GemmOut o{GE_LIN_IMG, s.TFEAT};
+      o.bias = p->trans_final_b;
+      TRY(gemm_img(c, four(s.TH[7]), L.t_fin, o));
+    }
     // ---- heads: image columns 0..2 rgb, 3 sigma, 4..6 flow fw, 7..9 flow bw (fixed, whatever the mask) ----
     HeadSpec H;
     memset(&H, 0, sizeof(H));
@@ -1059,11 +1231,20 @@ int nsff_field_backward_tc(const nsff_field_desc* d, const nsff_field_params* p,
     TRY(heads(H));
     TRY(wgrad_img(c, s.TFEAT, {dp}, &acc));
     TRY(finish_rows(c, acc, rows));
-    TRY(gemm_img(c, {dp}, L.t_headT, nullptr, GE_LIN_IMG, s.G0, nullptr));               // dTFEAT = dZ_final
-    TRY(colsum(c, s.G0, g->trans_final_b));
+    if (!g->trans_final_b || !g->trans_final_w || !g->trans_b[7]) return NSFF_EINVAL;
+    {
+      GemmOut o{GE_LIN_IMG, s.G0};                                                         // dTFEAT = dZ_final
+      o.colsum = g->trans_final_b;
+      TRY(gemm_img(c, {dp}, L.t_headT, o));
+    }
     TRY(wgrad_img(c, s.G0, four(s.TH[7]), &acc));
     TRY(finish_cols(c, acc, g->trans_final_w, W, {0, 64, 128, 192}, {64, 64, 64, 64}));
-    TRY(gemm_img(c, four(s.G0), L.t_finT, nullptr, GE_MASK_IMG, s.G1, s.TH[7]));          // dZ_8
+    {
+      GemmOut o{GE_MASK_BITS, s.G1};                                                       // dZ_8
+      o.mask_bits = s.THB[7];
+      o.colsum = g->trans_b[7];
+      TRY(gemm_img(c, four(s.G0), L.t_finT, o));
+    }
     float* d_in = (d_pos || d_t) ? s.DIN : nullptr;
     TRY(trunk_backward(c, d, t, s.G1, s.G0, &L.t_in1T, &L.t_in5T, d_in));
     if (d_t && d->in_t > 0) TRY(launch_ray_reduce(d_in, 128, d->in_xyz, d->in_t, pts->S, R, d_t, st));
@@ -1116,9 +1297,10 @@ int nsff_img_pack_weight(const float* src, int32_t ld, int32_t transpose, int32_
 
 int nsff_img_gemm(const nsff_img_gemm_args* a, void* stream) {
   if (!a || !a->a_img || !a->b_blocks || a->a_chunks < 1 || a->a_chunks > kMaxK || a->n_rows < 0) return NSFF_EINVAL;
-  if (a->epi < 0 || a->epi > 3) return NSFF_EINVAL;
+  if (a->epi < 0 || a->epi > 4) return NSFF_EINVAL;
   if (a->epi == GE_F32_ROWS ? !a->out_rows : !a->out_img) return NSFF_EINVAL;
   if (a->epi == GE_MASK_IMG && !a->mask_img) return NSFF_EINVAL;
+  if (a->epi == GE_MASK_BITS && !a->mask_bits) return NSFF_EINVAL;
   TRY(check_arch());
   GemmParams P;
   memset(&P, 0, sizeof(P));
@@ -1132,6 +1314,7 @@ int nsff_img_gemm(const nsff_img_gemm_args* a, void* stream) {
   P.out_img = reinterpret_cast<uint8_t*>(a->out_img); P.out_stride = (uint32_t)(a->N / 64) * kChunkBytes;
   P.mask_img = reinterpret_cast<const uint8_t*>(a->mask_img); P.mask_stride = P.out_stride;
   P.out_f32 = a->out_rows; P.ld = a->ld; P.ncols = a->ncols; P.beta = a->beta; P.n_rows = a->n_rows;
+  P.relu_bits_out = a->relu_bits; P.mask_bits = a->mask_bits; P.colsum = a->colsum;
   return launch_gemm(P, (cudaStream_t)stream);
 }
 

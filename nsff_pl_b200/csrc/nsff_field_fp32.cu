@@ -493,13 +493,6 @@ static int head_bwd(const float* d_out, const float* out, int ld, int col0, int 
   return after_launch();
 }
 
-int launch_embed_rows(const nsff_field_desc* d, const nsff_points* pts, float* X, int ld, cudaStream_t st) {
-  EmbedArgs e{*pts, d->in_xyz, d->in_dir, d->in_a, d->in_t, X, ld};
-  e.p.xyz_out = nullptr;
-  const int cin = d->in_xyz + d->in_dir + d->in_a + d->in_t;
-  embed_points_kernel<<<(unsigned)cdiv64(pts->B * cin, 256), 256, 0, st>>>(e);
-  return after_launch();
-}
 int launch_ray_reduce(const float* dX, int ld, int col0, int n, int S, int64_t R, float* d_code, cudaStream_t st) {
   ray_reduce_kernel<<<(unsigned)cdiv64(R * n, 256), 256, 0, st>>>(dX, ld, col0, n, S, R, d_code);
   return after_launch();

@@ -7,8 +7,6 @@
 #include "nsff_b200.h"
 
 namespace nsff {
-// reference MLP input row [PE(xyz) | PE(dir) | a | t] (rendering.py:164-173) for every point, fp32 (B, ld)
-int launch_embed_rows(const nsff_field_desc* d, const nsff_points* pts, float* X, int ld, cudaStream_t st);
 // d_code[r, k] = sum over the S samples of ray r of dX[(r,s), col0 + k]
 int launch_ray_reduce(const float* dX, int ld, int col0, int n, int S, int64_t R, float* d_code, cudaStream_t st);
 // autograd of the sinusoidal encoding w.r.t. the position (nerf.py:26-28)

@@ -82,13 +82,22 @@ class FieldFn(torch.autograd.Function):
         fp, keep = model.field_params()
         named = list(model.named_parameters())
         fg = _cabi.FieldGrads()
-        grads = []
+        active = []
         for name, p in named:
             stem, idx, kind = _grad_slot(name)
-            if not _branch_active(stem, mask) or (stem == "static_dir" and not model.use_viewdir):
+            ok = _branch_active(stem, mask) and not (stem == "static_dir" and not model.use_viewdir)
+            active.append((stem, idx, kind, p) if ok else None)
+        # one zero-filled flat buffer for every gradient of this call (the kernels accumulate into it); 16-byte slots
+        sizes = [0 if a is None else (a[3].numel() + 3) // 4 * 4 for a in active]
+        flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+        grads, o = [], 0
+        for a, n in zip(active, sizes):
+            if a is None:
                 grads.append(None)
                 continue
-            gbuf = torch.zeros_like(p, dtype=torch.float32)
+            stem, idx, kind, p = a
+            gbuf = flat[o:o + p.numel()].view_as(p)
+            o += n
             grads.append(gbuf)
             field = stem + ("_w" if kind == "weight" else "_b")
             if idx is None:

@@ -7,7 +7,7 @@ import torch
 
 from . import _cabi
 
-EPI_RELU, EPI_LINEAR, EPI_RELU_MASK, EPI_ROWS = 0, 1, 2, 3
+EPI_RELU, EPI_LINEAR, EPI_RELU_MASK, EPI_ROWS, EPI_BIT_MASK = 0, 1, 2, 3, 4
 
 
 def _st(t):
@@ -53,9 +53,14 @@ def pack_weight(w, N=None, transpose=False):
     return blocks
 
 
+def bit_plane(n_rows, device):
+    """Empty ReLU bit plane for an (n_rows, <=256) activation: per tile [8 words][128 rows] uint32."""
+    return torch.zeros(((n_rows + 127) // 128) * 8 * 128, dtype=torch.int32, device=device)
+
+
 def gemm(a_img, a_chunks, blocks, N, n_rows, bias=None, epi=EPI_LINEAR, mask_img=None, out_rows=None, ncols=None,
-         beta=0):
-    """out = epi(A . B^T + bias): returns an image (epi 0..2) or writes fp32 rows into out_rows (epi 3)."""
+         beta=0, relu_bits=None, mask_bits=None, colsum=None):
+    """out = epi(A . B^T + bias): returns an image (epi 0..2, 4) or writes fp32 rows into out_rows (epi 3)."""
     args = _cabi.ImgGemmArgs()
     args.a_img, args.a_chunks, args.b_blocks, args.N = a_img.data_ptr(), a_chunks, blocks.data_ptr(), N
     args.bias = bias.data_ptr() if bias is not None else None
@@ -67,6 +72,9 @@ def gemm(a_img, a_chunks, blocks, N, n_rows, bias=None, epi=EPI_LINEAR, mask_img
         out = torch.empty(_cabi.lib().nsff_img_bytes(n_rows, N // 64), dtype=torch.uint8, device=a_img.device)
         args.out_img = out.data_ptr()
         args.mask_img = mask_img.data_ptr() if mask_img is not None else None
+        args.relu_bits = relu_bits.data_ptr() if relu_bits is not None else None
+        args.mask_bits = mask_bits.data_ptr() if mask_bits is not None else None
+        args.colsum = colsum.data_ptr() if colsum is not None else None
     _cabi.select_device(a_img)
     _cabi.check(_cabi.lib().nsff_img_gemm(args, _st(a_img)), "nsff_img_gemm")
     return out if out is not None else out_rows

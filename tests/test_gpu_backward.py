@@ -14,7 +14,7 @@ Tolerance (relative L2 error per parameter tensor):
 import pytest
 import torch
 
-from parity_util import build_fields, synthetic_rays
+from parity_util import max_abs, build_fields, synthetic_rays
 from oracle import nsff_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -33,7 +33,7 @@ def _loss(results, seed=0):
     return total
 
 
-def _run(precision, R, S, kw, coarse=False, seed=3, energise=True):
+def _run(precision, R, S, kw, coarse=False, seed=3, energise=True, grad_precision=None):
     from nsff_pl_b200.models.rendering import render_rays
     import parity_util
     real = parity_util.energise_
@@ -45,6 +45,7 @@ def _run(precision, R, S, kw, coarse=False, seed=3, energise=True):
         parity_util.energise_ = real
     for m in models.values():
         m.requires_grad_(True)
+        m.grad_precision = grad_precision
     emb["t"].weight.requires_grad_(True)
     rays, ts = synthetic_rays(R, n_frames=8, seed=R)
     res = render_rays(models, emb, rays.cuda(), ts.cuda(), 7, N_samples=S, **kw)
@@ -135,10 +136,16 @@ def test_static_only_field_gradients_fp32():
         assert err <= 1e-2, f"{name}: {err:.3e}"
 
 
-def test_full_nsff_gradients_bf16_forward():
-    models, emb, specs, enc, loss, loss_ref, _, _ = _run("bf16", 16, 64, TRAIN_KW, energise=False)
+@pytest.mark.parametrize("grad_precision,tol", [("fp32", 5e-2), ("bf16", 0.2)])
+def test_full_nsff_gradients_bf16_forward(grad_precision, tol):
+    """Default-initialised weights (where training starts), tcgen05 forward, against the fp32 oracle's autograd.
+    With the fp32 backward the ReLU masks come from an fp32 recompute (<= 5e-2); the tensor-core backward differentiates
+    the bf16 network itself, whose masks differ from the oracle's on units within bf16 noise of zero (<= 0.2, measured
+    0.11 at layer 1 where the gradient norm is 0.06)."""
+    models, emb, specs, enc, loss, loss_ref, _, _ = _run("bf16", 16, 64, TRAIN_KW, energise=False,
+                                                         grad_precision=grad_precision)
     assert abs(loss - loss_ref) <= 2e-2 * max(1.0, abs(loss_ref))
-    _check_grads(models, emb, specs, enc, tol=5e-2, flow_tol=0.2)
+    _check_grads(models, emb, specs, enc, tol=tol, flow_tol=max(0.2, tol))
 
 
 def test_training_step_reduces_the_loss():
@@ -185,32 +192,127 @@ def _grads_with(grad_precision, R, S, kw, transient=True, appearance=False, seed
     return out
 
 
-@pytest.mark.parametrize("R,S", [(24, 48), (7, 33)])
-def test_tensor_core_backward_matches_fp32_backward(R, S):
-    """Same bf16 forward; gradients through nsff_field_backward_tc (bf16 tcgen05 GEMMs over tile images) against
-    nsff_field_backward_fp32 (itself pinned to the oracle's autograd above).  bf16 operands: 2e-2 of each norm."""
-    ref = _grads_with("fp32", R, S, TRAIN_KW)
-    got = _grads_with("bf16", R, S, TRAIN_KW)
+def _close_enough(ref, got, tol=0.3, cos_min=0.95):
+    """The two backwards differentiate slightly different functions: the tensor-core one recomputes the bf16 network
+    the forward kernel evaluated (ReLU masks of the bf16 activations), the fp32 one an fp32 network.  Units whose
+    pre-activation is within bf16 noise of zero flip their mask; a fraction f of flipped units is a sqrt(f) relative
+    change of the gradient, growing with depth (measured: 0.5 % at the heads, 13 % at layer 1 of the energised test
+    network).  The tight check of the kernels is test_tensor_core_backward_matches_bf16_network_autograd below."""
     assert set(ref) == set(got)
     for k in ref:
         err = float((got[k] - ref[k]).norm() / (ref[k].norm() + 1e-30))
-        assert err <= 2e-2, f"{k}: relative error {err:.3e} (|ref| {float(ref[k].norm()):.3e})"
+        cos = float((got[k] * ref[k]).sum() / (got[k].norm() * ref[k].norm() + 1e-30))
+        assert err <= tol and cos >= cos_min, f"{k}: relative error {err:.3e}, cosine {cos:.4f}"
+
+
+@pytest.mark.parametrize("R,S", [(24, 48), (13, 50)])
+def test_tensor_core_backward_matches_fp32_backward(R, S):
+    """Same bf16 forward; gradients through nsff_field_backward_tc (bf16 tcgen05 GEMMs over tile images) against
+    nsff_field_backward_fp32 (itself pinned to the oracle's autograd above)."""
+    ref = _grads_with("fp32", R, S, TRAIN_KW)
+    got = _grads_with("bf16", R, S, TRAIN_KW)
+    assert set(ref) == set(got)
+    _close_enough(ref, got)
 
 
 def test_tensor_core_backward_static_only_model():
     kw = dict(perturb=0, noise_std=0, N_importance=0, test_time=False)
     ref = _grads_with("fp32", 10, 40, kw, transient=False, seed=9)
     got = _grads_with("bf16", 10, 40, kw, transient=False, seed=9)
-    assert set(ref) == set(got)
-    for k in ref:
-        err = float((got[k] - ref[k]).norm() / (ref[k].norm() + 1e-30))
-        assert err <= 2e-2, f"{k}: relative error {err:.3e}"
+    _close_enough(ref, got)
 
 
 def test_tensor_core_backward_appearance_code():
     ref = _grads_with("fp32", 9, 40, TRAIN_KW, appearance=True, seed=5)
     got = _grads_with("bf16", 9, 40, TRAIN_KW, appearance=True, seed=5)
-    assert set(ref) == set(got) and "embedding_a" in ref
+    assert "embedding_a" in ref
+    _close_enough(ref, got)
+
+
+def _ste_bf16(x):
+    return x + (x.to(torch.bfloat16).float() - x).detach()
+
+
+def _pe(x, n_freqs):
+    out = [x]
+    for f in range(n_freqs):
+        out += [torch.sin(2.0 ** f * x), torch.cos(2.0 ** f * x)]
+    return torch.cat(out, -1)
+
+
+@pytest.mark.parametrize("mask_name,R,S", [("main", 11, 37), ("warp_fw", 16, 24)])
+def test_tensor_core_backward_matches_bf16_network_autograd(mask_name, R, S):
+    """Tight check of nsff_field_backward_tc: torch autograd (fp32 arithmetic on the GPU) of the SAME bf16 network the
+    kernels evaluate - weights, inputs and hidden activations rounded to bf16 with a straight-through gradient - so the
+    ReLU masks are identical and only the bf16 rounding of the gradient planes remains: ~0.3 % per layer, accumulating
+    to 1.8e-2 at layer 1 of the 9-deep chain (bound: 3e-2 of each norm; a layout or indexing bug gives O(1))."""
+    from nsff_pl_b200 import _cabi
+    from nsff_pl_b200.models.autograd import FieldFn
+    models, emb, _, _ = build_fields(W=256, seed=21, precision="bf16", n_frames=8)
+    f = models["fine"].requires_grad_(True)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B = R * S
+    # positions carry gradient only in the warped passes (dynamic branch alone); the main pass samples are constants
+    pos = (torch.rand(B, 3, device="cuda", generator=g) * 2 - 1).requires_grad_(mask_name != "main")
+    t_code = torch.randn(R, 48, device="cuda", generator=g).requires_grad_(True)
+    dirs = torch.nn.functional.normalize(torch.randn(R, 3, device="cuda", generator=g), dim=-1)
+    zs = torch.rand(B, device="cuda", generator=g)
+    if mask_name == "main":
+        mask = _cabi.OUT_STATIC | _cabi.OUT_TRANSIENT | _cabi.OUT_FLOW_FW | _cabi.OUT_FLOW_BW
+    else:
+        mask = _cabi.OUT_TRANSIENT | _cabi.OUT_FLOW_FW
+    names = [n for n, _ in f.named_parameters()]
+    params = [p for _, p in f.named_parameters()]
+    raw = FieldFn.apply(f, mask, S, pos, t_code, None, dirs, zs, *params)
+    # positive loss weights: with random signs a column sum (bias gradient) can cancel to ~0 by chance and turn the
+    # 0.2 % bf16 rounding of the summands into a several-% error of the sum (seen: sigma head, 4 %)
+    w = torch.rand(raw.shape, device="cuda", generator=g) + 0.5
+    (raw * w).sum().backward()
+    got = {n: p.grad.clone() for n, p in zip(names, params) if p.grad is not None}
+    got["t_code"] = t_code.grad.clone()
+    if pos.requires_grad:
+        got["pos"] = pos.grad.clone()
+    for p in params + [pos, t_code]:
+        p.grad = None
+
+    P = dict(f.named_parameters())
+
+    def lin(name, x):
+        return x @ _ste_bf16(P[name + ".weight"]).T + P[name + ".bias"]
+
+    def trunk(prefix, x_in):
+        h = x_in
+        for i in range(8):
+            if i == 4:
+                h = torch.cat([x_in, h], 1)
+            h = _ste_bf16(torch.relu(lin(f"{prefix}_xyz_encoding_{i + 1}.0", h)))
+        return h
+
+    pe = _ste_bf16(_pe(pos, 10))
+    de = _ste_bf16(_pe(dirs, 4)).repeat_interleave(S, 0)
+    tt = _ste_bf16(t_code).repeat_interleave(S, 0)
+    near = (zs <= 0.95).float()[:, None]
+    pieces = []
+    if mask & _cabi.OUT_STATIC:
+        h = trunk("static", pe)
+        feat = _ste_bf16(lin("static_xyz_encoding_final", h))
+        feat = _ste_bf16(torch.relu(lin("static_dir_encoding.0", torch.cat([feat, de], 1))))
+        pieces += [torch.sigmoid(lin("static_rgb.0", feat)), lin("static_sigma", h)]
+    ht = trunk("transient", torch.cat([pe, tt], 1))
+    ft = _ste_bf16(lin("transient_xyz_encoding_final", ht))
+    pieces += [torch.sigmoid(lin("transient_rgb.0", ft)), lin("transient_sigma", ft)]
+    if mask & _cabi.OUT_FLOW_FW:
+        pieces.append(0.2 * torch.tanh(lin("transient_flow_fw.0", ft)) * near)
+    if mask & _cabi.OUT_FLOW_BW:
+        pieces.append(0.2 * torch.tanh(lin("transient_flow_bw.0", ft)) * near)
+    want_raw = torch.cat(pieces, 1)
+    assert max_abs(raw, want_raw.detach()) <= 1e-2 * max(1.0, float(want_raw.detach().abs().max()))
+    (want_raw * w).sum().backward()
+    ref = {n: p.grad for n, p in zip(names, params) if p.grad is not None}
+    ref["t_code"] = t_code.grad
+    if pos.requires_grad:
+        ref["pos"] = pos.grad
+    assert set(ref) == set(got)
     for k in ref:
-        err = float((got[k] - ref[k]).norm() / (ref[k].norm() + 1e-30))
-        assert err <= 2e-2, f"{k}: relative error {err:.3e}"
+        err = float((got[k] - ref[k]).double().norm() / (ref[k].double().norm() + 1e-30))
+        assert err <= 3e-2, f"{k}: relative error {err:.3e} (|ref| {float(ref[k].norm()):.3e})"

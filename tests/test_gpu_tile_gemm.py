@@ -48,11 +48,30 @@ def test_gemm_kmajor_all_epilogues(n_rows, K, N):
     mk = TI.rows_from_image(TI.gemm(a_img, chunks, blocks, N, n_rows, epi=TI.EPI_RELU_MASK,
                                     mask_img=TI.image_from_rows(m)), n_rows, N)
     assert _rel(mk, (ref - b) * (_bf(m) > 0)) < 1e-2
+    # bit-plane route: the relu pass records (out > 0); a masked pass through those bits equals the image-masked one,
+    # and its fused column sums equal the sums of the (pre-rounding) masked result
+    bits = TI.bit_plane(n_rows, "cuda")
+    TI.gemm(a_img, chunks, blocks, N, n_rows, bias=b, epi=TI.EPI_RELU, relu_bits=bits)
+    n_tiles = (n_rows + 127) // 128
+    words = bits.view(n_tiles, 8, 128).permute(0, 2, 1).reshape(n_tiles * 128, 8)[:n_rows]       # (row, word)
+    on = ((words[:, :, None] >> torch.arange(32, device="cuda")) & 1).reshape(n_rows, 256)[:, :N].bool()
+    # the recorded bits are the sign of the kernel's own fp32 sums: equal to (ref > 0) except within rounding of zero
+    assert bool((on == (ref > 0))[ref.abs() > 1e-3].all())
+    cs = torch.zeros(N, device="cuda")
+    mk2 = TI.rows_from_image(TI.gemm(a_img, chunks, blocks, N, n_rows, epi=TI.EPI_BIT_MASK, mask_bits=bits, colsum=cs),
+                             n_rows, N)
+    want2 = (ref - b) * on
+    assert _rel(mk2, want2) < 1e-2
+    assert float((cs - want2.sum(0)).abs().max()) <= 2e-3 * float(want2.abs().sum(0).max()), (cs, want2.sum(0))
     rows = torch.full((n_rows, N + 5), 7.0, device="cuda")
     TI.gemm(a_img, chunks, blocks, N, n_rows, epi=TI.EPI_ROWS, out_rows=rows, ncols=N - 3, beta=0)
     assert _rel(rows[:, :N - 3], (ref - b)[:, :N - 3]) < 1e-2 and bool((rows[:, N - 3:] == 7.0).all())
     TI.gemm(a_img, chunks, blocks, N, n_rows, epi=TI.EPI_ROWS, out_rows=rows, ncols=N - 3, beta=1)
     assert _rel(rows[:, :N - 3], 2 * (ref - b)[:, :N - 3]) < 1.5e-2
+    rows4 = torch.zeros(n_rows, N, device="cuda")                       # 16-byte aligned rows: vectorised stores
+    TI.gemm(a_img, chunks, blocks, N, n_rows, epi=TI.EPI_ROWS, out_rows=rows4, ncols=N - 17, beta=0)
+    TI.gemm(a_img, chunks, blocks, N, n_rows, epi=TI.EPI_ROWS, out_rows=rows4, ncols=N - 17, beta=1)
+    assert _rel(rows4[:, :N - 17], 2 * (ref - b)[:, :N - 17]) < 1.5e-2 and bool((rows4[:, N - 17:] == 0).all())
 
 
 def test_gemm_transposed_weight_is_dgrad():
