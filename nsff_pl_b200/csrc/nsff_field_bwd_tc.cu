@@ -277,13 +277,15 @@ struct GemmParams {
   int32_t l2_hint;                // 1: operand tiles are loaded with an L2 evict-first policy
 };
 
-constexpr int kGemmEpiWarps = 8;
+constexpr int kGemmEpiWarps = 16;    // 4 TMEM lane quadrants x 4 column parts: 4 warps per SMSP hide the TMEM-load and
+                                     // dependent-arithmetic latency of the epilogue (8 warps: 6 cycles per instruction)
 constexpr int kGemmThreads = (kGemmEpiWarps + 2) * 32;
 constexpr int kGemmMaxStages = 8;
 enum { GB_B_FULL = 0, GB_A_FULL = 1, GB_A_EMPTY = GB_A_FULL + kGemmMaxStages, GB_ACC_FULL = GB_A_EMPTY + kGemmMaxStages,
        GB_ACC_EMPTY = GB_ACC_FULL + 2, GB_COUNT = GB_ACC_EMPTY + 2 };
 constexpr uint32_t kGemmAux = 1024 /*bias*/ + 256 /*barriers + tmem ptr*/;
 
+template <int kEpi>
 __global__ void __launch_bounds__(kGemmThreads, 1) img_gemm_kernel(const __grid_constant__ GemmParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -366,23 +368,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) img_gemm_kernel(const __grid_
       }
     }
   } else {
-    // ===== epilogue: warp (q, half) drains rows 32q.. of columns [half*N/2, (half+1)*N/2) =====
-    const int q = warp & 3, half = warp >> 2;
+    // ===== epilogue: warp (q, part) drains rows 32q.. of a quarter of the columns (32 at least) =====
+    const int q = warp & 3, part = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t roff = row_off(row);
     const int rsw = row & 7;
-    const int c_begin = half * (P.N / 2);
-    const int n_batches = P.N / 64;                         // 32-column batches of this warp: 1, 2 or 4
+    const int cols_per_part = P.N >= 128 ? P.N / 4 : 32;
+    const int n_batches = part * cols_per_part < P.N ? cols_per_part / 32 : 0;       // 32-column batches: 0, 1 or 2
+    const int c_begin = part * cols_per_part;
     const int word0 = (P.col0 + c_begin) >> 5;
-    float colacc[4] = {0.f, 0.f, 0.f, 0.f};
+    float colacc[2] = {0.f, 0.f};
     uint32_t local = 0;
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++local) {
       const uint32_t slot = local & 1u, use = local >> 1;
       // the ReLU bits of this row are fetched before the accumulator is awaited: off the critical path
-      uint32_t mbits[4] = {~0u, ~0u, ~0u, ~0u};
-      if (P.epi == GE_MASK_BITS) {
+      uint32_t mbits[2] = {~0u, ~0u};
+      if constexpr (kEpi == GE_MASK_BITS) {
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
+        for (int b = 0; b < 2; ++b)
           if (b < n_batches) mbits[b] = P.mask_bits[(size_t)tile * kBitsPerTile + (size_t)(word0 + b) * 128 + row];
       }
       mbar_wait(bar(GB_ACC_FULL + slot), use & 1u);
@@ -390,13 +393,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) img_gemm_kernel(const __grid_
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 256u;
       const int64_t p = (int64_t)tile * 128 + row;
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
+      for (int b = 0; b < 2; ++b) {
         if (b >= n_batches) break;
         const int cb = c_begin + 32 * b;
         uint32_t v[32];
         tmem_ld32(t_acc + (uint32_t)cb, v);
         tmem_ld_wait();
-        if (P.epi == GE_F32_ROWS) {
+        if constexpr (kEpi == GE_F32_ROWS) {
           if (p < P.n_rows) {
             float* o = P.out_f32 + p * P.ld + cb;
             const bool vec = ((P.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.out_f32) & 15) == 0);
@@ -426,7 +429,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) img_gemm_kernel(const __grid_
           const size_t off = (size_t)tile * P.out_stride + (size_t)(gc >> 6) * kChunkBytes + roff;
           const int unit0 = (gc & 63) >> 3;
           uint32_t mb = mbits[b];
-          if (P.epi == GE_MASK_IMG) {
+          if constexpr (kEpi == GE_MASK_IMG) {
             // ReLU mask given as an activation image: max(x,0) in bf16, so "> 0" == "any magnitude bit set"
             mb = 0;
 #pragma unroll
@@ -443,14 +446,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) img_gemm_kernel(const __grid_
             }
           }
           float f[32];
-          uint32_t pos_bits = 0;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float x = __uint_as_float(v[i]) + bias_s[cb + i];
-            if (P.epi == GE_RELU_IMG) x = fmaxf(x, 0.f);
-            if (P.epi == GE_MASK_IMG || P.epi == GE_MASK_BITS) x = ((mb >> i) & 1u) ? x : 0.f;
-            pos_bits |= (x > 0.f ? 1u : 0u) << i;
-            f[i] = x;
+          for (int i = 0; i < 32; i += 4) {
+            const float4 bb = *reinterpret_cast<const float4*>(bias_s + cb + i);
+            f[i] = __uint_as_float(v[i]) + bb.x;
+            f[i + 1] = __uint_as_float(v[i + 1]) + bb.y;
+            f[i + 2] = __uint_as_float(v[i + 2]) + bb.z;
+            f[i + 3] = __uint_as_float(v[i + 3]) + bb.w;
+          }
+          if constexpr (kEpi == GE_RELU_IMG) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          if constexpr (kEpi == GE_MASK_IMG || kEpi == GE_MASK_BITS) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = ((mb >> i) & 1u) ? f[i] : 0.f;
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -459,7 +469,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) img_gemm_kernel(const __grid_
                 make_uint4(pack_bf16x2(f[u * 8], f[u * 8 + 1]), pack_bf16x2(f[u * 8 + 2], f[u * 8 + 3]),
                            pack_bf16x2(f[u * 8 + 4], f[u * 8 + 5]), pack_bf16x2(f[u * 8 + 6], f[u * 8 + 7]));
           }
-          if (P.relu_bits_out) P.relu_bits_out[(size_t)tile * kBitsPerTile + (size_t)(gc >> 5) * 128 + row] = pos_bits;
+          if (P.relu_bits_out) {
+            uint32_t pos_bits = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) pos_bits |= (f[i] > 0.f ? 1u : 0u) << i;
+            P.relu_bits_out[(size_t)tile * kBitsPerTile + (size_t)(gc >> 5) * 128 + row] = pos_bits;
+          }
           if (P.colsum) {
             // transpose-reduce over the warp's 32 rows: after the butterfly lane L holds the sum of column cb + L
 #pragma unroll
@@ -480,10 +495,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) img_gemm_kernel(const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(GB_ACC_EMPTY + slot));
     }
-    if (P.colsum && P.epi != GE_F32_ROWS) {
+    if constexpr (kEpi != GE_F32_ROWS) {
+      if (P.colsum) {
 #pragma unroll
-      for (int b = 0; b < 4; ++b)
-        if (b < n_batches) atomicAdd(P.colsum + c_begin + 32 * b + lane, colacc[b]);
+        for (int b = 0; b < 2; ++b)
+          if (b < n_batches) atomicAdd(P.colsum + c_begin + 32 * b + lane, colacc[b]);
+      }
     }
   }
 
@@ -607,7 +624,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) img_wgrad_kernel(const __grid_c
       tc_fence_after_sync();
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)mh * 256u;
       float* dst = P.acc_t + mh * 128 + q * 32 + lane;
-      for (uint32_t cb = 0; cb < N; cb += 32) {
+      // every CTA adds into the same 64*nb x 256 words: start each CTA at a different column so that the L2 atomic
+      // units see different addresses at any one time
+      const uint32_t rot = ((uint32_t)blockIdx.x * 32u) % N;
+      for (uint32_t c0 = 0; c0 < N; c0 += 32) {
+        const uint32_t cb = (c0 + rot) % N;
         uint32_t v[32];
         tmem_ld32(t_acc + cb, v);
         tmem_ld_wait();
@@ -655,6 +676,13 @@ static int l2_hint_enabled() {
   return v;
 }
 
+template <int kEpi>
+static int launch_gemm_t(const GemmParams& P, int grid, uint32_t smem, cudaStream_t st) {
+  NSFF_CUDA_TRY(cudaFuncSetAttribute(img_gemm_kernel<kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+  img_gemm_kernel<kEpi><<<grid, kGemmThreads, smem, st>>>(P);
+  return after_launch();
+}
+
 static int launch_gemm(GemmParams& P, cudaStream_t st) {
   if (P.n_tiles <= 0) return NSFF_OK;
   if (P.n_chunks < 1 || P.n_chunks > kMaxK || (P.N != 256 && P.N != 128 && P.N != 64)) return NSFF_EINVAL;
@@ -665,25 +693,22 @@ static int launch_gemm(GemmParams& P, cudaStream_t st) {
   P.stages = stages;
   P.l2_hint = l2_hint_enabled();
   const uint32_t smem = fixed + (uint32_t)stages * kChunkBytes;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NSFF_CUDA_TRY(cudaFuncSetAttribute(img_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-    attr_set = true;
-  }
   int grid = sm_count();
   if (grid > P.n_tiles) grid = P.n_tiles;
-  img_gemm_kernel<<<grid, kGemmThreads, smem, st>>>(P);
-  return after_launch();
+  switch (P.epi) {
+    case GE_RELU_IMG: return launch_gemm_t<GE_RELU_IMG>(P, grid, smem, st);
+    case GE_LIN_IMG: return launch_gemm_t<GE_LIN_IMG>(P, grid, smem, st);
+    case GE_MASK_IMG: return launch_gemm_t<GE_MASK_IMG>(P, grid, smem, st);
+    case GE_F32_ROWS: return launch_gemm_t<GE_F32_ROWS>(P, grid, smem, st);
+    case GE_MASK_BITS: return launch_gemm_t<GE_MASK_BITS>(P, grid, smem, st);
+  }
+  return NSFF_EINVAL;
 }
 
 static int launch_wgrad(WgradParams& P, cudaStream_t st) {
   if (P.n_tiles <= 0) return NSFF_OK;
   if (P.nb < 1 || P.nb > 4) return NSFF_EINVAL;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NSFF_CUDA_TRY(cudaFuncSetAttribute(img_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem));
-    attr_set = true;
-  }
+  NSFF_CUDA_TRY(cudaFuncSetAttribute(img_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem));
   P.l2_hint = l2_hint_enabled();
   int grid = sm_count();
   if (grid > P.n_tiles) grid = P.n_tiles;
