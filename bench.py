@@ -173,6 +173,7 @@ def run_train(args, rank, local_rank, world):
     for m in models.values():
         m.requires_grad_(True)
         m.grad_precision = args.grad_precision
+        m.recompute_in_backward = args.bwd_recompute
     emb["t"].weight.requires_grad_(True)
     params = [p for m in models.values() for p in m.parameters()] + [emb["t"].weight]
     opt = torch.optim.Adam(params, lr=5e-4)
@@ -223,14 +224,17 @@ def run_train(args, rank, local_rank, world):
     torch.cuda.synchronize()
     n0 = _cabi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         loss = step()
+        marks[i].record()
     e1.record()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    per_step = sorted(([e0] + marks)[i].elapsed_time(marks[i]) for i in range(args.steps))
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -250,9 +254,12 @@ def run_train(args, rank, local_rank, world):
                           "dtype": "bf16" if tc else "bf16 fwd / f32 bwd", "data": "synthetic",
                           "config": {"workload": "training step, 1024 rays x 128 samples per GPU, full NSFF + warp, surrogate "
                                                  "photometric/cycle/flow loss, Adam (BASELINE.json configs[2])",
-                                     "backward": ("bf16 tcgen05 GEMMs over tile images (recompute + dgrad + wgrad per layer)"
+                                     "backward": (("bf16 tcgen05 GEMMs over tile images (dgrad + wgrad per layer; activations "
+                                                   + ("recomputed" if args.bwd_recompute else "saved by the forward kernel") + ")")
                                                   if tc else "fp32 CUDA-core kernels (verification path)")},
                           "phase_ms": split,
+                          "step_ms": {"min": round(per_step[0], 3), "median": round(per_step[len(per_step) // 2], 3),
+                                      "max": round(per_step[-1], 3)},
                           "algorithmic_tflop_per_step": round(R * S * 14.28e6 / 1e12, 3),
                           "gpu_launches": int(_cabi.launch_count() - n0), "final_loss": float(loss)}), flush=True)
     if world > 1:
@@ -279,6 +286,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--grad-precision", default="bf16", choices=["bf16", "fp32"],
                     help="train workload: tensor-core backward (default) or the fp32 verification backward")
+    ap.add_argument("--bwd-recompute", action="store_true",
+                    help="train workload: re-evaluate the layers in the backward instead of saving them in the forward")
     ap.add_argument("--workload", default="render", choices=["render", "train"],
                     help="render = BASELINE.json metric (default, what the driver runs); train = configs[2] step")
     args = ap.parse_args()

@@ -200,11 +200,21 @@ NSFF_API int nsff_field_backward_fp32(const nsff_field_desc* desc /*host*/, cons
 NSFF_API size_t nsff_field_bwd_tc_pack_bytes(const nsff_field_desc* desc /*host*/);
 NSFF_API int nsff_field_bwd_tc_pack(const nsff_field_desc* desc /*host*/, const nsff_field_params* params /*host*/,
                                     void* pack, void* stream);
-NSFF_API size_t nsff_field_bwd_tc_scratch_bytes(const nsff_field_desc* desc /*host*/, int64_t B);
+/*     `saved` (optional) = the buffer nsff_field_forward_save filled for the same (desc, B, out_mask): the hidden
+ *     activations of every layer as tile images + ReLU bit planes, written by the forward kernel itself (its shared
+ *     memory hidden chunks are those images).  With it nothing is recomputed; without it (NULL) the layers are
+ *     re-evaluated by the GEMM kernel first.
+ */
+NSFF_API size_t nsff_field_save_bytes(const nsff_field_desc* desc /*host*/, int64_t B, int out_mask);
+NSFF_API int nsff_field_forward_save(const nsff_field_desc* desc /*host*/, const void* pack,
+                                     const nsff_points* pts /*host*/, int out_mask, float* out, int32_t out_ld,
+                                     void* save /*device, 16 B aligned*/, void* stream);
+NSFF_API size_t nsff_field_bwd_tc_scratch_bytes(const nsff_field_desc* desc /*host*/, int64_t B, int with_saved);
 NSFF_API int nsff_field_backward_tc(const nsff_field_desc* desc /*host*/, const nsff_field_params* params /*host*/,
                                     const void* pack, const nsff_points* pts /*host*/, int out_mask, const float* out,
                                     const float* d_out, int32_t out_ld, const nsff_field_grads* grads /*host*/,
-                                    float* d_pos, float* d_t, float* d_a, void* scratch, void* stream);
+                                    float* d_pos, float* d_t, float* d_a, const void* saved, void* scratch,
+                                    void* stream);
 
 /* The two GEMM kernels of that backward, exposed for hosts that keep their own tile images (and for the unit tests).
  * Image = [ceil(n_rows/128) tiles][chunks][128 rows x 64 bf16, 128B swizzle]; weight block = [N rows x 64 bf16], same

@@ -131,10 +131,13 @@ PROTOTYPES = {
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsff_field_bwd_tc_pack_bytes": (C.c_size_t, [C.POINTER(FieldDesc)]),
     "nsff_field_bwd_tc_pack": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(FieldParams), C.c_void_p, C.c_void_p]),
-    "nsff_field_bwd_tc_scratch_bytes": (C.c_size_t, [C.POINTER(FieldDesc), C.c_int64]),
+    "nsff_field_save_bytes": (C.c_size_t, [C.POINTER(FieldDesc), C.c_int64, C.c_int]),
+    "nsff_field_forward_save": (C.c_int, [C.POINTER(FieldDesc), C.c_void_p, C.POINTER(Points), C.c_int, C.c_void_p,
+                                          C.c_int32, C.c_void_p, C.c_void_p]),
+    "nsff_field_bwd_tc_scratch_bytes": (C.c_size_t, [C.POINTER(FieldDesc), C.c_int64, C.c_int]),
     "nsff_field_backward_tc": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(FieldParams), C.c_void_p, C.POINTER(Points),
                                          C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(FieldGrads), C.c_void_p,
-                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsff_img_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
     "nsff_img_from_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int32,
                                      C.c_int32, C.c_void_p]),

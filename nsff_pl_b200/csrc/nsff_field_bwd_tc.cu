@@ -21,6 +21,7 @@
 
 #include "nsff_common.cuh"
 #include "nsff_field_host.cuh"
+#include "nsff_field_save.cuh"
 #include "nsff_sm100.cuh"
 
 #define TRY(expr)                   \
@@ -462,12 +463,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) img_gemm_kernel(const __grid_
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = ((mb >> i) & 1u) ? f[i] : 0.f;
           }
+          // two aligned 32-byte sectors per row: the swizzle only swaps the 16-byte units inside each pair
+          const bool swap = rsw & 1;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const uint32_t uo = (uint32_t)(((unit0 + u) ^ rsw) & 7) << 4;
-            *reinterpret_cast<uint4*>(P.out_img + off + uo) =
-                make_uint4(pack_bf16x2(f[u * 8], f[u * 8 + 1]), pack_bf16x2(f[u * 8 + 2], f[u * 8 + 3]),
-                           pack_bf16x2(f[u * 8 + 4], f[u * 8 + 5]), pack_bf16x2(f[u * 8 + 6], f[u * 8 + 7]));
+          for (int j = 0; j < 2; ++j) {
+            const int u = 2 * j;
+            const uint4 a = make_uint4(pack_bf16x2(f[u * 8], f[u * 8 + 1]), pack_bf16x2(f[u * 8 + 2], f[u * 8 + 3]),
+                                       pack_bf16x2(f[u * 8 + 4], f[u * 8 + 5]), pack_bf16x2(f[u * 8 + 6], f[u * 8 + 7]));
+            const uint4 b2 = make_uint4(pack_bf16x2(f[u * 8 + 8], f[u * 8 + 9]), pack_bf16x2(f[u * 8 + 10], f[u * 8 + 11]),
+                                        pack_bf16x2(f[u * 8 + 12], f[u * 8 + 13]), pack_bf16x2(f[u * 8 + 14], f[u * 8 + 15]));
+            st_global_v8(P.out_img + off + ((uint32_t)(((unit0 + u) ^ rsw) & 6) << 4), swap ? b2 : a, swap ? a : b2);
           }
           if (P.relu_bits_out) {
             uint32_t pos_bits = 0;
@@ -863,7 +868,8 @@ struct Scratch {
   size_t acc_bytes, total;
 };
 constexpr size_t kAccSlots = 96;          // 64-row x 256 fp32 wgrad result slots per call
-static Scratch carve(const nsff_field_desc* d, int64_t B, uint8_t* base) {
+// with_acts = false: the activation images come from the forward's save buffer (nsff_field_forward_save)
+static Scratch carve(const nsff_field_desc* d, int64_t B, uint8_t* base, bool with_acts) {
   Scratch s;
   const size_t nt = (size_t)cdiv64(B, 128);
   const size_t one = nt * kChunkBytes, four = 4 * one;
@@ -875,13 +881,15 @@ static Scratch carve(const nsff_field_desc* d, int64_t B, uint8_t* base) {
   };
   const size_t bits = nt * kBitsPerTile * sizeof(uint32_t);
   s.PE = take(one); s.T = take(one); s.DIR = take(one); s.A = take(one);
-  for (int i = 0; i < 8; ++i) s.SH[i] = take(four), s.SHB[i] = reinterpret_cast<uint32_t*>(take(bits));
-  s.SFEAT = take(four); s.SDIRO = take(four); s.SDIROB = reinterpret_cast<uint32_t*>(take(bits));
+  const size_t a4 = with_acts ? four : 0, ab = with_acts ? bits : 0, t4 = d->has_transient ? a4 : 0,
+               tb = d->has_transient ? ab : 0;
+  for (int i = 0; i < 8; ++i) s.SH[i] = take(a4), s.SHB[i] = reinterpret_cast<uint32_t*>(take(ab));
+  s.SFEAT = take(a4); s.SDIRO = take(a4); s.SDIROB = reinterpret_cast<uint32_t*>(take(ab));
   for (int i = 0; i < 8; ++i) {
-    s.TH[i] = take(d->has_transient ? four : 0);
-    s.THB[i] = reinterpret_cast<uint32_t*>(take(d->has_transient ? bits : 0));
+    s.TH[i] = take(t4);
+    s.THB[i] = reinterpret_cast<uint32_t*>(take(tb));
   }
-  s.TFEAT = take(d->has_transient ? four : 0);
+  s.TFEAT = take(t4);
   s.G0 = take(four); s.G1 = take(four); s.DP = take(one);
   s.DIN = reinterpret_cast<float*>(take((size_t)B * 128 * sizeof(float)));
   s.acc_bytes = kAccSlots * 64 * 256 * sizeof(float);
@@ -1073,15 +1081,15 @@ int nsff_field_bwd_tc_pack(const nsff_field_desc* d, const nsff_field_params* p,
   return flush_pack_jobs(pb, st);
 }
 
-size_t nsff_field_bwd_tc_scratch_bytes(const nsff_field_desc* d, int64_t B) {
+size_t nsff_field_bwd_tc_scratch_bytes(const nsff_field_desc* d, int64_t B, int with_saved) {
   if (!d || B < 0 || supported(d) != NSFF_OK) return 0;
-  return carve(d, B, nullptr).total;
+  return carve(d, B, nullptr, !with_saved).total;
 }
 
 int nsff_field_backward_tc(const nsff_field_desc* d, const nsff_field_params* p, const void* pack,
                            const nsff_points* pts, int out_mask,
                            const float* out, const float* d_out, int32_t out_ld, const nsff_field_grads* g,
-                           float* d_pos, float* d_t, float* d_a, void* scratch, void* stream) {
+                           float* d_pos, float* d_t, float* d_a, const void* saved, void* scratch, void* stream) {
   if (!d || !p || !pack || !pts || !out || !d_out || !g || !scratch) return NSFF_EINVAL;
   TRY(supported(d));
   if (out_mask & NSFF_OUT_SIGMA_ONLY) return NSFF_EUNSUPPORTED;
@@ -1102,7 +1110,21 @@ int nsff_field_backward_tc(const nsff_field_desc* d, const nsff_field_params* p,
     PackBuilder pb;
     build_pack(d, nullptr, L, pb);
   }
-  Scratch s = carve(d, B, reinterpret_cast<uint8_t*>(scratch));
+  Scratch s = carve(d, B, reinterpret_cast<uint8_t*>(scratch), saved == nullptr);
+  if (saved) {
+    // activations written by nsff_field_forward_save for the same (desc, B, out_mask): nothing is recomputed
+    if ((uintptr_t)saved & 15u) return NSFF_EINVAL;
+    const SaveLayout SL = save_layout(d, B, out_mask);
+    uint8_t* sv = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(saved));
+    auto at = [&](uint64_t off) { return off == kNoSave ? nullptr : sv + off; };
+    for (int i = 0; i < 8; ++i) {
+      s.SH[i] = at(SL.s_h[i]); s.SHB[i] = reinterpret_cast<uint32_t*>(at(SL.s_hb[i]));
+      s.TH[i] = at(SL.t_h[i]); s.THB[i] = reinterpret_cast<uint32_t*>(at(SL.t_hb[i]));
+    }
+    s.SFEAT = at(SL.s_feat); s.SDIRO = at(SL.s_dir); s.SDIROB = reinterpret_cast<uint32_t*>(at(SL.s_dirb));
+    s.TFEAT = at(SL.t_feat);
+  }
+  const bool recompute = saved == nullptr;
   Ctx c{st, (int)cdiv64(B, 128), B, reinterpret_cast<const uint8_t*>(pack), s.ACC, 0, s.acc_bytes / sizeof(float)};
   NSFF_CUDA_TRY(cudaMemsetAsync(s.ACC, 0, s.acc_bytes, st));
   if (d_pos) NSFF_CUDA_TRY(cudaMemsetAsync(d_pos, 0, (size_t)B * 3 * sizeof(float), st));
@@ -1136,22 +1158,24 @@ int nsff_field_backward_tc(const nsff_field_desc* d, const nsff_field_params* p,
 
   if (want_s) {
     Trunk t{false, L.s_fwd, L.s_hidT, p->static_b, g->static_w, g->static_b, s.SH, s.SHB, {pe}, d->in_xyz};
-    // ---- recompute, keeping every layer ----
-    TRY(trunk_forward(c, d, t));
-    {
+    // ---- recompute, keeping every layer (unless the forward saved them) ----
+    if (recompute) {
+      TRY(trunk_forward(c, d, t));
       GemmOut o{GE_LIN_IMG, s.SFEAT};
       o.bias = p->static_final_b;
       TRY(gemm_img(c, four(s.SH[7]), L.s_fin, o));
     }
     const uint8_t* rgb_in = s.SFEAT;
     if (d->use_viewdir) {
-      std::vector<Src> a = four(s.SFEAT);
-      a.push_back(dirc);
-      if (d->in_a > 0) a.push_back(ac);
-      GemmOut o{GE_RELU_IMG, s.SDIRO};
-      o.bias = p->static_dir_b;
-      o.relu_bits = s.SDIROB;
-      TRY(gemm_img(c, a, L.s_dir, o));
+      if (recompute) {
+        std::vector<Src> a = four(s.SFEAT);
+        a.push_back(dirc);
+        if (d->in_a > 0) a.push_back(ac);
+        GemmOut o{GE_RELU_IMG, s.SDIRO};
+        o.bias = p->static_dir_b;
+        o.relu_bits = s.SDIROB;
+        TRY(gemm_img(c, a, L.s_dir, o));
+      }
       rgb_in = s.SDIRO;
     }
     // ---- heads: image columns 0..2 = rgb (sigmoid), 3 = sigma ----
@@ -1222,8 +1246,8 @@ int nsff_field_backward_tc(const nsff_field_desc* d, const nsff_field_params* p,
   }
   if (want_t) {
     Trunk t{true, L.t_fwd, L.t_hidT, p->trans_b, g->trans_w, g->trans_b, s.TH, s.THB, {pe, tc}, d->in_xyz + d->in_t};
-    TRY(trunk_forward(c, d, t));
-    {
+    if (recompute) {
+      TRY(trunk_forward(c, d, t));
       GemmOut o{GE_LIN_IMG, s.TFEAT};
       o.bias = p->trans_final_b;
       TRY(gemm_img(c, four(s.TH[7]), L.t_fin, o));

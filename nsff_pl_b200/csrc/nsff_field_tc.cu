@@ -28,6 +28,7 @@
 #include <initializer_list>
 
 #include "nsff_common.cuh"
+#include "nsff_field_save.cuh"
 #include "nsff_sm100.cuh"
 
 namespace nsff {
@@ -193,6 +194,8 @@ struct Step {
   uint8_t kcnt[kMaxChunks];
   int8_t head_dst[16];
   uint8_t head_act[16];
+  uint64_t save_off;        // training mode: byte offset of this layer's activation image in the save buffer (kNoSave: none)
+  uint64_t bits_off;        // ... and of its ReLU bit plane
 };
 
 struct FwdParams {
@@ -209,6 +212,7 @@ struct FwdParams {
   int32_t last_extra_step;  // last step whose K-chunks include PE / time code / PE(dir): after its MMAs the three
                             // prologue chunks are dead and the NEXT tile's prologue can be written early
   float flow_scale;
+  uint8_t* save_base;       // training mode (kSave kernels): activation save buffer, see nsff_field_save.cuh
   unsigned long long* dbg;  // NSFF_TIMELINE builds only: (tag, clock64) event log of CTA 0
   int32_t exp_flags;        // NSFF_EXPERIMENT builds only: 1 = MMA ignores hidden-chunk readiness (wrong results),
                             // 2 = MMA ignores accumulator-drained, 4 = MMA ignores weight readiness
@@ -406,7 +410,7 @@ __device__ __forceinline__ void encode_tile_row(const FwdParams& P, uint32_t sA,
   }
 }
 
-template <int kCtas, bool kAppear>
+template <int kCtas, bool kAppear, bool kSave>
 __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid_constant__ FwdParams P) {
   using C = Cfg<kCtas, kAppear>;
   constexpr int kStages = C::kStages;
@@ -658,6 +662,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
               if (lane == 0) arrive_leader(BAR_ACC_EMPTY + slot);
             }
             const uint32_t row_base = sA + (uint32_t)c * kChunkBytes + row_off;
+            uint4 kept[2];
+            uint32_t pos16 = 0;
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               float f[8];
@@ -667,12 +673,38 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
                 const float bv = (i & 3) == 0 ? bb.x : (i & 3) == 1 ? bb.y : (i & 3) == 2 ? bb.z : bb.w;
                 f[i] = __uint_as_float(v[c & 1][u * 8 + i]) + bv;
               }
-              if (relu) store_unit_at<true>(row_base, rsw, part * 2 + u, f);
-              else store_unit_at<false>(row_base, rsw, part * 2 + u, f);
+              if constexpr (kSave) {
+                const uint4 w = relu ? make_uint4(pack_bf16x2_relu(f[0], f[1]), pack_bf16x2_relu(f[2], f[3]),
+                                                  pack_bf16x2_relu(f[4], f[5]), pack_bf16x2_relu(f[6], f[7]))
+                                     : make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                                  pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                st_shared_v4(row_base + (uint32_t)((((part * 2 + u) ^ rsw) & 7) << 4), w.x, w.y, w.z, w.w);
+                kept[u] = w;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) pos16 |= (f[i] > 0.f ? 1u : 0u) << (u * 8 + i);
+              } else {
+                if (relu) store_unit_at<true>(row_base, rsw, part * 2 + u, f);
+                else store_unit_at<false>(row_base, rsw, part * 2 + u, f);
+              }
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) arrive_leader(BAR_HID_FULL + c);
+            if constexpr (kSave) {
+              // training mode: the hidden chunk just published to shared memory is also the backward's tile image;
+              // copy it (and the ReLU bits) to the save buffer after the arrive, off the MMA's critical path
+              if (st.save_off != kNoSave && tile < P.n_tiles) {
+                uint8_t* g = P.save_base + st.save_off + (size_t)tile * kSaveImgPerTile + (size_t)c * kChunkBytes +
+                             (row_off);
+                // the warp's two 16-byte units of this row are one aligned 32-byte sector (swizzle only swaps them)
+                const bool swap = rsw & 1;
+                st_global_v8(g + ((((part * 2) ^ rsw) & 6) << 4), swap ? kept[1] : kept[0], swap ? kept[0] : kept[1]);
+                if (relu)
+                  *reinterpret_cast<uint16_t*>(P.save_base + st.bits_off + (size_t)tile * kSaveBitsPerTile +
+                                               ((size_t)(2 * c + (part >> 1)) * 128 + row) * 4 + (part & 1) * 2) =
+                      (uint16_t)pos16;
+              }
+            }
             NSFF_TL((gstep << 8) | (c << 4) | 7);            // epi: hidden chunk c published
             if (c < 3) {
 #pragma unroll
@@ -834,7 +866,8 @@ extern "C" int nsff_field_pack(const nsff_field_desc* desc, const nsff_field_par
   return after_launch();
 }
 
-static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_mask, FwdParams& P, int* n_out_cols) {
+static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_mask, FwdParams& P, int* n_out_cols,
+                         const SaveLayout* SL) {
   const bool sigma_only = out_mask & NSFF_OUT_SIGMA_ONLY;
   const bool want_s = out_mask & NSFF_OUT_STATIC, want_t = out_mask & NSFF_OUT_TRANSIENT;
   const bool want_fw = out_mask & NSFF_OUT_FLOW_FW, want_bw = out_mask & NSFF_OUT_FLOW_BW;
@@ -856,6 +889,14 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
       if (i < pl.nchunks) s.chunk_pack |= (uint32_t)pl.chunk[i] << (4 * i), s.kcnt_pack |= (uint32_t)pl.kcnt[i] << (4 * i);
     }
     for (int i = 0; i < 16; ++i) s.head_dst[i] = -1, s.head_act[i] = HA_NONE;
+    s.save_off = s.bits_off = kNoSave;
+    if (SL) {
+      if (lid >= L_S1 && lid <= L_S8) s.save_off = SL->s_h[lid - L_S1], s.bits_off = SL->s_hb[lid - L_S1];
+      else if (lid == L_SFIN) s.save_off = SL->s_feat;
+      else if (lid == L_SDIR) s.save_off = SL->s_dir, s.bits_off = SL->s_dirb;
+      else if (lid >= L_T1 && lid <= L_T8) s.save_off = SL->t_h[lid - L_T1], s.bits_off = SL->t_hb[lid - L_T1];
+      else if (lid == L_TFIN) s.save_off = SL->t_feat;
+    }
     return s;
   };
   P.need_dir = 0;
@@ -914,7 +955,7 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
 }
 
 static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdParams& P, int out_mask, int64_t B,
-                          float* out, int32_t out_ld, void* stream) {
+                          float* out, int32_t out_ld, void* stream, void* save = nullptr) {
   if (!desc || !pack || !out) return NSFF_EINVAL;
   if (B < 0 || B > ((int64_t)1 << 31) - 256) return NSFF_EINVAL;
   if (B == 0) return NSFF_OK;
@@ -922,7 +963,13 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
   int rc = build_layout(*desc, L);
   if (rc != NSFF_OK) return rc;
   int ncols = 0;
-  rc = build_program(*desc, L, out_mask, P, &ncols);
+  SaveLayout SL;
+  if (save) {
+    if (out_mask & NSFF_OUT_SIGMA_ONLY) return NSFF_EUNSUPPORTED;
+    SL = save_layout(desc, B, out_mask);
+    P.save_base = static_cast<uint8_t*>(save);
+  }
+  rc = build_program(*desc, L, out_mask, P, &ncols, save ? &SL : nullptr);
   if (rc != NSFF_OK) return rc;
   if (out_ld < ncols) return NSFF_EINVAL;
   int dev = 0, major = 0, sms = 0;
@@ -987,12 +1034,20 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
     return NSFF_OK;
   };
   int lrc;
-  if (ctas == 1) {
-    lrc = appear ? launch_single(field_forward_kernel<1, true>, Cfg<1, true>::kSmemTotal)
-                 : launch_single(field_forward_kernel<1, false>, Cfg<1, false>::kSmemTotal);
+  if (save) {
+    if (ctas == 1) {
+      lrc = appear ? launch_single(field_forward_kernel<1, true, true>, Cfg<1, true>::kSmemTotal)
+                   : launch_single(field_forward_kernel<1, false, true>, Cfg<1, false>::kSmemTotal);
+    } else {
+      lrc = appear ? launch_pair(field_forward_kernel<2, true, true>, Cfg<2, true>::kSmemTotal)
+                   : launch_pair(field_forward_kernel<2, false, true>, Cfg<2, false>::kSmemTotal);
+    }
+  } else if (ctas == 1) {
+    lrc = appear ? launch_single(field_forward_kernel<1, true, false>, Cfg<1, true>::kSmemTotal)
+                 : launch_single(field_forward_kernel<1, false, false>, Cfg<1, false>::kSmemTotal);
   } else {
-    lrc = appear ? launch_pair(field_forward_kernel<2, true>, Cfg<2, true>::kSmemTotal)
-                 : launch_pair(field_forward_kernel<2, false>, Cfg<2, false>::kSmemTotal);
+    lrc = appear ? launch_pair(field_forward_kernel<2, true, false>, Cfg<2, true>::kSmemTotal)
+                 : launch_pair(field_forward_kernel<2, false, false>, Cfg<2, false>::kSmemTotal);
   }
   if (lrc != NSFF_OK) return lrc;
 #ifdef NSFF_TIMELINE
@@ -1030,6 +1085,29 @@ extern "C" int nsff_field_forward(const nsff_field_desc* desc, const void* pack,
   P.pts = *pts;
   P.x_emb = nullptr;
   return launch_forward(desc, pack, P, out_mask, pts->B, out, out_ld, stream);
+}
+
+extern "C" size_t nsff_field_save_bytes(const nsff_field_desc* desc, int64_t B, int out_mask) {
+  if (!desc || B < 0 || (out_mask & NSFF_OUT_SIGMA_ONLY)) return 0;
+  return (size_t)save_layout(desc, B, out_mask).total;
+}
+
+extern "C" int nsff_field_forward_save(const nsff_field_desc* desc, const void* pack, const nsff_points* pts,
+                                       int out_mask, float* out, int32_t out_ld, void* save, void* stream) {
+  if (!pts || !desc || !save) return NSFF_EINVAL;
+  if (pts->B > 0 && (!pts->xyz || pts->S < 1)) return NSFF_EINVAL;
+  if ((out_mask & NSFF_OUT_TRANSIENT) && !pts->t_table) return NSFF_EINVAL;
+  if ((out_mask & NSFF_OUT_STATIC) && desc->use_viewdir && !pts->dirs) return NSFF_EINVAL;
+  if (pts->t_table && ((uintptr_t)pts->t_table & 15u)) return NSFF_EINVAL;
+  if ((out_mask & NSFF_OUT_STATIC) && desc->use_viewdir && desc->in_a > 0 &&
+      (!pts->a_table || ((uintptr_t)pts->a_table & 15u)))
+    return NSFF_EINVAL;
+  if ((uintptr_t)save & 15u) return NSFF_EINVAL;
+  FwdParams P;
+  memset(&P, 0, sizeof(P));
+  P.pts = *pts;
+  P.x_emb = nullptr;
+  return launch_forward(desc, pack, P, out_mask, pts->B, out, out_ld, stream, save);
 }
 
 extern "C" int nsff_field_forward_embedded(const nsff_field_desc* desc, const void* pack, const float* x,

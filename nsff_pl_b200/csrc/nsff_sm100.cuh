@@ -208,6 +208,13 @@ __device__ __forceinline__ void lds_v4(uint32_t addr, float4& v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 32-byte global store (STG.256, sm_100): one full sector per thread; `p` must be 32-byte aligned
+__device__ __forceinline__ void st_global_v8(void* p, const uint4& lo, const uint4& hi) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z),
+               "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
+}
+
 // same with ReLU folded into the conversion (max(x, 0) then round)
 __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
   uint32_t r;

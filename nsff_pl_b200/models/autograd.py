@@ -30,6 +30,9 @@ _FIELD_OF = [  # parameter-name pattern -> (FieldGrads field stem, has layer ind
 ]
 
 
+_SAVE_MAX_POINTS = 1 << 19     # 9.9 KB of saved activations per point and pass: 5 GB at this size
+
+
 def _grad_slot(name):
     for rx, stem, indexed in _FIELD_OF:
         m = rx.match(name)
@@ -63,8 +66,17 @@ class FieldFn(torch.autograd.Function):
         pts.t_table = None if t_code is None else t_code.data_ptr()
         pts.a_table = None if a_code is None else a_code.data_ptr()
         pts.B, pts.S = B, S
+        # tensor-core backward: let the forward kernel save every hidden activation (its shared-memory chunks already
+        # are the backward's tile images) instead of recomputing them layer by layer
+        save = None
+        if (model.precision == "bf16" and model.backward_precision() == "bf16" and B <= _SAVE_MAX_POINTS
+                and not getattr(model, "recompute_in_backward", False)):
+            nbytes = _cabi.lib().nsff_field_save_bytes(C.byref(model.field_desc()), B, mask)
+            if nbytes:
+                save = torch.empty(nbytes, dtype=torch.uint8, device=pos.device)
         with torch.no_grad():
-            model.run_field(mask, out, pts=pts)
+            model.run_field(mask, out, pts=pts, save=save)
+        ctx.saved_acts = save
         ctx.model, ctx.mask, ctx.S = model, mask, S
         ctx.save_for_backward(pos, t_code, a_code, dirs, zs, out)
         return out
@@ -114,7 +126,10 @@ class FieldFn(torch.autograd.Function):
         st = _cabi.stream_ptr(dev)
         tc = model.backward_precision() == "bf16"
         bwd_pack = model.field_bwd_pack() if tc else None
-        rays_per = max(1, (262144 if tc else 32768) // S)
+        saved = ctx.saved_acts if tc else None
+        ctx.saved_acts = None        # consumed here: the node may outlive this call (e.g. a kept `loss`), the 10 KB/point must not
+                                     # (a second backward through a retained graph falls back to the recompute path)
+        rays_per = R if saved is not None else max(1, (262144 if tc else 32768) // S)
         ld = out.stride(0)
         for r0 in range(0, R, rays_per):
             nr = min(rays_per, R - r0)
@@ -132,10 +147,10 @@ class FieldFn(torch.autograd.Function):
                     None if d_t is None else C.c_void_p(d_t.data_ptr() + r0 * d_t.shape[1] * 4),
                     None if d_a is None else C.c_void_p(d_a.data_ptr() + r0 * d_a.shape[1] * 4))
             if tc:
-                scratch = torch.empty(L.nsff_field_bwd_tc_scratch_bytes(C.byref(desc), nb), device=dev,
-                                      dtype=torch.uint8)
+                scratch = torch.empty(L.nsff_field_bwd_tc_scratch_bytes(C.byref(desc), nb, int(saved is not None)),
+                                      device=dev, dtype=torch.uint8)
                 rc = L.nsff_field_backward_tc(C.byref(desc), C.byref(fp), _cabi.ptr(bwd_pack), C.byref(pts), mask,
-                                              *tail, _cabi.ptr(scratch), st)
+                                              *tail, _cabi.ptr(saved), _cabi.ptr(scratch), st)
                 _cabi.check(rc, "nsff_field_backward_tc")
             else:
                 scratch = torch.empty(L.nsff_field_bwd_scratch_floats(C.byref(desc), nb), device=dev,

@@ -250,8 +250,10 @@ class NeRF(nn.Module):
                 "nsff_pl_b200: NeRF.forward on a pre-embedded row records no autograd graph - call it under "
                 "torch.no_grad(); training goes through render_rays (models/autograd.py), which is differentiable.")
 
-    def run_field(self, mask, out, pts=None, x=None):
-        """Launch the MLP on raw points (`pts`: _cabi.Points) or an embedded matrix `x` into `out` (B, C)."""
+    def run_field(self, mask, out, pts=None, x=None, save=None):
+        """Launch the MLP on raw points (`pts`: _cabi.Points) or an embedded matrix `x` into `out` (B, C).
+        `save` (uint8 CUDA tensor of nsff_field_save_bytes): training mode, the kernel also writes every hidden
+        activation for the tensor-core backward."""
         L = _cabi.lib()
         desc = self.field_desc()
         _cabi.select_device(out)
@@ -263,7 +265,10 @@ class NeRF(nn.Module):
             if FIELD_EVENTS is not None:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record(torch.cuda.current_stream(out.device))
-            if pts is not None:
+            if pts is not None and save is not None:
+                rc = L.nsff_field_forward_save(C.byref(desc), _cabi.ptr(pack), C.byref(pts), mask, _cabi.ptr(out),
+                                               out.stride(0), _cabi.ptr(save), st)
+            elif pts is not None:
                 rc = L.nsff_field_forward(C.byref(desc), _cabi.ptr(pack), C.byref(pts), mask, _cabi.ptr(out),
                                           out.stride(0), st)
             else:

@@ -24,7 +24,7 @@ def declared_symbols():
 
 def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
-    assert len(syms) == 35, syms
+    assert len(syms) == 37, syms
     for must in ("nsff_field_forward", "nsff_composite", "nsff_sample_points", "nsff_sample_pdf", "nsff_field_pack",
                  "nsff_field_backward_fp32", "nsff_composite_backward"):
         assert must in syms
