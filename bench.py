@@ -266,6 +266,93 @@ def run_train(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_sequence(args, rank, local_rank, world):
+    """BASELINE.json configs[4]: coarse + fine hierarchical render (64 + 64 importance samples -> 192 fine samples per
+    ray, test_time=True, flows on) of consecutive frames of a 30-frame sequence at a fixed pose, each followed by one
+    time-interpolated frame (rendering.py:365-460: softmax-splat of every sample plane + MPI composite) between the
+    previous and the current frame.  A step = one frame render + one interpolated frame; frames are sharded over ranks
+    (rank r handles frames r, r+world, ...), no collective."""
+    import torch.distributed as dist
+    from nsff_pl_b200 import _cabi
+    from nsff_pl_b200.datasets import ray_utils
+    from nsff_pl_b200.models import nerf as nerf_mod
+    from nsff_pl_b200.models.rendering import interpolate, render_rays
+    from parity_util import build_fields
+    from scenes import FakeDataset
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    w, h = IMG_WH
+    R = w * h
+    models, emb, _, _ = build_fields(W=256, coarse=True, seed=0, n_frames=N_FRAMES, device=dev, precision="bf16")
+    ds = FakeDataset(n_frames=N_FRAMES, n_cams=1, img_wh=IMG_WH, seed=2)
+    K, c2w = ds.Ks[0], torch.tensor(ds.poses[0])
+    rays = ray_utils.frame_rays(h, w, K, c2w, device=dev)             # built on the device (section 8f #4)
+    kw = dict(N_samples=64, N_importance=64, perturb=0, noise_std=0, test_time=True, output_transient_flow=["fw", "bw"])
+
+    def render(t):
+        ts = torch.full((R,), t % N_FRAMES, dtype=torch.long, device=dev)
+        with torch.no_grad():
+            return render_rays(models, emb, rays, ts, N_FRAMES - 1, **kw)
+
+    t0 = rank
+    prev = render(t0)
+    for i in range(max(3, args.warmup)):
+        cur = render(t0 + 1)
+        interpolate(prev, cur, 0.5, K, c2w, IMG_WH)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n0 = _cabi.launch_count()
+    nerf_mod.FIELD_EVENTS = []
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+    ev[0].record()
+    for i in range(args.steps):
+        cur = render(t0 + (i + 1) * world)
+        ev[2 * i + 1].record()
+        rgb, depth = interpolate(prev, cur, 0.5, K, c2w, IMG_WH)
+        ev[2 * i + 2].record()
+        prev = cur
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    field_ev, nerf_mod.FIELD_EVENTS = nerf_mod.FIELD_EVENTS, None
+    ms = ev[0].elapsed_time(ev[-1])
+    render_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)) / args.steps
+    interp_ms = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)) / args.steps
+    field_ms = sum(a.elapsed_time(b) for a, b, _ in field_ev)
+    field_flop = sum(f for _, _, f in field_ev)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        s_fine = cur["zs_fine"].shape[1]
+        peaks = measured_peaks()
+        print(json.dumps({"metric": "ray-samples/sec (hierarchical render_rays + time interpolation)",
+                          "value": R * s_fine * world * args.steps / (ms * 1e-3), "unit": "ray-samples/s",
+                          "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                          "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "bf16", "data": "synthetic",
+                          "config": {"workload": "coarse+fine hierarchical (64 + 64 importance samples per pdf -> "
+                                                 f"{s_fine} fine samples/ray), 512x288 frames of a 30-frame sequence at a "
+                                                 "fixed pose + one interpolated frame (dt=0.5) per rendered frame "
+                                                 "(BASELINE.json configs[4])",
+                                     "rays_per_frame": R, "fine_samples_per_ray": int(s_fine)},
+                          "render_ms_per_frame": render_ms, "interpolate_ms_per_frame": interp_ms,
+                          "field_kernel": {"ms_per_frame": field_ms / args.steps,
+                                           "tflops": field_flop / (field_ms * 1e-3) / 1e12 if field_ms else None,
+                                           "frac_of_peak": (field_flop / (field_ms * 1e-3) / 1e12 / peaks["tflops"])
+                                           if field_ms else None, "peak_source": peaks["source"]},
+                          "gpu_launches": int(_cabi.launch_count() - n0),
+                          "image_checksum": float(rgb.double().sum()), "depth_checksum": float(depth.double().sum())}),
+              flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def workload_config(args, world):
     return {"workload": "full NSFF static+dynamic+flow-warp +-1, 512x288 frame x 128 samples/ray, inference "
                         "(BASELINE.json configs[1])",
@@ -288,8 +375,9 @@ def main():
                     help="train workload: tensor-core backward (default) or the fp32 verification backward")
     ap.add_argument("--bwd-recompute", action="store_true",
                     help="train workload: re-evaluate the layers in the backward instead of saving them in the forward")
-    ap.add_argument("--workload", default="render", choices=["render", "train"],
-                    help="render = BASELINE.json metric (default, what the driver runs); train = configs[2] step")
+    ap.add_argument("--workload", default="render", choices=["render", "train", "sequence"],
+                    help="render = BASELINE.json metric (default, what the driver runs); train = configs[2] step; "
+                         "sequence = configs[4] hierarchical frames + time interpolation")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -298,6 +386,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "sequence":
+        run_sequence(args, rank, local_rank, world)
         return
     if args.workload == "train":
         run_train(args, rank, local_rank, world)

@@ -2,14 +2,13 @@
 // models/softsplat.py:6-44,303-329.  The reference loops over the S sample planes on the host, launching 2 cupy
 // kernels and 4 PCIe copies per plane; here all planes are splatted by ONE launch (projection of the dt-scaled scene
 // flow fused in) and composited front to back by a second one.
-//   splat buffer: (2 directions, S planes, h, w, 5) fp32 = rgb * 1, alpha, weight-sum ; caller-owned scratch
+//   splat buffer: (2 directions, S planes, h, w, 8) fp32 = rgb, alpha | weight-sum, 3 pad: one 32-byte sector per
+//   pixel, updated by ONE 16-byte vector reduction (red.global.add.v4.f32) + one scalar; caller-owned scratch
 #include "nsff_common.cuh"
 
 namespace nsff {
 
-struct InterpArgs {
-  nsff_interpolate_args a;
-};
+constexpr int kSplatStride = 8;   // floats per pixel of the splat buffer
 
 __device__ __forceinline__ void ndc2world_d(const float* p, float fx, float fy, float cx, float cy, float (&o)[3]) {
   // datasets/ray_utils.py:143-148 (eps = 1e-6)
@@ -45,16 +44,16 @@ __global__ void interp_splat_kernel(const nsff_interpolate_args a, float* __rest
   const float x0 = floorf(ox), y0 = floorf(oy);
   const float* rgb = (dir ? a.rgb_tp1 : a.rgb_t) + p * (dir ? a.ld_tp1 : a.ld_t);
   const float alpha = (dir ? a.alpha_tp1 : a.alpha_t)[p];
-  const float val[5] = {rgb[0], rgb[1], rgb[2], alpha, 1.f};
-  float* plane = buf + ((int64_t)dir * a.S + s) * a.R * 5;
+  const float val[4] = {rgb[0], rgb[1], rgb[2], alpha};
+  float* plane = buf + ((int64_t)dir * a.S + s) * a.R * kSplatStride;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const float xi = x0 + (float)(k & 1), yi = y0 + (float)(k >> 1);
     if (!(xi >= 0.f && xi < (float)a.w && yi >= 0.f && yi < (float)a.h)) continue;
     const float wgt = (1.f - fabsf(ox - xi)) * (1.f - fabsf(oy - yi));
-    float* dst = plane + ((int64_t)yi * a.w + (int64_t)xi) * 5;
-#pragma unroll
-    for (int c = 0; c < 5; ++c) atomicAdd(dst + c, val[c] * wgt);
+    float* dst = plane + ((int64_t)yi * a.w + (int64_t)xi) * kSplatStride;
+    atomicAdd(reinterpret_cast<float4*>(dst), make_float4(val[0] * wgt, val[1] * wgt, val[2] * wgt, val[3] * wgt));
+    atomicAdd(dst + 4, wgt);
   }
 }
 
@@ -64,9 +63,12 @@ __global__ void interp_composite_kernel(const nsff_interpolate_args a, const flo
   if (pix >= a.R) return;
   float acc[3] = {0.f, 0.f, 0.f}, acc_a = 0.f, depth = 0.f;
   for (int s = 0; s < a.S; ++s) {
-    const float* f = buf + ((int64_t)s * a.R + pix) * 5;
-    const float* b = buf + ((int64_t)(a.S + s) * a.R + pix) * 5;
-    const float nf = f[4] == 0.f ? 1.f : f[4], nb = b[4] == 0.f ? 1.f : b[4];
+    const float4 f4 = *reinterpret_cast<const float4*>(buf + ((int64_t)s * a.R + pix) * kSplatStride);
+    const float4 b4 = *reinterpret_cast<const float4*>(buf + ((int64_t)(a.S + s) * a.R + pix) * kSplatStride);
+    const float fw = buf[((int64_t)s * a.R + pix) * kSplatStride + 4];
+    const float bw = buf[((int64_t)(a.S + s) * a.R + pix) * kSplatStride + 4];
+    const float f[4] = {f4.x, f4.y, f4.z, f4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+    const float nf = fw == 0.f ? 1.f : fw, nb = bw == 0.f ? 1.f : bw;
     const float fa = f[3] / nf, ba = b[3] / nb;
     const int64_t p = pix * a.S + s;
     const float* srgb = a.static_rgb + p * a.ld_t;
@@ -91,7 +93,7 @@ __global__ void interp_composite_kernel(const nsff_interpolate_args a, const flo
 
 using namespace nsff;
 
-extern "C" size_t nsff_interpolate_scratch_floats(int64_t R, int S) { return (R < 0 || S < 0) ? 0 : (size_t)2 * S * R * 5; }
+extern "C" size_t nsff_interpolate_scratch_floats(int64_t R, int S) { return (R < 0 || S < 0) ? 0 : (size_t)2 * S * R * nsff::kSplatStride; }
 
 extern "C" int nsff_interpolate(const nsff_interpolate_args* args, float* scratch, float* rgb, float* depth,
                                 void* stream) {
