@@ -237,7 +237,12 @@ struct FinishJob {
   int32_t dcol0[4], ncols[4];
   float* drow[16];           // direct mode: destination of acc_t row n (256 floats) or NULL
 };
-__global__ void wgrad_finish_kernel(const __grid_constant__ FinishJob J) {
+constexpr int kFinishBatch = 16;
+struct FinishJobs {
+  FinishJob job[kFinishBatch];
+};
+__global__ void wgrad_finish_kernel(const __grid_constant__ FinishJobs JJ) {
+  const FinishJob& J = JJ.job[blockIdx.y];
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = idx >> 8, m = idx & 255;
   if (J.direct) {
@@ -914,7 +919,21 @@ struct Ctx {
   const uint8_t* pack;
   float* acc;
   size_t acc_used, acc_cap;   // in floats
+  std::vector<FinishJob> finish;   // scatter jobs of the wgrad results, launched in batches (each owns its acc slot)
 };
+
+static int flush_finish(Ctx& c) {
+  for (size_t i = 0; i < c.finish.size(); i += kFinishBatch) {
+    FinishJobs JJ;
+    memset(&JJ, 0, sizeof(JJ));
+    const int n = (int)std::min<size_t>(kFinishBatch, c.finish.size() - i);
+    for (int k = 0; k < n; ++k) JJ.job[k] = c.finish[i + k];
+    wgrad_finish_kernel<<<dim3(256, (unsigned)n), 256, 0, c.st>>>(JJ);
+    TRY(after_launch());
+  }
+  c.finish.clear();
+  return NSFF_OK;
+}
 
 struct GemmOut {
   int epi;
@@ -979,16 +998,16 @@ static int finish_cols(Ctx& c, const float* acc, float* dW, int ldw, std::initia
   for (int v : dcol0) J.dcol0[i++] = v;
   i = 0;
   for (int v : ncols) J.ncols[i++] = v;
-  wgrad_finish_kernel<<<J.nb * 64, 256, 0, c.st>>>(J);
-  return after_launch();
+  c.finish.push_back(J);
+  return NSFF_OK;
 }
 static int finish_rows(Ctx& c, const float* acc, float* const (&drow)[16]) {
   FinishJob J;
   memset(&J, 0, sizeof(J));
   J.acc_t = acc; J.direct = 1;
   for (int i = 0; i < 16; ++i) J.drow[i] = drow[i];
-  wgrad_finish_kernel<<<16, 256, 0, c.st>>>(J);
-  return after_launch();
+  c.finish.push_back(J);
+  return NSFF_OK;
 }
 struct Trunk {
   bool trans;
@@ -1125,7 +1144,7 @@ int nsff_field_backward_tc(const nsff_field_desc* d, const nsff_field_params* p,
     s.TFEAT = at(SL.t_feat);
   }
   const bool recompute = saved == nullptr;
-  Ctx c{st, (int)cdiv64(B, 128), B, reinterpret_cast<const uint8_t*>(pack), s.ACC, 0, s.acc_bytes / sizeof(float)};
+  Ctx c{st, (int)cdiv64(B, 128), B, reinterpret_cast<const uint8_t*>(pack), s.ACC, 0, s.acc_bytes / sizeof(float), {}};
   NSFF_CUDA_TRY(cudaMemsetAsync(s.ACC, 0, s.acc_bytes, st));
   if (d_pos) NSFF_CUDA_TRY(cudaMemsetAsync(d_pos, 0, (size_t)B * 3 * sizeof(float), st));
   if (d_t) NSFF_CUDA_TRY(cudaMemsetAsync(d_t, 0, (size_t)R * d->in_t * sizeof(float), st));
@@ -1299,7 +1318,7 @@ int nsff_field_backward_tc(const nsff_field_desc* d, const nsff_field_params* p,
     if (d_t && d->in_t > 0) TRY(launch_ray_reduce(d_in, 128, d->in_xyz, d->in_t, pts->S, R, d_t, st));
     if (d_pos) TRY(launch_pe_bwd(d_in, 128, pts->xyz, (d->in_xyz - 3) / 6, d_pos, B, st));
   }
-  return NSFF_OK;
+  return flush_finish(c);
 }
 
 // ---- generic entry points (unit tests; hosts that keep their own bf16 tile images) -------------------------------

@@ -119,3 +119,30 @@ def test_pack_unpack_pixels_roundtrip():
     back = unpack_pixels(buf, res)
     for k in PIXEL_KEYS:
         assert torch.equal(back[k], res[k])
+
+
+def test_backward_buffer_sizes_are_host_side_pure_functions():
+    """Size queries of the tensor-core backward need no GPU: tile-image bytes, the activation save buffer written by
+    nsff_field_forward_save, the W / W^T block pack and the scratch (smaller when the forward saved the activations)."""
+    import ctypes as C
+    from nsff_pl_b200 import _cabi
+    from nsff_pl_b200.models.nerf import NeRF
+    L = _cabi.lib()
+    assert L.nsff_img_bytes(1, 1) == 128 * 128 and L.nsff_img_bytes(129, 4) == 2 * 4 * 128 * 128
+    assert L.nsff_img_bytes(0, 4) == 0
+    fine = NeRF("fine", encode_transient=True, in_channels_t=48, output_flow=True)
+    desc = fine.field_desc()
+    B = 1000                                                   # 8 tiles
+    img, bits = 8 * 4 * 128 * 128, 8 * 8 * 128 * 4
+    both = _cabi.OUT_STATIC | _cabi.OUT_TRANSIENT | _cabi.OUT_FLOW_FW | _cabi.OUT_FLOW_BW
+    # static: 8 trunk layers + final + dir (bits for the 9 ReLU layers); transient: 8 trunk + final (8 bit planes)
+    assert L.nsff_field_save_bytes(C.byref(desc), B, both) == (10 + 9) * img + (9 + 8) * bits
+    assert L.nsff_field_save_bytes(C.byref(desc), B, _cabi.OUT_TRANSIENT | _cabi.OUT_FLOW_FW) == 9 * img + 8 * bits
+    assert L.nsff_field_save_bytes(C.byref(desc), B, _cabi.OUT_STATIC | _cabi.OUT_SIGMA_ONLY) == 0
+    pack = L.nsff_field_bwd_tc_pack_bytes(C.byref(desc))
+    assert pack > 0 and pack % (64 * 128) == 0                 # whole 64-row x 64-column bf16 blocks
+    full = L.nsff_field_bwd_tc_scratch_bytes(C.byref(desc), B, 0)
+    lean = L.nsff_field_bwd_tc_scratch_bytes(C.byref(desc), B, 1)
+    assert 0 < lean < full and full - lean >= (10 + 9) * img
+    small = NeRF("fine", W=64, encode_transient=True, in_channels_t=48, output_flow=True)
+    assert L.nsff_field_bwd_tc_pack_bytes(C.byref(small.field_desc())) == 0      # tcgen05 path: 8 x 256 only
