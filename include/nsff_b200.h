@@ -140,6 +140,9 @@ typedef struct {
   const float*   zs;         /* (B,) depths; flow heads are zeroed where z > 0.95 (:126,187) */
   int64_t        B;
   int32_t        S;
+  float*         xyz_fw_out; /* (B,3) optional, passes that evaluate the flow heads: xyz + flow_fw and              */
+  float*         xyz_bw_out; /*       xyz + flow_bw = the points of the warped passes (rendering.py:219,225), so   */
+                             /*       those passes read 12 B/pt instead of 12 B out of every 56-byte output row    */
 } nsff_points;
 
 /* Fused PE + MLP forward on tensor cores (tcgen05/TMEM, bf16 operands, fp32 accumulate).

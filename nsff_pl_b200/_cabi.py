@@ -47,7 +47,7 @@ class Points(C.Structure):
                 ("xyz_out", C.c_void_p), ("dirs", C.c_void_p), ("t_table", C.c_void_p),
                 ("t_index", C.c_void_p), ("t_shift", C.c_int32), ("max_t", C.c_int32),
                 ("a_table", C.c_void_p), ("a_index", C.c_void_p), ("zs", C.c_void_p),
-                ("B", C.c_int64), ("S", C.c_int32)]
+                ("B", C.c_int64), ("S", C.c_int32), ("xyz_fw_out", C.c_void_p), ("xyz_bw_out", C.c_void_p)]
 
 
 class CompositeArgs(C.Structure):

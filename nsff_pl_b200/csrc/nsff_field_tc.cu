@@ -724,6 +724,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
             if (valid) {
               float* orow = P.out + p * P.out_ld;
 #pragma unroll
+              float fl[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // flow fw / bw = head columns 4..9 of the dynamic block
+              bool has_flow = false;
               for (int i = 0; i < 16; ++i) {
                 const int dst = st.head_dst[i];
                 if (dst < 0) continue;
@@ -732,8 +734,23 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
                 float x = __uint_as_float(v[i]) + bi;
                 const int act = st.head_act[i];
                 if (act == HA_SIGMOID) x = sigmoid_f(x);
-                else if (act == HA_FLOW) x = (zrow > kZFar) ? 0.f : P.flow_scale * tanhf(x);
+                else if (act == HA_FLOW) {
+                  x = (zrow > kZFar) ? 0.f : P.flow_scale * tanhf(x);
+                  if (i >= 4 && i < 10) fl[i - 4] = x, has_flow = true;
+                }
                 orow[dst] = x;
+              }
+              // points of the warped passes, written here so those passes do not gather 12 B out of every output row
+              if (has_flow && P.x_emb == nullptr && P.pts.offset == nullptr) {
+                const float* x3 = P.pts.xyz + p * 3;
+                if (P.pts.xyz_fw_out) {
+#pragma unroll
+                  for (int c = 0; c < 3; ++c) P.pts.xyz_fw_out[p * 3 + c] = __fadd_rn(x3[c], fl[c]);
+                }
+                if (P.pts.xyz_bw_out) {
+#pragma unroll
+                  for (int c = 0; c < 3; ++c) P.pts.xyz_bw_out[p * 3 + c] = __fadd_rn(x3[c], fl[3 + c]);
+                }
               }
             }
           }

@@ -117,7 +117,15 @@ def _field_pass(results, model, embeddings, xyz, zs, dirs, ts, max_t, want_trans
             p.a_table, p.a_index = a_embedded.data_ptr(), None
         return p
 
-    model.run_field(mask, raw.view(B, Cn), pts=points(xyz))
+    # training-mode flow passes: the main pass also writes the warped points xyz + flow_fw / xyz + flow_bw
+    # (rendering.py:219,225), which the two re-query passes then read as plain positions
+    pre_warp = (want_transient and (not test_time) and bool(flow_heads) and "fw" in flow_heads and "bw" in flow_heads
+                and model.precision == "bf16")
+    main_pts = points(xyz)
+    if pre_warp:
+        xyz_fw, xyz_bw = torch.empty(R, S, 3, **f32), torch.empty(R, S, 3, **f32)
+        main_pts.xyz_fw_out, main_pts.xyz_bw_out = xyz_fw.data_ptr(), xyz_bw.data_ptr()
+    model.run_field(mask, raw.view(B, Cn), pts=main_pts)
 
     if not sigma_only:
         results[f"static_rgbs_{typ}"] = raw[..., :3]
@@ -172,15 +180,19 @@ def _field_pass(results, model, embeddings, xyz, zs, dirs, ts, max_t, want_trans
         if warp:                                                       # rendering.py:217-232
             warp_mask_fw = NeRF.out_mask(False, False, True, ["bw"])   # forward-warped points want the bw flow
             warp_mask_bw = NeRF.out_mask(False, False, True, ["fw"])
-            xyz_fw, raw_fw = torch.empty(R, S, 3, **f32), torch.empty(R, S, 7, **f32)
-            xyz_bw, raw_bw = torch.empty(R, S, 3, **f32), torch.empty(R, S, 7, **f32)
-            model.run_field(warp_mask_fw, raw_fw.view(B, 7),
-                            pts=points(xyz, offset=raw.data_ptr() + 8 * 4, offset_ld=Cn, xyz_out=xyz_fw, t_shift=+1,
-                                       use_t_embedded=False))
+            raw_fw, raw_bw = torch.empty(R, S, 7, **f32), torch.empty(R, S, 7, **f32)
+            if pre_warp:
+                pts_fw = points(xyz_fw, t_shift=+1, use_t_embedded=False)
+                pts_bw = points(xyz_bw, t_shift=-1, use_t_embedded=False)
+            else:
+                xyz_fw, xyz_bw = torch.empty(R, S, 3, **f32), torch.empty(R, S, 3, **f32)
+                pts_fw = points(xyz, offset=raw.data_ptr() + 8 * 4, offset_ld=Cn, xyz_out=xyz_fw, t_shift=+1,
+                                use_t_embedded=False)
+                pts_bw = points(xyz, offset=raw.data_ptr() + 11 * 4, offset_ld=Cn, xyz_out=xyz_bw, t_shift=-1,
+                                use_t_embedded=False)
+            model.run_field(warp_mask_fw, raw_fw.view(B, 7), pts=pts_fw)
             a.noise_fw = noise()
-            model.run_field(warp_mask_bw, raw_bw.view(B, 7),
-                            pts=points(xyz, offset=raw.data_ptr() + 11 * 4, offset_ld=Cn, xyz_out=xyz_bw, t_shift=-1,
-                                       use_t_embedded=False))
+            model.run_field(warp_mask_bw, raw_bw.view(B, 7), pts=pts_bw)
             a.noise_bw = noise()
             a.raw_fw, a.raw_bw, a.raw_w_ld = raw_fw.data_ptr(), raw_bw.data_ptr(), 7
             a.xyz_fw, a.xyz_bw = xyz_fw.data_ptr(), xyz_bw.data_ptr()

@@ -66,7 +66,7 @@ def test_struct_layouts_match_the_c_header(libpath, tmp_path):
     fields = {
         "nsff_field_desc": ["W", "flow_scale"],
         "nsff_field_params": ["static_w", "static_final_w", "trans_w", "trans_bw_b"],
-        "nsff_points": ["xyz", "offset_ld", "xyz_out", "t_shift", "a_table", "zs", "B", "S"],
+        "nsff_points": ["xyz", "offset_ld", "xyz_out", "t_shift", "a_table", "zs", "B", "S", "xyz_fw_out", "xyz_bw_out"],
         "nsff_composite_args": ["R", "S", "raw_ld", "noise_std", "vis", "raw_w_ld", "xyz_fw", "static_sigmas",
                                 "disoccs_bw", "depth", "disocc_bw"],
         "nsff_composite_grads": ["static_sigmas", "xyzs_fw_bw", "depth", "xyz_bw_ray", "rgb_bw", "d_raw", "d_raw_bw"],
