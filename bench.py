@@ -159,7 +159,7 @@ def run_train(args, rank, local_rank, world):
     surrogate photometric + warped-photometric + cycle + flow-regulariser loss (the reference's NeRFWLoss needs
     kornia and dataset tensors), Adam step and bf16 re-pack inside the timed region; gradients all-reduced over ranks."""
     import torch.distributed as dist
-    from nsff_pl_b200 import _cabi
+    from nsff_pl_b200 import _cabi, parallel
     from nsff_pl_b200.models.rendering import render_rays
     from parity_util import build_fields, synthetic_rays
     torch.cuda.set_device(local_rank)
@@ -204,15 +204,7 @@ def run_train(args, rank, local_rank, world):
         loss.backward()
         mark("backward")
         if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
-            dist.all_reduce(flat)
-            flat /= world
-            o = 0
-            for p in params:
-                if p.grad is not None:
-                    n = p.grad.numel()
-                    p.grad.copy_(flat[o:o + n].view_as(p.grad))
-                    o += n
+            parallel.all_reduce_gradients(params)
         opt.step()
         mark("allreduce+adam")
         return loss

@@ -58,3 +58,47 @@ def test_sharded_render_equals_single_process(n_rays):
     mp.spawn(_worker, args=(2, _free_port(), n_rays, ret), nprocs=2, join=True)
     assert ret["ok"] is True
     assert ret["shapes"]["rgb_fine"] == (n_rays, 3) and ret["shapes"]["depth_fine"] == (n_rays,)
+
+
+def _grad_worker(rank, world, port, ret):
+    for p in (ROOT, HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from nsff_pl_b200 import parallel
+        torch.manual_seed(0)                                     # replicated parameters
+        params = [torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(7)),
+                  torch.nn.Parameter(torch.randn(2, 2), requires_grad=False), torch.nn.Parameter(torch.randn(4))]
+        g = torch.Generator().manual_seed(100 + rank)            # per-rank ray batch -> per-rank gradients
+        params[0].grad = torch.randn(5, 3, generator=g)
+        params[1].grad = torch.randn(7, generator=g)
+        if rank == 0:                                            # a head that only rank 0 exercised
+            params[3].grad = torch.randn(4, generator=g)
+        n = parallel.all_reduce_gradients(params)
+        ret[rank] = (n, [None if p.grad is None else p.grad.clone() for p in params])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_all_reduce_averages_over_ranks():
+    """Training N>1: one flat all-reduce, gradients averaged, frozen parameters untouched,
+    a parameter that received a gradient on one rank only is averaged with zeros on the others."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_grad_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    (n0, g0), (n1, g1) = ret[0], ret[1]
+    assert n0 == n1 == 15 + 7 + 4
+    want0, want1, want3 = [], [], []
+    for r in range(world):
+        g = torch.Generator().manual_seed(100 + r)
+        want0.append(torch.randn(5, 3, generator=g))
+        want1.append(torch.randn(7, generator=g))
+        want3.append(torch.randn(4, generator=g) if r == 0 else torch.zeros(4))
+    for got in (g0, g1):
+        assert torch.allclose(got[0], sum(want0) / world) and torch.allclose(got[1], sum(want1) / world)
+        assert got[2] is None
+        assert torch.allclose(got[3], sum(want3) / world)
