@@ -52,6 +52,12 @@ __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void* src
       : "memory");
 }
 
+// Programmatic dependent launch: the next GEMM of the chain may start its preamble (barrier init, TMEM allocation,
+// weight blocks into shared memory) while this one drains; nothing that depends on the previous kernel's output is
+// touched before griddep_wait().  Both are no-ops when the launch does not carry the PDL attribute.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t row_off(int row) { return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128); }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -318,6 +324,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) img_gemm_kernel(const __grid_
     }
     fence_mbar_init();
   }
+  griddep_launch_dependents();
   if (warp == kGemmEpiWarps + 1) tmem_alloc(sTmemPtr, 512);
   for (int i = threadIdx.x; i < P.N; i += blockDim.x) bias_s[i] = P.bias ? P.bias[i] : 0.f;
   tc_fence_before_sync();
@@ -332,6 +339,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) img_gemm_kernel(const __grid_
       mbar_arrive_expect_tx(bar(GB_B_FULL), (uint32_t)P.n_chunks * blk_bytes);
       for (int c = 0; c < P.n_chunks; ++c)
         bulk_g2s(sB + (uint32_t)c * blk_bytes, P.b_blocks + (size_t)c * blk_bytes, blk_bytes, bar(GB_B_FULL));
+      griddep_wait();                       // weights are constants of the backward; the A tiles are not
       uint32_t stage = 0, par = 1;
       const uint64_t pol = policy_evict_first();
       for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
@@ -375,6 +383,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) img_gemm_kernel(const __grid_
     }
   } else {
     // ===== epilogue: warp (q, part) drains rows 32q.. of a quarter of the columns (32 at least) =====
+    griddep_wait();                         // reads bit planes / accumulates into rows written by earlier kernels
     const int q = warp & 3, part = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t roff = row_off(row);
@@ -575,6 +584,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) img_wgrad_kernel(const __grid_c
     mbar_init(bar(WB_ACC), 1);
     fence_mbar_init();
   }
+  griddep_launch_dependents();
   if (warp == kWgEpiWarps + 1) tmem_alloc(sTmemPtr, 512);
   tc_fence_before_sync();
   __syncthreads();
@@ -582,6 +592,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) img_wgrad_kernel(const __grid_c
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sTmemPtr));
   const uint32_t N = (uint32_t)P.nb * 64u;
+  if (warp != kWgEpiWarps + 1) griddep_wait();       // operand tiles and the RED target belong to earlier kernels
 
   if (n_half > 0) {
     if (warp == kWgEpiWarps) {
@@ -686,11 +697,35 @@ static int l2_hint_enabled() {
   return v;
 }
 
+static int pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NSFF_BWD_PDL");        // A/B knob.  Measured on the 1024 x 128 training step: backward phase
+    v = e ? atoi(e) : 0;                           // 4.19 -> 4.00 ms, but median step 4.92 -> 5.08 ms (more jitter): off
+  }
+  return v;
+}
+
+template <typename Kern, typename Params>
+static int launch_pdl(Kern kern, int grid, int threads, uint32_t smem, cudaStream_t st, const Params& P) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  NSFF_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, P));
+  return after_launch();
+}
+
 template <int kEpi>
 static int launch_gemm_t(const GemmParams& P, int grid, uint32_t smem, cudaStream_t st) {
   NSFF_CUDA_TRY(cudaFuncSetAttribute(img_gemm_kernel<kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-  img_gemm_kernel<kEpi><<<grid, kGemmThreads, smem, st>>>(P);
-  return after_launch();
+  return launch_pdl(img_gemm_kernel<kEpi>, grid, kGemmThreads, smem, st, P);
 }
 
 static int launch_gemm(GemmParams& P, cudaStream_t st) {
@@ -722,8 +757,7 @@ static int launch_wgrad(WgradParams& P, cudaStream_t st) {
   P.l2_hint = l2_hint_enabled();
   int grid = sm_count();
   if (grid > P.n_tiles) grid = P.n_tiles;
-  img_wgrad_kernel<<<grid, kWgThreads, kWgSmem, st>>>(P);
-  return after_launch();
+  return launch_pdl(img_wgrad_kernel, grid, kWgThreads, kWgSmem, st, P);
 }
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
