@@ -58,7 +58,8 @@ def full(path, out):
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     with open(out, "w") as fh:
-        fh.write(f"# ncu --set full summary ({path})\n\n`ncu --set full --clock-control none --import-source on -k regex:field_forward`\n\n")
+        fh.write(f"# ncu --set full summary ({path})\n\n`ncu --set full --clock-control none --import-source on -k regex:<kernel>` "
+                 "(see tools/profile_round.sh for the exact command)\n\n")
         names = [r[hdr.index("Kernel Name")].split("(")[0] for r in data]
         fh.write("| metric | unit | " + " | ".join(f"launch {i}" for i in range(len(data))) + " |\n|---|---|" + "---:|" * len(data) + "\n")
         for k in KEYS:
