@@ -42,6 +42,15 @@ RENDER_KW = dict(N_samples=N_SAMPLES, perturb=0, noise_std=0, N_importance=0, te
 CPU_SAMPLE_RAYS = 2048
 
 
+def _traffic(name):
+    """dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture (profiles/)."""
+    path = os.path.join(ROOT, "profiles", name)
+    if not os.path.exists(path):
+        return None
+    with open(path) as fh:
+        return json.load(fh).get("dram_bytes_per_launch")
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -486,11 +495,7 @@ def main():
         flops = [f for _, _, f in field_events]
         per_launch_ms = sum(kern_ms) / max(1, len(kern_ms))
         achieved = (sum(flops) / (sum(kern_ms) * 1e-3)) / 1e12 if kern_ms else None
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "field_forward_traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as fh:
-                traffic = json.load(fh).get("dram_bytes_per_launch")
+        traffic = _traffic("field_forward_traffic.json")
         roofline = {"bound": "tensor", "kernel": "nsff::tc::field_forward_kernel", "achieved": achieved,
                     "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": None if achieved is None else achieved / peaks["tflops"],
                     "traffic": traffic, "peak_source": f"{peaks['source']} bf16_tflops_sustained",
@@ -502,7 +507,7 @@ def main():
         comp_gbs = (sum(comp_bytes) / (sum(comp_ms) * 1e-3)) / 1e9 if comp_ms else None
         roofline_composite = {"bound": "hbm", "kernel": "nsff::composite_kernel<1,1,1>", "achieved": comp_gbs,
                               "peak": peaks["hbm"], "unit": "GB/s", "frac": None if comp_gbs is None else comp_gbs / peaks["hbm"],
-                              "traffic": None, "peak_source": f"{peaks['source']} hbm_gbs",
+                              "traffic": _traffic("composite_traffic.json"), "peak_source": f"{peaks['source']} hbm_gbs",
                               "launches_timed": len(comp_ms), "avg_launch_ms": sum(comp_ms) / max(1, len(comp_ms)),
                               "kernel_share_of_step": (sum(comp_ms) / ms) if comp_ms else None,
                               "algorithmic_bytes_per_launch": (sum(comp_bytes) / len(comp_bytes)) if comp_bytes else None}

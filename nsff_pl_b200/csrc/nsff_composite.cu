@@ -55,8 +55,11 @@ __device__ __forceinline__ void st3_reduced(float* dst, int64_t ray, Vec3 v, int
   }
 }
 
+#ifndef NSFF_COMP_MINB
+#define NSFF_COMP_MINB 3
+#endif
 template <bool kTransient, bool kFlow, bool kWarp>
-__global__ void __launch_bounds__(256) composite_kernel(const nsff_composite_args a) {
+__global__ void __launch_bounds__(256, NSFF_COMP_MINB) composite_kernel(const nsff_composite_args a) {
   const int lane = threadIdx.x & 31;
   const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (ray >= a.R) return;
