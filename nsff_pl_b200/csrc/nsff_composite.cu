@@ -55,8 +55,11 @@ __device__ __forceinline__ void st3_reduced(float* dst, int64_t ray, Vec3 v, int
   }
 }
 
+// The kernel is latency-bound (ncu: long-scoreboard stalls, 35 % issue slots) and its 78 registers allowed only
+// 3 blocks = 24 warps per SM; capping at 64 registers (4 blocks, 80 bytes of spills) measured 1.01 -> 0.89 ms on the
+// bench frame (3.8 -> 4.3 TB/s); 5 and 6 blocks spill more and are slower (tools/comp_occ.sh).
 #ifndef NSFF_COMP_MINB
-#define NSFF_COMP_MINB 3
+#define NSFF_COMP_MINB 4
 #endif
 template <bool kTransient, bool kFlow, bool kWarp>
 __global__ void __launch_bounds__(256, NSFF_COMP_MINB) composite_kernel(const nsff_composite_args a) {
