@@ -1089,6 +1089,7 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
 extern "C" int nsff_field_forward(const nsff_field_desc* desc, const void* pack, const nsff_points* pts,
                                   int out_mask, float* out, int32_t out_ld, void* stream) {
   if (!pts || !desc) return NSFF_EINVAL;
+  if (pts->B == 0) return NSFF_OK;                       // empty batch: data pointers of empty tensors are NULL
   if (pts->B > 0 && (!pts->xyz || pts->S < 1)) return NSFF_EINVAL;
   if ((out_mask & NSFF_OUT_TRANSIENT) && !pts->t_table) return NSFF_EINVAL;
   if ((out_mask & NSFF_OUT_STATIC) && !(out_mask & NSFF_OUT_SIGMA_ONLY) && desc->use_viewdir && !pts->dirs)
@@ -1111,7 +1112,9 @@ extern "C" size_t nsff_field_save_bytes(const nsff_field_desc* desc, int64_t B, 
 
 extern "C" int nsff_field_forward_save(const nsff_field_desc* desc, const void* pack, const nsff_points* pts,
                                        int out_mask, float* out, int32_t out_ld, void* save, void* stream) {
-  if (!pts || !desc || !save) return NSFF_EINVAL;
+  if (!pts || !desc) return NSFF_EINVAL;
+  if (pts->B == 0) return NSFF_OK;
+  if (!save) return NSFF_EINVAL;
   if (pts->B > 0 && (!pts->xyz || pts->S < 1)) return NSFF_EINVAL;
   if ((out_mask & NSFF_OUT_TRANSIENT) && !pts->t_table) return NSFF_EINVAL;
   if ((out_mask & NSFF_OUT_STATIC) && desc->use_viewdir && !pts->dirs) return NSFF_EINVAL;
@@ -1131,6 +1134,7 @@ extern "C" int nsff_field_forward_embedded(const nsff_field_desc* desc, const vo
                                            int32_t x_ld, int64_t B, int out_mask, float* out, int32_t out_ld,
                                            void* stream) {
   if (!desc || (B > 0 && !x)) return NSFF_EINVAL;
+  if (B == 0) return NSFF_OK;
   FwdParams P;
   memset(&P, 0, sizeof(P));
   P.pts.B = B;

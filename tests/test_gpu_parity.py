@@ -465,3 +465,22 @@ def test_frame_rays_on_device_match_reference_fixture_and_oracle():
     o_ref = torch.stack([-1 / (cx / fx) * o[:, 0] / o[:, 2], -1 / (cy / fy) * o[:, 1] / o[:, 2], 1 + 2 / o[:, 2]], -1)
     assert max_abs(o_d.cpu(), o_ref) < 1e-5
     assert float((o_d[:, 2] + d_d[:, 2] - 1).abs().max()) < 1e-6
+
+
+@pytest.mark.gpu
+def test_empty_ray_batch_returns_empty_results_with_the_same_keys():
+    """Edge case: R = 0 (a ragged last chunk of eval.f can be empty).  No kernel launch may fail; every result keeps its
+    key, dtype and trailing shape with a leading dimension of 0."""
+    from nsff_pl_b200.models.rendering import render_rays
+    models, emb, _, _ = build_fields(W=256, seed=2, precision="bf16", n_frames=8)
+    rays, ts = synthetic_rays(3, n_frames=8, seed=7)
+    for kw in (dict(N_samples=16, test_time=False, output_transient_flow=["fw", "bw", "disocc"]),
+               dict(N_samples=16, test_time=True, output_transient_flow=["fw", "bw"])):
+        with torch.no_grad():
+            one = render_rays(models, emb, rays[:1].cuda(), ts[:1].cuda(), 7, **kw)
+            none = render_rays(models, emb, rays[:0].cuda(), ts[:0].cuda(), 7, **kw)
+        torch.cuda.synchronize()
+        assert list(one.keys()) == list(none.keys())
+        for k in one:
+            assert none[k].shape == (0,) + tuple(one[k].shape[1:]), k
+            assert none[k].dtype == one[k].dtype
