@@ -262,6 +262,8 @@ def run_train(args, rank, local_rank, world):
                           "step_ms": {"min": round(per_step[0], 3), "median": round(per_step[len(per_step) // 2], 3),
                                       "max": round(per_step[-1], 3)},
                           "algorithmic_tflop_per_step": round(R * S * 14.28e6 / 1e12, 3),
+                          "tflops_whole_step": R * S * world * 14.28e6 / (ms / args.steps * 1e-3) / 1e12,
+                          "frac_of_bf16_peak": R * S * 14.28e6 / (ms / args.steps * 1e-3) / 1e12 / measured_peaks()["tflops"],
                           "gpu_launches": int(_cabi.launch_count() - n0), "final_loss": float(loss)}), flush=True)
     if world > 1:
         dist.destroy_process_group()
