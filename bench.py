@@ -39,7 +39,7 @@ FLOP_PER_POINT_WARP = 2 * 582_912                    # dynamic branch, one flow 
 FLOP_PER_POINT = FLOP_PER_POINT_MAIN + 2 * FLOP_PER_POINT_WARP   # 4,759,040
 RENDER_KW = dict(N_samples=N_SAMPLES, perturb=0, noise_std=0, N_importance=0, test_time=False,
                  output_transient_flow=["fw", "bw", "disocc"])
-CPU_SAMPLE_RAYS = 2048
+CPU_SAMPLE_RAYS = int(os.environ.get("NSFF_BENCH_CPU_SAMPLE_RAYS", "2048"))   # bounded sample of the frame for the CPU arm
 
 
 def _traffic(name):
