@@ -113,7 +113,7 @@ struct PackJobs {
 __global__ void pack_blocks_kernel(const __grid_constant__ PackJobs J) {
   const PackJob& j = J.job[blockIdx.x];
   const int total = j.n_valid * j.k_valid;
-  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+  for (int e = threadIdx.x + blockIdx.y * blockDim.x; e < total; e += blockDim.x * gridDim.y) {
     int n, k;
     if (j.transpose) n = e % j.n_valid, k = e / j.n_valid;     // consecutive threads walk the contiguous source dim
     else k = e % j.k_valid, n = e / j.k_valid;
@@ -808,7 +808,7 @@ static int flush_pack_jobs(PackBuilder& pb, cudaStream_t st) {
     memset(&J, 0, sizeof(J));
     const int n = (int)std::min<size_t>(kPackJobsPerLaunch, pb.jobs.size() - i);
     for (int k = 0; k < n; ++k) J.job[k] = pb.jobs[i + k];
-    pack_blocks_kernel<<<n, 256, 0, st>>>(J);
+    pack_blocks_kernel<<<dim3((unsigned)n, 8), 256, 0, st>>>(J);      // 8 blocks per 16K-element job
     TRY(after_launch());
   }
   pb.jobs.clear();
