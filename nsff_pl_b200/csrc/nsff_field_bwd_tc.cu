@@ -134,42 +134,51 @@ struct HeadSpec {
 __global__ void __launch_bounds__(128) heads_dpre_kernel(const float* __restrict__ d_out, const float* __restrict__ out,
                                                          int ld, const __grid_constant__ HeadSpec H,
                                                          const float* __restrict__ zs, float scale, int64_t B,
-                                                         uint8_t* __restrict__ img, uint32_t tile_stride) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per image row (incl. pad rows)
-  const int row = (int)(r & 127);
-  float g[16];
-  const bool valid = r < B;
-  const bool far = valid && zs && zs[r] > kZFar;
+                                                         uint8_t* __restrict__ img, uint32_t tile_stride, int n_tiles) {
+  __shared__ float red_s[4][16];
+  const int row = threadIdx.x;                       // one thread per image row; the block strides over the tiles
+  float sum[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    float v = 0.f;
-    if (valid && H.src[i] >= 0) {
-      const float go = d_out[r * ld + H.src[i]], y = out[r * ld + H.src[i]];
-      if (H.act[i] == 1) v = go * y * (1.f - y);
-      else if (H.act[i] == 2) {
-        const float t = y / scale;
-        v = far ? 0.f : go * scale * (1.f - t * t);
-      } else v = go;
+  for (int i = 0; i < 16; ++i) sum[i] = 0.f;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t r = (int64_t)tile * 128 + row;
+    float g[16];
+    const bool valid = r < B;
+    const bool far = valid && zs && zs[r] > kZFar;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float v = 0.f;
+      if (valid && H.src[i] >= 0) {
+        const float go = d_out[r * ld + H.src[i]], y = out[r * ld + H.src[i]];
+        if (H.act[i] == 1) v = go * y * (1.f - y);
+        else if (H.act[i] == 2) {
+          const float t = y / scale;
+          v = far ? 0.f : go * scale * (1.f - t * t);
+        } else v = go;
+      }
+      g[i] = v;
+      sum[i] += v;
     }
-    g[i] = v;
-  }
-  uint8_t* rowp = img + (r >> 7) * tile_stride + row_off(row);
+    uint8_t* rowp = img + (size_t)tile * tile_stride + row_off(row);
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    uint4 q = make_uint4(0, 0, 0, 0);
-    if (u < 2) q = make_uint4(pack_bf16x2(g[u * 8], g[u * 8 + 1]), pack_bf16x2(g[u * 8 + 2], g[u * 8 + 3]),
-                              pack_bf16x2(g[u * 8 + 4], g[u * 8 + 5]), pack_bf16x2(g[u * 8 + 6], g[u * 8 + 7]));
-    *reinterpret_cast<uint4*>(rowp + (((u ^ row) & 7) << 4)) = q;
+    for (int u = 0; u < 8; ++u) {
+      uint4 q = make_uint4(0, 0, 0, 0);
+      if (u < 2) q = make_uint4(pack_bf16x2(g[u * 8], g[u * 8 + 1]), pack_bf16x2(g[u * 8 + 2], g[u * 8 + 3]),
+                                pack_bf16x2(g[u * 8 + 4], g[u * 8 + 5]), pack_bf16x2(g[u * 8 + 6], g[u * 8 + 7]));
+      *reinterpret_cast<uint4*>(rowp + (((u ^ row) & 7) << 4)) = q;
+    }
   }
-  // bias gradients: warp reduce, one atomic per warp and column
+  // bias gradients: warp reduce, block reduce, ONE atomic per column and block (every block hits the same <= 10 words)
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    if (H.src[i] < 0) continue;      // uniform across the block
-    float s = g[i];
+    float v = sum[i];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0 && H.db[i]) atomicAdd(H.db[i], s);
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red_s[threadIdx.x >> 5][i] = v;
   }
+  __syncthreads();
+  if (threadIdx.x < 16 && H.src[threadIdx.x] >= 0 && H.db[threadIdx.x])
+    atomicAdd(H.db[threadIdx.x], red_s[0][threadIdx.x] + red_s[1][threadIdx.x] + red_s[2][threadIdx.x] + red_s[3][threadIdx.x]);
 }
 
 // The MLP input row of every point (rendering.py:164-173) as bf16 chunk images, one launch: PE(xyz) (63 -> 64 columns),
@@ -1203,8 +1212,9 @@ int nsff_field_backward_tc(const nsff_field_desc* d, const nsff_field_params* p,
             ac = chunk_of(s.A, 1, 0, 3), dp = chunk_of(s.DP, 1, 0, 1);
   int col = 0;
   auto heads = [&](const HeadSpec& H) {
-    heads_dpre_kernel<<<(unsigned)c.n_tiles, 128, 0, st>>>(d_out, out, out_ld, H, pts->zs, d->flow_scale, B, s.DP,
-                                                           kChunkBytes);
+    const int blocks = c.n_tiles < 4 * sm_count() ? c.n_tiles : 4 * sm_count();
+    heads_dpre_kernel<<<(unsigned)blocks, 128, 0, st>>>(d_out, out, out_ld, H, pts->zs, d->flow_scale, B, s.DP,
+                                                        kChunkBytes, c.n_tiles);
     return after_launch();
   };
   float* acc;
