@@ -146,3 +146,12 @@ def test_backward_buffer_sizes_are_host_side_pure_functions():
     assert 0 < lean < full and full - lean >= (10 + 9) * img
     small = NeRF("fine", W=64, encode_transient=True, in_channels_t=48, output_flow=True)
     assert L.nsff_field_bwd_tc_pack_bytes(C.byref(small.field_desc())) == 0      # tcgen05 path: 8 x 256 only
+
+
+def test_tile_image_helpers_refuse_cpu_tensors():
+    """nsff_pl_b200.tile_image wraps CUDA-only kernels: CPU tensors raise like every other entry point (no fallback)."""
+    from nsff_pl_b200 import tile_image as TI
+    with pytest.raises(NotImplementedError):
+        TI.image_from_rows(torch.zeros(4, 64))
+    with pytest.raises(NotImplementedError):
+        TI.pack_weight(torch.zeros(256, 64))
