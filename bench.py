@@ -12,9 +12,10 @@ rank r renders frame index r) followed by ONE all-gather of the packed per-ray p
 `value`  : ray-samples/s with rays/ts already resident in HBM, CUDA-event timed, max over ranks.
 `e2e`    : same metric through the public API from pinned HOST buffers (H2D of rays+ts and D2H of the
            gathered pixels inside the timed region).
-`--impl reference`: the reference's own CPU implementation of this path is Python that cannot travel to the
-GPU box, so this arm times its pinned restatement (oracle/nsff_oracle.py, torch CPU, all host threads) on a
-bounded ray sample of the same workload; rank 0 only.
+`--impl reference`: the reference's own CPU implementation of this path: the UNMODIFIED models/rendering.py +
+models/nerf.py, staged by build() into git-ignored baseline/_ref/ (oracle/ref_loader.py; it travels with the gpurun
+snapshot) and run on torch CPU with the fastest thread count up to os.cpu_count(), on a bounded ray sample of the
+same workload; rank 0 only.  Falls back to the pinned restatement oracle/nsff_oracle.py (kind "port") if not staged.
 """
 import argparse
 import json
@@ -101,63 +102,80 @@ class ClockSampler(threading.Thread):
 
 
 def _cpu_setup(n_rays):
+    """Weights + the first `n_rays` rays of the bench frame, for the CPU arm: the UNMODIFIED reference staged in
+    baseline/_ref (kind "reference") when present, else its pinned restatement oracle/nsff_oracle.py (kind "port")."""
     from parity_util import build_fields, synthetic_rays
-    _, _, specs, enc = build_fields(W=256, seed=0, n_frames=N_FRAMES, device=None)
+    from oracle import ref_loader
+    models, emb, specs, enc = build_fields(W=256, seed=0, n_frames=N_FRAMES, device=None)
     rays, ts = synthetic_rays(IMG_WH[0] * IMG_WH[1], n_frames=N_FRAMES, seed=1, img_wh=IMG_WH, frame=8)
-    return specs, enc, rays[:n_rays].contiguous(), ts[:n_rays].contiguous()
+    rays, ts = rays[:n_rays].contiguous(), ts[:n_rays].contiguous()
+    if os.environ.get("NSFF_BENCH_CPU_KIND", "reference") == "reference" and ref_loader.available():
+        ref = ref_loader.load()
+        rmodels, remb = ref_loader.build_reference_fields(models, emb)
 
-
-def _cpu_render(specs, enc, rays, ts):
+        def render(r, t):
+            return ref.rendering.render_rays(rmodels, remb, r, t, N_FRAMES - 1, **RENDER_KW)
+        return "reference", render, rays, ts
     from oracle import nsff_oracle as O
+
+    def render(r, t):
+        return O.render_rays(specs, enc, r, t, N_FRAMES - 1, **RENDER_KW)
+    return "port", render, rays, ts
+
+
+def _cpu_render(render, rays, ts):
     t0 = time.perf_counter()
     with torch.no_grad():
-        O.render_rays(specs, enc, rays, ts, N_FRAMES - 1, **RENDER_KW)
+        render(rays, ts)
     return time.perf_counter() - t0
 
 
-def pick_cpu_threads(specs, enc, rays, ts):
-    """torch's intra-op pool does not scale to every core for 256-wide GEMMs on a few thousand rows; use the
-    thread count that is fastest on a 256-ray probe (reported as `cores`)."""
+def pick_cpu_threads(render, rays, ts):
+    """torch's intra-op pool does not scale to every core for 256-wide GEMMs on a few thousand rows: sweep the thread
+    count up to os.cpu_count() on a 256-ray probe and keep the fastest (reported as `cores`)."""
     ncpu = os.cpu_count() or 1
-    cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
+    cands = sorted({c for c in (4, 8, 16, 32, 64, 128, ncpu) if c <= ncpu})
     best, best_t = cands[0], float("inf")
     for c in cands:
         torch.set_num_threads(c)
-        _cpu_render(specs, enc, rays[:64], ts[:64])
-        t = _cpu_render(specs, enc, rays[:256], ts[:256])
+        _cpu_render(render, rays[:64], ts[:64])
+        t = _cpu_render(render, rays[:256], ts[:256])
         if t < best_t:
             best, best_t = c, t
     torch.set_num_threads(best)
     return best
 
 
-def cpu_port_throughput(n_rays, reps):
-    """ray-samples/s of the oracle (CPU restatement of the reference path) on `n_rays` rays of the workload."""
-    specs, enc, rays, ts = _cpu_setup(n_rays)
-    cores = pick_cpu_threads(specs, enc, rays, ts)
-    times = [_cpu_render(specs, enc, rays, ts) for _ in range(reps)]
-    return n_rays * N_SAMPLES / min(times), times, cores
+def cpu_throughput(n_rays, reps):
+    """ray-samples/s of the reference's CPU render_rays on `n_rays` rays of the workload."""
+    kind, render, rays, ts = _cpu_setup(n_rays)
+    cores = pick_cpu_threads(render, rays, ts)
+    times = [_cpu_render(render, rays, ts) for _ in range(reps)]
+    return n_rays * N_SAMPLES / min(times), times, cores, kind
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     n_rays = CPU_SAMPLE_RAYS
-    specs, enc, rays, ts = _cpu_setup(n_rays)
-    cores = pick_cpu_threads(specs, enc, rays, ts)
+    kind, render, rays, ts = _cpu_setup(n_rays)
+    cores = pick_cpu_threads(render, rays, ts)
     times = []
     for i in range(args.warmup + args.steps):
-        t = _cpu_render(specs, enc, rays, ts)
+        t = _cpu_render(render, rays, ts)
         if i >= args.warmup:
             times.append(t)
     total = sum(times)
     value = n_rays * N_SAMPLES * args.steps / total
     sample = f"{n_rays} rays x {N_SAMPLES} samples of the 512x288 frame per step (first rows of frame 8)"
+    what = ("unmodified reference models/rendering.py render_rays (staged in baseline/_ref), torch CPU fp32" if kind == "reference"
+            else "oracle/nsff_oracle.py (pinned restatement; baseline/_ref not staged), torch CPU fp32")
     line = {"impl": "reference", "metric": "ray-samples/sec (render_rays fwd)", "value": value, "unit": "ray-samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world),
-            "cpu_baseline": {"value": value, "unit": "ray-samples/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "ray-samples/s", "cores": cores, "kind": kind, "sample": sample,
+                             "what": what, "host_cores": os.cpu_count()},
             "e2e": {"value": value, "unit": "ray-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -515,8 +533,8 @@ def main():
                               "algorithmic_bytes_per_launch": (sum(comp_bytes) / len(comp_bytes)) if comp_bytes else None}
         cpu = None
         if not args.no_cpu_baseline and world >= 1:
-            v, times, cores = cpu_port_throughput(CPU_SAMPLE_RAYS, reps=2)
-            cpu = {"value": v, "unit": "ray-samples/s", "cores": cores, "kind": "port",
+            v, times, cores, kind = cpu_throughput(CPU_SAMPLE_RAYS, reps=2)
+            cpu = {"value": v, "unit": "ray-samples/s", "cores": cores, "kind": kind, "host_cores": os.cpu_count(),
                    "sample": f"{CPU_SAMPLE_RAYS} rays x {N_SAMPLES} samples of the same frame, best of 2 "
                              f"({', '.join(f'{t:.1f}s' for t in times)})"}
         line = {"metric": "ray-samples/sec (render_rays fwd)", "value": value, "unit": "ray-samples/s",
