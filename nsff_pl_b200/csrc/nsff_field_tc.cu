@@ -3,23 +3,38 @@
 //   reference: models/nerf.py:118-213 (NeRF.forward, all call modes) fed by
 //              models/rendering.py:113-120,152-175 (PE(xyz) | PE(dir) | a | t input rows)
 //
-// One persistent CTA per SM walks 128-point tiles.  For each tile the whole layer program of the
-// requested heads (static trunk -> sigma head -> final -> dir layer -> rgb head, then the dynamic
-// trunk -> final -> rgb/sigma/flow heads) runs without the activations ever leaving the SM:
+// One persistent CTA PAIR (cluster of 2 = one TPC, cta_group::2) walks pairs of 128-point tiles.  For each tile the
+// whole layer program of the requested heads (static trunk -> sigma head -> final -> dir layer -> rgb head, then the
+// dynamic trunk -> final -> rgb/sigma/flow heads) runs without the activations ever leaving the SM - and, since
+// round 2, without the hidden activation ever touching SHARED memory either:
 //
-//   smem  A operand : 4 "hidden" chunks (128 rows x 64 bf16, 128B-swizzled, K-major) + 3 "extra"
-//                     chunks written once per tile by the prologue: PE(xyz) (63 -> 64 cols),
-//                     time code (48), PE(dir) (27 -> 32)
-//   smem  B operand : 3-stage ring of weight blocks (N x 64 bf16, same swizzle) streamed from the
-//                     L2-resident field pack with cp.async.bulk + mbarrier complete_tx
-//   TMEM            : two 128x256 fp32 accumulators, alternating per layer
-//   warps 0-7       : prologue (encoding) + epilogue (tcgen05.ld -> bias/act -> bf16 -> swizzled st.shared)
-//   warp  8         : weight producer (one thread)
-//   warp  9         : TMEM owner + tcgen05.mma issuer (one thread)
+//   TMEM (512 columns / CTA): two 256-column regions X, Y.  A layer accumulates D (128 x 256 fp32) into the region that
+//       does not hold its input.  The epilogue drains D with tcgen05.ld, adds the bias, applies ReLU, rounds to bf16 and
+//       writes the rows back IN PLACE with tcgen05.st, packed two per column: K-step j of 64-channel chunk c lands at
+//       column (c>>1)*H + 16 j + (c&1)*8 of the same region (H = 64, or 128 in split mode) - each warp only overwrites
+//       columns it has itself drained.  The next layer reads that image as its A operand straight from tensor memory
+//       (tcgen05.mma, .ts form).  Compared with round 1 (hidden chunks in swizzled shared memory) this removes the
+//       st.shared, the fence.proxy.async (measured 140 cycles per 64-column slice, profiles/r02a_ubench_tmem.txt), the
+//       shared-memory A-operand fetch of every MMA and 64 KB of shared memory.
+//       Heads (N = 16) accumulate into the free upper columns of the region that holds their input; their K-chunks run
+//       last-chunk-first so that "chunk 3 published" proves the whole region has been drained.
+//   split mode (NSFF_TC_SPLIT=1): every 256-wide layer is issued as two N = 128 halves with their own accumulator
+//       columns and barriers, so the epilogue of half 0 runs under the MMAs of half 1 and the first two K-chunks of the
+//       next layer are ready when half 1 completes: no accumulator-drain bubble between layers.
+//   smem  A operand : only the "extra" chunks written once per tile by the prologue: PE(xyz) (63 -> 64 cols), time code
+//                     (48), PE(dir) (27 -> 32) [+ appearance code (48)]  (128 rows x 64 bf16, 128B-swizzled, K-major)
+//   smem  B operand : 10-stage ring of weight pieces ((N/2) x 64 bf16 per CTA) streamed from the L2-resident field pack
+//                     with cp.async.bulk + mbarrier complete_tx
+//   warps 0-15      : prologue (encoding) + epilogue (4 TMEM lane quadrants x 4 column parts)
+//   warp  16        : weight + bias producer (one elected lane)
+//   warp  17        : leader CTA: tcgen05.mma issuer (one elected lane walks a flat, host-built list of K-chunk ops);
+//                     peer CTA: relays "my weight half has landed" to the leader's barriers
 //
-// Layer l+1's MMAs for K-chunk c start as soon as the epilogue of layer l has written hidden chunk c
-// (one mbarrier per chunk), so the tensor pipe only idles for the first 64-column slice of each
-// epilogue; the other accumulator absorbs layer l+1 while layer l is still being drained.
+// Ordering notes.  (1) tcgen05.st -> tcgen05.wait::st -> tcgen05.fence::before_thread_sync -> mbarrier arrive |
+// mbarrier wait -> tcgen05.fence::after_thread_sync -> tcgen05.mma makes the written rows visible to the MMA.
+// (2) A region is overwritten by the accumulator of the layer after next.  Its first MMA may be issued while MMAs of
+// the previous layer that still READ the region are in flight (extras-first K order, split mode): tcgen05.mma
+// instructions of one issuing thread execute in order and read their operands before a later instruction writes.
 #include <cuda_bf16.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -88,19 +103,21 @@ static int build_layout(const nsff_field_desc& d, PackLayout& L) {
     off += (uint32_t)p.nchunks * (uint32_t)n * 128u;
     boff += (uint32_t)n;
   };
-  // extras first so the tensor pipe has work while the previous epilogue is still producing hidden chunk 0
+  // extras first so the tensor pipe has work while the previous epilogue is still producing hidden chunk 0;
+  // head blocks read the hidden chunks LAST FIRST: waiting for chunk 3 proves that every epilogue warp has drained the
+  // whole accumulator, whose upper columns the head's own accumulator reuses (TMEM map in the kernel header)
   add(L_S1, 256, {CH_PE});
   for (int i = L_S2; i <= L_S8; ++i) {
     if (i == L_S5) add(i, 256, {CH_PE, CH_H0, CH_H1, CH_H2, CH_H3});
     else add(i, 256, {CH_H0, CH_H1, CH_H2, CH_H3});
   }
-  add(L_SSIG, 16, {CH_H0, CH_H1, CH_H2, CH_H3});
+  add(L_SSIG, 16, {CH_H3, CH_H2, CH_H1, CH_H0});
   add(L_SFIN, 256, {CH_H0, CH_H1, CH_H2, CH_H3});
   if (d.use_viewdir) {
     if (d.in_a > 0) add(L_SDIR, 256, {CH_DIR, CH_A, CH_H0, CH_H1, CH_H2, CH_H3});
     else add(L_SDIR, 256, {CH_DIR, CH_H0, CH_H1, CH_H2, CH_H3});
   }
-  add(L_SRGB, 16, {CH_H0, CH_H1, CH_H2, CH_H3});
+  add(L_SRGB, 16, {CH_H3, CH_H2, CH_H1, CH_H0});
   if (d.has_transient) {
     add(L_T1, 256, {CH_PE, CH_T});
     for (int i = L_T2; i <= L_T8; ++i) {
@@ -108,7 +125,7 @@ static int build_layout(const nsff_field_desc& d, PackLayout& L) {
       else add(i, 256, {CH_H0, CH_H1, CH_H2, CH_H3});
     }
     add(L_TFIN, 256, {CH_H0, CH_H1, CH_H2, CH_H3});
-    add(L_THEAD, 16, {CH_H0, CH_H1, CH_H2, CH_H3});
+    add(L_THEAD, 16, {CH_H3, CH_H2, CH_H1, CH_H0});
   }
   L.bias_base = off;
   L.n_bias = boff;
@@ -157,45 +174,59 @@ __global__ void pack_kernel(const PackJobs* __restrict__ jobs_dev, uint8_t* __re
 // forward kernel
 // ---------------------------------------------------------------------------------------------
 constexpr int kTileM = 128;
-constexpr int kEpiWarps = 16;        // 4 TMEM lane quadrants x 4 column parts: enough warps per SMSP to hide
-                                     // the TMEM-load / st.shared / proxy-fence latencies of the epilogue
+constexpr int kEpiWarps = 16;        // 4 TMEM lane quadrants x 4 column parts
 constexpr int kThreads = (kEpiWarps + 2) * 32;
 constexpr uint32_t kChunkBytes = 128 * 128;          // 128 rows x 64 bf16
+constexpr uint32_t kStageBytes = 128 * 128;          // (256 / 2) rows x 64 bf16: this CTA's half of a 256-wide block
 constexpr int kBiasSlots = 4;
-constexpr uint32_t kSmemBias = kBiasSlots * 1024;    // fp32 bias rows of the steps in flight
+constexpr uint32_t kSmemBias = kBiasSlots * 1024;    // fp32 bias rows of the sub-steps in flight
 constexpr uint32_t kSmemBar = 512;
-constexpr int kMaxSteps = 24;
-constexpr int kMaxStages = 6;
+constexpr int kMaxStages = 10;
+constexpr int kMaxSubs = 44;                         // sub-steps per tile (main pass, split: 19 x 2 + 3 heads = 41)
+constexpr int kMaxOps = 168;                         // K-chunk ops per tile (main pass, split, appearance: 164)
+constexpr int kAccIds = 5;                           // accumulators with their own full/empty barriers: X.h0 X.h1 Y.h0 Y.h1 head
+constexpr int kHeadAcc = 4;
 
-// kCtas = 1: one CTA per tile, cta_group::1 MMAs (M=128), each CTA streams whole weight blocks.
-// kCtas = 2: CTA pair (cluster of 2, one TPC), cta_group::2 MMAs (M=256 = two tiles): each CTA stages only
-//            its half of every weight block (N/2 rows), so the L2->SM weight stream and the B-operand smem
-//            traffic halve and the ring holds twice as many K-chunks (6 stages of 16 KB).
 // kAppear: one more prologue chunk (the 48-wide NeRF-W appearance code feeding the dir layer), paid for with one
 //          ring stage.
-template <int kCtas, bool kAppear>
+template <bool kAppear>
 struct Cfg {
-  static constexpr int kStages = kCtas == 1 ? (kAppear ? 2 : 3) : (kAppear ? 5 : 6);
-  static constexpr uint32_t kStageBytes = (256 / kCtas) * 128;     // (N/kCtas) rows x 64 bf16
-  static constexpr uint32_t kSmemA = (kAppear ? 8 : 7) * kChunkBytes;   // 4 hidden + PE + T + DIR (+ A)
+  static constexpr int kStages = kAppear ? 9 : 10;
+  static constexpr uint32_t kSmemA = (kAppear ? 4 : 3) * kChunkBytes;   // PE + T + DIR (+ A)
   static constexpr uint32_t kSmemB = kStages * kStageBytes;
   static constexpr uint32_t kSmemTotal = kSmemA + kSmemB + kSmemBias + kSmemBar + 1024;   // + alignment slack
 };
 
-struct Step {
-  uint32_t w_off;
-  uint32_t bias_off;
-  uint32_t chunk_pack;      // 4 bits per K-chunk: A-operand chunk id      (hot-loop copies of chunk[]/kcnt[])
-  uint32_t kcnt_pack;       // 4 bits per K-chunk: number of K=16 MMAs
-  uint16_t n;
-  uint8_t nchunks;
+enum : uint8_t { OP_TS = 1, OP_FIRST = 2, OP_LAST = 4, OP_ADV_HID = 8 };
+
+// One K-chunk (<= 4 tcgen05.mma of K = 16) of one sub-step: what the producer copies and what the issuer issues.
+struct ChunkOp {
+  uint32_t w_src;      // byte offset in the pack of the leader CTA's rows of this weight piece (peer: + bytes)
+  uint16_t a;          // OP_TS: TMEM column of K-step 0 (+16 per K-step); else smem offset / 16 of the extra chunk
+  uint16_t d_col;      // TMEM column of the accumulator
+  uint16_t bytes;      // weight bytes per CTA = (N / 2) * 128
+  uint8_t n16;         // N / 16
+  uint8_t kcnt;        // K = 16 steps in this chunk (2..4)
+  uint8_t flags;       // OP_*
+  uint8_t wait_hid;    // 1 + hidden-chunk barrier to wait for before issuing (0: none; only the first use in a layer)
+  uint8_t acc_id;
+  uint8_t wait_empty;  // OP_FIRST: bit mask of accumulators that must have been drained
+};
+static_assert(sizeof(ChunkOp) == 16, "ChunkOp is read with one 16-byte constant load");
+
+// One accumulator's worth of work for the epilogue warps (a whole layer, or one N = 128 half of it in split mode).
+struct SubStep {
+  uint32_t bias_off;       // float index of the first bias of this sub-step
+  uint16_t n;              // 256 / 128 (hidden) or 16 (head)
+  uint16_t d_col;          // TMEM column of the accumulator (and of the in-place bf16 image)
+  uint8_t acc_id;
   uint8_t epi;
-  uint8_t chunk[kMaxChunks];
-  uint8_t kcnt[kMaxChunks];
+  uint8_t slice0;          // first 64-column slice (= hidden chunk) this sub-step produces: 0 or 2
+  uint8_t nslices;         // 4, or 2 in split mode; 0 for heads
   int8_t head_dst[16];
   uint8_t head_act[16];
-  uint64_t save_off;        // training mode: byte offset of this layer's activation image in the save buffer (kNoSave: none)
-  uint64_t bits_off;        // ... and of its ReLU bit plane
+  uint64_t save_off;       // training mode: byte offset of this layer's activation image in the save buffer (kNoSave: none)
+  uint64_t bits_off;       // ... and of its ReLU bit plane
 };
 
 struct FwdParams {
@@ -206,17 +237,16 @@ struct FwdParams {
   int32_t x_ld, c_dir, c_t; // embedded-row column offsets
   float* out;
   int32_t out_ld;
-  int32_t n_steps;
+  int32_t n_subs, n_ops;
   int32_t n_tiles;
   int32_t need_t, need_dir, need_a, c_a;
-  int32_t last_extra_step;  // last step whose K-chunks include PE / time code / PE(dir): after its MMAs the three
-                            // prologue chunks are dead and the NEXT tile's prologue can be written early
+  int32_t last_extra_sub;   // last sub-step whose K-chunks include PE / time code / PE(dir): once its accumulator is
+                            // complete the prologue chunks are dead and the NEXT tile's prologue can be written early
   float flow_scale;
   uint8_t* save_base;       // training mode (kSave kernels): activation save buffer, see nsff_field_save.cuh
   unsigned long long* dbg;  // NSFF_TIMELINE builds only: (tag, clock64) event log of CTA 0
-  int32_t exp_flags;        // NSFF_EXPERIMENT builds only: 1 = MMA ignores hidden-chunk readiness (wrong results),
-                            // 2 = MMA ignores accumulator-drained, 4 = MMA ignores weight readiness
-  Step steps[kMaxSteps];
+  SubStep subs[kMaxSubs];
+  ChunkOp ops[kMaxOps];
 };
 
 // Timeline instrumentation (compiled in only with -DNSFF_TIMELINE; see tools/timeline.py).
@@ -238,13 +268,13 @@ constexpr int kDbgPerRole = 8192;
 
 // barrier slots (8 bytes each) inside the barrier region
 enum {
-  BAR_W_FULL = 0,                           // [kMaxStages] weight stage landed (tx; + partner relay in pair mode)
+  BAR_W_FULL = 0,                           // [kMaxStages] weight stage landed (tx + partner relay)
   BAR_W_EMPTY = BAR_W_FULL + kMaxStages,    // [kMaxStages] MMAs that read the stage completed (commit)
-  BAR_HID_FULL = BAR_W_EMPTY + kMaxStages,  // [4]  hidden chunk written (by all CTAs of the group)
+  BAR_HID_FULL = BAR_W_EMPTY + kMaxStages,  // [4]  bf16 hidden chunk written to TMEM (by both CTAs)
   BAR_EXTRA_FULL = BAR_HID_FULL + 4,        // [1]  prologue chunks written
-  BAR_ACC_FULL = BAR_EXTRA_FULL + 1,        // [2]  accumulator complete (commit)
-  BAR_ACC_EMPTY = BAR_ACC_FULL + 2,         // [2]  accumulator drained
-  BAR_BIAS_FULL = BAR_ACC_EMPTY + 2,        // [kBiasSlots]
+  BAR_ACC_FULL = BAR_EXTRA_FULL + 1,        // [kAccIds] accumulator complete (commit)
+  BAR_ACC_EMPTY = BAR_ACC_FULL + kAccIds,   // [kAccIds] accumulator drained
+  BAR_BIAS_FULL = BAR_ACC_EMPTY + kAccIds,  // [kBiasSlots]
   BAR_BIAS_EMPTY = BAR_BIAS_FULL + kBiasSlots,   // [kBiasSlots]
   BAR_COUNT = BAR_BIAS_EMPTY + kBiasSlots
 };
@@ -310,7 +340,7 @@ __device__ __forceinline__ void encode_pe_part(uint32_t chPE, int row, const flo
 // time-code units, part 3 the 4 PE(dir) units.
 __device__ __forceinline__ void encode_tile_row(const FwdParams& P, uint32_t sA, int row, int part, int64_t p,
                                                 bool valid) {
-  const uint32_t chPE = sA + CH_PE * kChunkBytes, chT = sA + CH_T * kChunkBytes, chD = sA + CH_DIR * kChunkBytes;
+  const uint32_t chPE = sA + 0 * kChunkBytes, chT = sA + 1 * kChunkBytes, chD = sA + 2 * kChunkBytes;
   if (P.x_emb == nullptr) {
     const int64_t ray = p / P.pts.S;
     float base[3];
@@ -349,7 +379,7 @@ __device__ __forceinline__ void encode_tile_row(const FwdParams& P, uint32_t sA,
       for (int u = 0; u < 2; ++u) {
         float4 a = __ldg(ap + 2 * u), b = __ldg(ap + 2 * u + 1);
         float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        store_unit(sA + CH_A * kChunkBytes, row, part * 2 + u, v);
+        store_unit(sA + 3 * kChunkBytes, row, part * 2 + u, v);
       }
     }
     if (P.need_dir && part == 3) {
@@ -395,7 +425,7 @@ __device__ __forceinline__ void encode_tile_row(const FwdParams& P, uint32_t sA,
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = xr[P.c_a + (part * 2 + u) * 8 + i];
-        store_unit(sA + CH_A * kChunkBytes, row, part * 2 + u, v);
+        store_unit(sA + 3 * kChunkBytes, row, part * 2 + u, v);
       }
     }
     if (P.need_dir && part == 3) {
@@ -410,42 +440,38 @@ __device__ __forceinline__ void encode_tile_row(const FwdParams& P, uint32_t sA,
   }
 }
 
-template <int kCtas, bool kAppear, bool kSave>
+template <bool kAppear, bool kSave>
 __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid_constant__ FwdParams P) {
-  using C = Cfg<kCtas, kAppear>;
+  using C = Cfg<kAppear>;
   constexpr int kStages = C::kStages;
-  constexpr uint32_t kStageBytes = C::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sA = smem_base;                       // 7 chunks
-  const uint32_t sB = smem_base + C::kSmemA;           // ring
+  const uint32_t sA = smem_base;                       // extra chunks
+  const uint32_t sB = smem_base + C::kSmemA;           // weight ring
   const uint32_t sBias = sB + C::kSmemB;
   const uint32_t sBar = sBias + kSmemBias;
   const uint32_t sTmemPtr = sBar + BAR_COUNT * 8;
   auto bar = [&](int i) { return sBar + (uint32_t)i * 8u; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t cta_rank = kCtas == 2 ? cluster_ctarank() : 0u;
+  const uint32_t cta_rank = cluster_ctarank();
   const bool leader = cta_rank == 0;
-  // barriers the MMA issuer waits on live in the leader CTA; both CTAs of a pair arrive there
-  auto arrive_leader = [&](int i) {
-    if constexpr (kCtas == 1) mbar_arrive(bar(i));
-    else mbar_arrive_cluster(mapa_cluster(bar(i), 0));
-  };
-  const int group = blockIdx.x / kCtas, n_groups = gridDim.x / kCtas;
-  const int n_units = (P.n_tiles + kCtas - 1) / kCtas;       // tiles (1 CTA) or tile pairs (CTA pair)
+  // barriers the MMA issuer waits on live in the leader CTA; both CTAs of the pair arrive there
+  auto arrive_leader = [&](int i) { mbar_arrive_cluster(mapa_cluster(bar(i), 0)); };
+  const int group = blockIdx.x >> 1, n_groups = gridDim.x >> 1;
+  const int n_units = (P.n_tiles + 1) >> 1;            // tile pairs
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
-      // pair mode, leader: own half (producer arrive + tx) AND the partner's relay arrive complete a stage
-      mbar_init(bar(BAR_W_FULL + i), (kCtas == 2 && leader) ? 2 : 1);
+      // leader: own half (producer arrive + tx) AND the partner's relay arrive complete a stage
+      mbar_init(bar(BAR_W_FULL + i), leader ? 2 : 1);
       mbar_init(bar(BAR_W_EMPTY + i), 1);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_HID_FULL + i), kEpiWarps * kCtas);
-    mbar_init(bar(BAR_EXTRA_FULL), kEpiWarps * kCtas);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_HID_FULL + i), kEpiWarps * 2);
+    mbar_init(bar(BAR_EXTRA_FULL), kEpiWarps * 2);
+    for (int i = 0; i < kAccIds; ++i) {
       mbar_init(bar(BAR_ACC_FULL + i), 1);
-      mbar_init(bar(BAR_ACC_EMPTY + i), kEpiWarps * kCtas);
+      mbar_init(bar(BAR_ACC_EMPTY + i), kEpiWarps * 2);
     }
     for (int i = 0; i < kBiasSlots; ++i) {
       mbar_init(bar(BAR_BIAS_FULL + i), 1);
@@ -453,144 +479,131 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
     }
     fence_mbar_init();
   }
-  if (warp == kEpiWarps + 1) {
-    if constexpr (kCtas == 1) tmem_alloc(sTmemPtr, 512);
-    else tmem_alloc_pair(sTmemPtr, 512);
-  }
+  if (warp == kEpiWarps + 1) tmem_alloc_pair(sTmemPtr, 512);
   tc_fence_before_sync();
-  if constexpr (kCtas == 1) __syncthreads();
-  else cluster_sync_all();              // also: the peer's barriers are initialised before any remote arrive
+  cluster_sync_all();              // also: the peer's barriers are initialised before any remote arrive
   tc_fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sTmemPtr));
 
-  const int n_steps = P.n_steps;
+  const int n_subs = P.n_subs, n_ops = P.n_ops;
 
   if (warp == kEpiWarps) {
-    // ===================== weight + bias producer (whole warp walks the program, one elected lane copies) ====
-    uint32_t stage = 0, epar = 1, gstep = 0;       // epar: parity that means "stage is free" (fresh barrier: 1)
+    // ===================== weight + bias producer (whole warp walks the op list, one elected lane copies) ====
+    uint32_t stage = 0, epar = 1, gsub = 0;        // epar: parity that means "stage is free" (fresh barrier: 1)
     NSFF_TL_DECL(0);
     for (int unit = group; unit < n_units; unit += n_groups) {
-      for (int s = 0; s < n_steps; ++s, ++gstep) {
-        const Step& st = P.steps[s];
-        const uint32_t block_bytes = (uint32_t)st.n * 128u;          // whole N x 64 block
-        const uint32_t bytes = block_bytes / kCtas;                  // this CTA's N/kCtas rows
-        {
-          const uint32_t bslot = gstep & (kBiasSlots - 1), buse = gstep / kBiasSlots;
-          mbar_wait(bar(BAR_BIAS_EMPTY + bslot), (buse & 1u) ^ 1u);
+      int sub = 0;
+      for (int i = 0; i < n_ops; ++i) {
+        const ChunkOp op = P.ops[i];
+        if (op.flags & OP_FIRST) {
+          const SubStep& ss = P.subs[sub];
+          const uint32_t bslot = gsub & (kBiasSlots - 1), buse = gsub / kBiasSlots;
+          mbar_wait_sleep(bar(BAR_BIAS_EMPTY + bslot), (buse & 1u) ^ 1u);
           if (elect_one()) {
-            mbar_arrive_expect_tx(bar(BAR_BIAS_FULL + bslot), (uint32_t)st.n * 4u);
-            bulk_g2s(sBias + bslot * 1024u, P.bias + st.bias_off, (uint32_t)st.n * 4u, bar(BAR_BIAS_FULL + bslot));
+            mbar_arrive_expect_tx(bar(BAR_BIAS_FULL + bslot), (uint32_t)ss.n * 4u);
+            bulk_g2s(sBias + bslot * 1024u, P.bias + ss.bias_off, (uint32_t)ss.n * 4u, bar(BAR_BIAS_FULL + bslot));
           }
           __syncwarp();
+          ++sub, ++gsub;
         }
-        const uint8_t* src = P.pack + st.w_off + cta_rank * bytes;
-        const int nchunks = st.nchunks;
-        for (int kc = 0; kc < nchunks; ++kc, src += block_bytes) {
-          mbar_wait(bar(BAR_W_EMPTY + stage), epar);
-          NSFF_TL((gstep << 8) | (kc << 4) | 1);            // producer: stage free, issuing copy
-          if (elect_one()) {
-            mbar_arrive_expect_tx(bar(BAR_W_FULL + stage), bytes);
-            bulk_g2s(sB + stage * kStageBytes, src, bytes, bar(BAR_W_FULL + stage));
-          }
-          if (++stage == (uint32_t)kStages) stage = 0, epar ^= 1u;
+        mbar_wait_sleep(bar(BAR_W_EMPTY + stage), epar);
+        NSFF_TL(((gsub - 1) << 8) | 1);                    // producer: stage free, issuing copy
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar(BAR_W_FULL + stage), op.bytes);
+          bulk_g2s(sB + stage * kStageBytes, P.pack + op.w_src + cta_rank * op.bytes, op.bytes, bar(BAR_W_FULL + stage));
         }
+        if (++stage == (uint32_t)kStages) stage = 0, epar ^= 1u;
       }
     }
   } else if (warp == kEpiWarps + 1) {
     if (leader) {
-      // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
-      // The loop body is the serial critical path of the kernel (one instruction stream feeds the tensor pipe), so it
-      // is kept to a few dozen instructions per K-chunk: running stage/parity counters, per-step packed chunk
-      // tables, both barrier probes issued back to back, descriptors built from precomputed 32-bit halves.
+      // ===================== MMA issuer =====================
+      // One elected lane walks the flat op list (the other 31 park at the reconvergence point).  The loop body is the
+      // serial critical path of the kernel - one instruction stream feeds the tensor pipe, 64 cycles per MMA in split
+      // mode - so everything that can be precomputed lives in the 16-byte op, and the barrier probes of op i+1 are
+      // issued before the MMAs of op i so that their round trip overlaps the issue work.
       const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);          // SBO | version | SWIZZLE_128B
       const uint32_t a_lo0 = ((sA & 0x3FFFFu) >> 4) | (1u << 16);
       const uint32_t b_lo0 = ((sB & 0x3FFFFu) >> 4) | (1u << 16);
       auto desc = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; };
-      // One elected lane runs the whole role (the other 31 park at the reconvergence point): no per-chunk
-      // elect / reconverge, and ptxas knows the tcgen05 operands are uniform.
       if (elect_one()) {
-        uint32_t stage = 0, wpar = 0, gstep = 0, hid_gen = 0, unit_iter = 0;
+        uint32_t stage = 0, wpar = 0, hid_gen = 0, unit_iter = 0, gsub = 0;
+        uint32_t fill_par = 0;             // bit a: (number of fills of accumulator a so far) & 1
         NSFF_TL_DECL(1);
         for (int unit = group; unit < n_units; unit += n_groups, ++unit_iter) {
           mbar_wait(bar(BAR_EXTRA_FULL), unit_iter & 1u);
-          NSFF_TL((gstep << 8) | 15);                          // mma: prologue chunks ready
-          for (int s = 0; s < n_steps; ++s, ++gstep) {
-            const Step& st = P.steps[s];
-            uint32_t chunks = st.chunk_pack, kcnts = st.kcnt_pack;
-            const int nchunks = st.nchunks;
-            const uint32_t slot = gstep & 1u;
-            const uint32_t d_tmem = tmem_base + slot * 256u;
-            const uint32_t idesc = make_idesc_bf16(kTileM * kCtas, st.n);
-            const uint32_t hid_parity = (hid_gen - 1u) & 1u;
-            const uint32_t acc_full_bar = bar(BAR_ACC_FULL + slot);
-            // probes of K-chunk kc+1 are issued before the MMAs of chunk kc so that their round trip to the
-            // barrier unit overlaps the issue work; `*_ok` carry the result into the next iteration
-            uint32_t ch = chunks & 15u;
-#ifdef NSFF_EXPERIMENT
-            const bool x_hid = P.exp_flags & 1, x_acc = P.exp_flags & 2, x_w = P.exp_flags & 4;
-#else
-            constexpr bool x_hid = false, x_acc = false, x_w = false;
-#endif
-            bool hid_ok = x_hid || ch >= 4 || mbar_try_wait(bar(BAR_HID_FULL + ch), hid_parity);
-            bool w_ok = x_w || mbar_try_wait(bar(BAR_W_FULL + stage), wpar);
-            if (!x_acc) mbar_wait(bar(BAR_ACC_EMPTY + slot), ((gstep >> 1) & 1u) ^ 1u);
-            NSFF_TL((gstep << 8) | 14);                        // mma: accumulator slot free
-            for (int kc = 0; kc < nchunks; ++kc) {
-              const uint32_t kcnt = kcnts & 15u;
-              chunks >>= 4;
-              kcnts >>= 4;
-              NSFF_TL((gstep << 8) | (kc << 4) | 2);         // mma: chunk loop top
-              if (!hid_ok) mbar_wait(bar(BAR_HID_FULL + ch), hid_parity);
-              NSFF_TL((gstep << 8) | (kc << 4) | 3);         // mma: A chunk ready
-              if (!w_ok) mbar_wait(bar(BAR_W_FULL + stage), wpar);
-              NSFF_TL((gstep << 8) | (kc << 4) | 4);         // mma: weights ready -> issue
-              const uint32_t a_lo = a_lo0 + ch * (kChunkBytes >> 4);
-              const uint32_t b_lo = b_lo0 + stage * (kStageBytes >> 4);
-              const uint32_t empty_bar = bar(BAR_W_EMPTY + stage);
-              if (++stage == (uint32_t)kStages) stage = 0, wpar ^= 1u;
-              if (kc + 1 < nchunks) {                          // early probes for the next K-chunk
-                ch = chunks & 15u;
-                hid_ok = x_hid || ch >= 4 || mbar_try_wait(bar(BAR_HID_FULL + ch), hid_parity);
-                w_ok = x_w || mbar_try_wait(bar(BAR_W_FULL + stage), wpar);
+          NSFF_TL((gsub << 8) | 15);                           // mma: prologue chunks ready
+          ChunkOp op = P.ops[0];
+          bool hid_ok = op.wait_hid == 0 || mbar_try_wait(bar(BAR_HID_FULL + op.wait_hid - 1), (hid_gen - 1u) & 1u);
+          bool w_ok = mbar_try_wait(bar(BAR_W_FULL + stage), wpar);
+          int kc = 0;
+          for (int i = 0; i < n_ops; ++i) {
+            if (op.flags & OP_FIRST) {
+              kc = 0;
+              uint32_t m = op.wait_empty;
+              while (m) {                                      // accumulators this sub-step overwrites: drained?
+                const int a = __ffs((int)m) - 1;
+                m &= m - 1u;
+                mbar_wait(bar(BAR_ACC_EMPTY + a), ((fill_par >> a) & 1u) ^ 1u);
               }
-              tc_fence_after_sync();
-              const uint32_t acc0 = kc > 0 ? 1u : 0u;
-              // +32 B per K=16 step inside the 128 B swizzle row (descriptor address unit = 16 B)
-              if constexpr (kCtas == 1) {
-                mma_bf16_ss(d_tmem, desc(a_lo), desc(b_lo), idesc, acc0);
-                mma_bf16_ss(d_tmem, desc(a_lo + 2), desc(b_lo + 2), idesc, 1u);
-                if (kcnt > 2) mma_bf16_ss(d_tmem, desc(a_lo + 4), desc(b_lo + 4), idesc, 1u);
-                if (kcnt > 3) mma_bf16_ss(d_tmem, desc(a_lo + 6), desc(b_lo + 6), idesc, 1u);
-                mma_commit(empty_bar);
-                if (kc == nchunks - 1) mma_commit(acc_full_bar);
-              } else {
-                mma_bf16_ss_pair(d_tmem, desc(a_lo), desc(b_lo), idesc, acc0);
-                mma_bf16_ss_pair(d_tmem, desc(a_lo + 2), desc(b_lo + 2), idesc, 1u);
-                if (kcnt > 2) mma_bf16_ss_pair(d_tmem, desc(a_lo + 4), desc(b_lo + 4), idesc, 1u);
-                if (kcnt > 3) mma_bf16_ss_pair(d_tmem, desc(a_lo + 6), desc(b_lo + 6), idesc, 1u);
-                mma_commit_pair_mc(empty_bar, 3);               // frees the stage in BOTH CTAs
-                if (kc == nchunks - 1) mma_commit_pair_mc(acc_full_bar, 3);
-              }
-              NSFF_TL((gstep << 8) | (kc << 4) | 11);        // mma: committed
+              NSFF_TL((gsub << 8) | 14);                       // mma: accumulator free
             }
-            if (st.epi != EPI_HEAD) ++hid_gen;
+            NSFF_TL((gsub << 8) | (kc << 4) | 2);              // mma: chunk loop top
+            if (!hid_ok) mbar_wait(bar(BAR_HID_FULL + op.wait_hid - 1), (hid_gen - 1u) & 1u);
+            NSFF_TL((gsub << 8) | (kc << 4) | 3);              // mma: A chunk ready
+            if (!w_ok) mbar_wait(bar(BAR_W_FULL + stage), wpar);
+            NSFF_TL((gsub << 8) | (kc << 4) | 4);              // mma: weights ready -> issue
+            const ChunkOp cur = op;
+            const uint32_t b_lo = b_lo0 + stage * (kStageBytes >> 4);
+            const uint32_t empty_bar = bar(BAR_W_EMPTY + stage);
+            if (++stage == (uint32_t)kStages) stage = 0, wpar ^= 1u;
+            const uint32_t hid_next = hid_gen + ((cur.flags & OP_ADV_HID) ? 1u : 0u);
+            if (i + 1 < n_ops) {                               // early probes for the next op
+              op = P.ops[i + 1];
+              hid_ok = op.wait_hid == 0 || mbar_try_wait(bar(BAR_HID_FULL + op.wait_hid - 1), (hid_next - 1u) & 1u);
+              w_ok = mbar_try_wait(bar(BAR_W_FULL + stage), wpar);
+            }
+            tc_fence_after_sync();
+            const uint32_t d_tmem = tmem_base + cur.d_col;
+            const uint32_t idesc = make_idesc_bf16(2 * kTileM, (uint32_t)cur.n16 * 16u);
+            const uint32_t acc0 = (cur.flags & OP_FIRST) ? 0u : 1u;
+            const uint32_t kcnt = cur.kcnt;
+            if (cur.flags & OP_TS) {
+              const uint32_t a_t = tmem_base + cur.a;          // 8 columns (16 bf16) per K-step, 16 columns apart
+              mma_bf16_ts_pair(d_tmem, a_t, desc(b_lo), idesc, acc0);
+              mma_bf16_ts_pair(d_tmem, a_t + 16, desc(b_lo + 2), idesc, 1u);
+              if (kcnt > 2) mma_bf16_ts_pair(d_tmem, a_t + 32, desc(b_lo + 4), idesc, 1u);
+              if (kcnt > 3) mma_bf16_ts_pair(d_tmem, a_t + 48, desc(b_lo + 6), idesc, 1u);
+            } else {
+              const uint32_t a_lo = a_lo0 + cur.a;             // +32 B per K-step inside the 128 B swizzle row
+              mma_bf16_ss_pair(d_tmem, desc(a_lo), desc(b_lo), idesc, acc0);
+              mma_bf16_ss_pair(d_tmem, desc(a_lo + 2), desc(b_lo + 2), idesc, 1u);
+              if (kcnt > 2) mma_bf16_ss_pair(d_tmem, desc(a_lo + 4), desc(b_lo + 4), idesc, 1u);
+              if (kcnt > 3) mma_bf16_ss_pair(d_tmem, desc(a_lo + 6), desc(b_lo + 6), idesc, 1u);
+            }
+            mma_commit_pair_mc(empty_bar, 3);                  // frees the stage in BOTH CTAs
+            if (cur.flags & OP_LAST) {
+              mma_commit_pair_mc(bar(BAR_ACC_FULL + cur.acc_id), 3);
+              fill_par ^= 1u << cur.acc_id;
+              ++gsub;
+            }
+            NSFF_TL(((gsub - ((cur.flags & OP_LAST) ? 1u : 0u)) << 8) | (kc << 4) | 11);   // mma: committed
+            hid_gen = hid_next;
+            ++kc;
           }
         }
       }
       __syncwarp();
     } else {
-      // ===================== pair mode, peer CTA: relay "my weight half has landed" to the leader ==============
+      // ===================== peer CTA: relay "my weight half has landed" to the leader ==============
       uint32_t stage = 0, wpar = 0;
       const uint32_t leader_w_full = mapa_cluster(bar(BAR_W_FULL), 0);
       for (int unit = group; unit < n_units; unit += n_groups) {
-        for (int s = 0; s < n_steps; ++s) {
-          const int nchunks = P.steps[s].nchunks;
-          for (int kc = 0; kc < nchunks; ++kc) {
-            mbar_wait(bar(BAR_W_FULL + stage), wpar);
-            if (lane == 0) mbar_arrive_cluster(leader_w_full + stage * 8u);
-            if (++stage == (uint32_t)kStages) stage = 0, wpar ^= 1u;
-          }
+        for (int i = 0; i < n_ops; ++i) {
+          mbar_wait_sleep(bar(BAR_W_FULL + stage), wpar);
+          if (lane == 0) mbar_arrive_cluster(leader_w_full + stage * 8u);
+          if (++stage == (uint32_t)kStages) stage = 0, wpar ^= 1u;
         }
       }
     }
@@ -601,16 +614,17 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
     const uint32_t lane_field = (uint32_t)(q * 32) << 16;
     const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
     const int rsw = row & 7;
-    uint32_t gstep = 0;
+    uint32_t gsub = 0;
+    uint32_t drain_par = 0;                        // bit a: (number of drains of accumulator a so far) & 1
 #ifdef NSFF_TIMELINE
     unsigned long long* tl_ptr = (P.dbg && blockIdx.x == 0 && warp == 0) ? P.dbg + 2 * 2 * kDbgPerRole : nullptr;
     int tl_n = 0;
 #endif
-    // Prologue: encode a tile's inputs into the three extra chunks.  Only the first tile pays for it up front; for
-    // every later tile it is run during the previous tile, right after the last step that reads those chunks
-    // (P.last_extra_step), i.e. hidden behind the remaining layers instead of idling the tensor pipe.
+    // Prologue: encode a tile's inputs into the extra chunks.  Only the first tile pays for it up front; for every
+    // later tile it is run during the previous tile, right after the last sub-step that reads those chunks
+    // (P.last_extra_sub), i.e. hidden behind the remaining layers instead of idling the tensor pipe.
     auto prologue = [&](int unit_) {
-      const int64_t pr = (int64_t)(unit_ * kCtas + (int)cta_rank) * kTileM + row;
+      const int64_t pr = (int64_t)(unit_ * 2 + (int)cta_rank) * kTileM + row;
       const bool ok = pr < P.pts.B;
       encode_tile_row(P, sA, row, part, ok ? pr : P.pts.B - 1, ok);
       fence_proxy_async_smem();
@@ -619,8 +633,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
     };
     if (group < n_units) prologue(group);
     for (int unit = group; unit < n_units; unit += n_groups) {
-      NSFF_TL((gstep << 8) | 13);                            // epi: tile start
-      const int tile = unit * kCtas + (int)cta_rank;
+      NSFF_TL((gsub << 8) | 13);                             // epi: tile start
+      const int tile = unit * 2 + (int)cta_rank;
       const int64_t p_raw = (int64_t)tile * kTileM + row;
       const bool valid = p_raw < P.pts.B;
       const int64_t p = valid ? p_raw : P.pts.B - 1;
@@ -628,153 +642,160 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
       float zrow = 0.f;
       if (P.pts.zs && P.x_emb == nullptr) zrow = P.pts.zs[p];
 
-      // ---------------- epilogues, one per step ----------------
-      for (int s = 0; s < n_steps; ++s, ++gstep) {
-        const Step& st = P.steps[s];
-        const uint32_t slot = gstep & 1u, use = gstep >> 1;
-        const uint32_t bslot = gstep & (kBiasSlots - 1);
-        mbar_wait(bar(BAR_BIAS_FULL + bslot), (gstep / kBiasSlots) & 1u);   // landed long ago: issued a step ahead
+      // ---------------- epilogues, one per sub-step ----------------
+      for (int s = 0; s < n_subs; ++s, ++gsub) {
+        const SubStep& ss = P.subs[s];
+        const uint32_t acc = ss.acc_id;
+        const uint32_t bslot = gsub & (kBiasSlots - 1);
+        mbar_wait(bar(BAR_BIAS_FULL + bslot), (gsub / kBiasSlots) & 1u);   // landed long ago: issued a sub-step ahead
         const uint32_t s_bias = sBias + bslot * 1024u;
-        const uint32_t t_acc = tmem_base + lane_field + slot * 256u;
-        if (st.epi != EPI_HEAD) {
+        const uint32_t t_acc = tmem_base + lane_field + ss.d_col;
+        if (ss.epi != EPI_HEAD) {
           // bias of the first slice is fetched before the accumulator is awaited: it is off the critical path
           float4 b[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) lds_v4(s_bias + (uint32_t)((part * 16 + i * 4) * 4), b[i]);
-          NSFF_TL((gstep << 8) | 5);                           // epi: waiting for the accumulator
-          mbar_wait(bar(BAR_ACC_FULL + slot), use & 1u);
-          NSFF_TL((gstep << 8) | 6);                           // epi: accumulator complete
+          NSFF_TL((gsub << 8) | 5);                            // epi: waiting for the accumulator
+          mbar_wait(bar(BAR_ACC_FULL + acc), (drain_par >> acc) & 1u);
+          NSFF_TL((gsub << 8) | 6);                            // epi: accumulator complete
           tc_fence_after_sync();
-          const bool relu = st.epi == EPI_RELU_HID;
-          // software pipeline over the four 64-column slices: TMEM load of slice c+1 is in flight while slice c
-          // is biased / activated / packed / stored.
+          const bool relu = ss.epi == EPI_RELU_HID;
+          const int nsl = ss.nslices;
+          // software pipeline over the 64-column slices: TMEM load of slice c+1 is in flight while slice c is biased /
+          // activated / packed / written back to TMEM as the next layer's A operand.
           uint32_t v[2][16];
           tmem_ld16(t_acc + (uint32_t)(part * 16), v[0]);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            tmem_ld_wait();
-            if (c < 3) {
-              tmem_ld16(t_acc + (uint32_t)((c + 1) * 64 + part * 16), v[(c + 1) & 1]);
-            } else {
-              // accumulator fully drained into registers: hand the TMEM slot back to the MMA warp
+            if (c < nsl) {
+              tmem_ld_wait();
+              if (c + 1 < nsl) {
+                tmem_ld16(t_acc + (uint32_t)((c + 1) * 64 + part * 16), v[(c + 1) & 1]);
+              } else {
+                // accumulator fully drained into registers: its columns may be overwritten by the layer after next
+                // (which cannot start before the bf16 image written below has been published and consumed)
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) arrive_leader(BAR_ACC_EMPTY + acc);
+              }
+              uint32_t w[8];
+              uint32_t pos16 = 0;
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 bb = b[u * 2 + (i >> 2)];
+                  const float bv = (i & 3) == 0 ? bb.x : (i & 3) == 1 ? bb.y : (i & 3) == 2 ? bb.z : bb.w;
+                  f[i] = __uint_as_float(v[c & 1][u * 8 + i]) + bv;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  w[u * 4 + i] = relu ? pack_bf16x2_relu(f[2 * i], f[2 * i + 1]) : pack_bf16x2(f[2 * i], f[2 * i + 1]);
+                if constexpr (kSave) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) pos16 |= (f[i] > 0.f ? 1u : 0u) << (u * 8 + i);
+                }
+              }
+              // K-step `part` of hidden chunk slice0+c: 16 bf16 = 8 columns, in place (columns this warp has drained)
+              tmem_st8(t_acc + (uint32_t)(((c >> 1) << 6) + ((c & 1) << 3) + part * 16), w[0], w[1], w[2], w[3], w[4],
+                       w[5], w[6], w[7]);
+              tmem_st_wait();
               tc_fence_before_sync();
               __syncwarp();
-              if (lane == 0) arrive_leader(BAR_ACC_EMPTY + slot);
-            }
-            const uint32_t row_base = sA + (uint32_t)c * kChunkBytes + row_off;
-            uint4 kept[2];
-            uint32_t pos16 = 0;
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              float f[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 bb = b[u * 2 + (i >> 2)];
-                const float bv = (i & 3) == 0 ? bb.x : (i & 3) == 1 ? bb.y : (i & 3) == 2 ? bb.z : bb.w;
-                f[i] = __uint_as_float(v[c & 1][u * 8 + i]) + bv;
-              }
+              if (lane == 0) arrive_leader(BAR_HID_FULL + ss.slice0 + c);
               if constexpr (kSave) {
-                const uint4 w = relu ? make_uint4(pack_bf16x2_relu(f[0], f[1]), pack_bf16x2_relu(f[2], f[3]),
-                                                  pack_bf16x2_relu(f[4], f[5]), pack_bf16x2_relu(f[6], f[7]))
-                                     : make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                                  pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-                st_shared_v4(row_base + (uint32_t)((((part * 2 + u) ^ rsw) & 7) << 4), w.x, w.y, w.z, w.w);
-                kept[u] = w;
+                // training mode: the bf16 rows just published are also the backward's tile image (128B-swizzled chunk
+                // [tile][chunk][128 rows x 128 B]); this warp owns one aligned 32-byte sector of its row
+                if (ss.save_off != kNoSave && tile < P.n_tiles) {
+                  const int cg = ss.slice0 + c;
+                  uint8_t* g = P.save_base + ss.save_off + (size_t)tile * kSaveImgPerTile + (size_t)cg * kChunkBytes +
+                               (row_off);
+                  const bool swap = rsw & 1;
+                  const uint4 lo = make_uint4(w[0], w[1], w[2], w[3]), hi = make_uint4(w[4], w[5], w[6], w[7]);
+                  st_global_v8(g + ((((part * 2) ^ rsw) & 6) << 4), swap ? hi : lo, swap ? lo : hi);
+                  if (relu)
+                    *reinterpret_cast<uint16_t*>(P.save_base + ss.bits_off + (size_t)tile * kSaveBitsPerTile +
+                                                 ((size_t)(2 * cg + (part >> 1)) * 128 + row) * 4 + (part & 1) * 2) =
+                        (uint16_t)pos16;
+                }
+              }
+              NSFF_TL((gsub << 8) | (c << 4) | 7);             // epi: hidden chunk published
+              if (c + 1 < nsl) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) pos16 |= (f[i] > 0.f ? 1u : 0u) << (u * 8 + i);
+                for (int i = 0; i < 4; ++i) lds_v4(s_bias + (uint32_t)(((c + 1) * 64 + part * 16 + i * 4) * 4), b[i]);
               } else {
-                if (relu) store_unit_at<true>(row_base, rsw, part * 2 + u, f);
-                else store_unit_at<false>(row_base, rsw, part * 2 + u, f);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(BAR_BIAS_EMPTY + bslot));      // bias row fully consumed
               }
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) arrive_leader(BAR_HID_FULL + c);
-            if constexpr (kSave) {
-              // training mode: the hidden chunk just published to shared memory is also the backward's tile image;
-              // copy it (and the ReLU bits) to the save buffer after the arrive, off the MMA's critical path
-              if (st.save_off != kNoSave && tile < P.n_tiles) {
-                uint8_t* g = P.save_base + st.save_off + (size_t)tile * kSaveImgPerTile + (size_t)c * kChunkBytes +
-                             (row_off);
-                // the warp's two 16-byte units of this row are one aligned 32-byte sector (swizzle only swaps them)
-                const bool swap = rsw & 1;
-                st_global_v8(g + ((((part * 2) ^ rsw) & 6) << 4), swap ? kept[1] : kept[0], swap ? kept[0] : kept[1]);
-                if (relu)
-                  *reinterpret_cast<uint16_t*>(P.save_base + st.bits_off + (size_t)tile * kSaveBitsPerTile +
-                                               ((size_t)(2 * c + (part >> 1)) * 128 + row) * 4 + (part & 1) * 2) =
-                      (uint16_t)pos16;
-              }
-            }
-            NSFF_TL((gstep << 8) | (c << 4) | 7);            // epi: hidden chunk c published
-            if (c < 3) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) lds_v4(s_bias + (uint32_t)(((c + 1) * 64 + part * 16 + i * 4) * 4), b[i]);
-            } else {
-              __syncwarp();
-              if (lane == 0) mbar_arrive(bar(BAR_BIAS_EMPTY + bslot));      // bias row fully consumed
             }
           }
         } else {
-          mbar_wait(bar(BAR_ACC_FULL + slot), use & 1u);
+          mbar_wait(bar(BAR_ACC_FULL + acc), (drain_par >> acc) & 1u);
           tc_fence_after_sync();
+          uint32_t v[16];
+          float hb[16];
           if (part == 0) {
-            uint32_t v[16];
             tmem_ld16(t_acc, v);
-            tmem_ld_wait();
-            if (valid) {
-              float* orow = P.out + p * P.out_ld;
 #pragma unroll
-              float fl[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // flow fw / bw = head columns 4..9 of the dynamic block
-              bool has_flow = false;
-              for (int i = 0; i < 16; ++i) {
-                const int dst = st.head_dst[i];
-                if (dst < 0) continue;
-                float bi;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(bi) : "r"(s_bias + (uint32_t)(i * 4)));
-                float x = __uint_as_float(v[i]) + bi;
-                const int act = st.head_act[i];
-                if (act == HA_SIGMOID) x = sigmoid_f(x);
-                else if (act == HA_FLOW) {
-                  x = (zrow > kZFar) ? 0.f : P.flow_scale * tanhf(x);
-                  if (i >= 4 && i < 10) fl[i - 4] = x, has_flow = true;
-                }
-                orow[dst] = x;
-              }
-              // points of the warped passes, written here so those passes do not gather 12 B out of every output row
-              if (has_flow && P.x_emb == nullptr && P.pts.offset == nullptr) {
-                const float* x3 = P.pts.xyz + p * 3;
-                if (P.pts.xyz_fw_out) {
-#pragma unroll
-                  for (int c = 0; c < 3; ++c) P.pts.xyz_fw_out[p * 3 + c] = __fadd_rn(x3[c], fl[c]);
-                }
-                if (P.pts.xyz_bw_out) {
-#pragma unroll
-                  for (int c = 0; c < 3; ++c) P.pts.xyz_bw_out[p * 3 + c] = __fadd_rn(x3[c], fl[3 + c]);
-                }
-              }
+            for (int i = 0; i < 4; ++i) {
+              float4 t4;
+              lds_v4(s_bias + (uint32_t)(i * 16), t4);
+              hb[4 * i] = t4.x, hb[4 * i + 1] = t4.y, hb[4 * i + 2] = t4.z, hb[4 * i + 3] = t4.w;
             }
+            tmem_ld_wait();
           }
+          // accumulator and bias row are in registers: hand both back before the activations / global stores
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) {
-            arrive_leader(BAR_ACC_EMPTY + slot);
+            arrive_leader(BAR_ACC_EMPTY + acc);
             mbar_arrive(bar(BAR_BIAS_EMPTY + bslot));
           }
+          if (part == 0 && valid) {
+            float* orow = P.out + p * P.out_ld;
+            float fl[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // flow fw / bw = head columns 4..9 of the dynamic block
+            bool has_flow = false;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int dst = ss.head_dst[i];
+              if (dst < 0) continue;
+              float x = __uint_as_float(v[i]) + hb[i];
+              const int act = ss.head_act[i];
+              if (act == HA_SIGMOID) x = sigmoid_f(x);
+              else if (act == HA_FLOW) {
+                x = (zrow > kZFar) ? 0.f : P.flow_scale * tanhf(x);
+                if (i >= 4 && i < 10) fl[i - 4] = x, has_flow = true;
+              }
+              orow[dst] = x;
+            }
+            // points of the warped passes, written here so those passes do not gather 12 B out of every output row
+            if (has_flow && P.x_emb == nullptr && P.pts.offset == nullptr) {
+              const float* x3 = P.pts.xyz + p * 3;
+              if (P.pts.xyz_fw_out) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) P.pts.xyz_fw_out[p * 3 + c] = __fadd_rn(x3[c], fl[c]);
+              }
+              if (P.pts.xyz_bw_out) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) P.pts.xyz_bw_out[p * 3 + c] = __fadd_rn(x3[c], fl[3 + c]);
+              }
+            }
+          }
         }
-        // this step's accumulator was complete => every MMA up to and including it has finished reading smem
-        if (s == P.last_extra_step && unit + n_groups < n_units) prologue(unit + n_groups);
+        drain_par ^= 1u << acc;
+        // this sub-step's accumulator was complete => every MMA up to and including it has finished reading smem
+        if (s == P.last_extra_sub && unit + n_groups < n_units) prologue(unit + n_groups);
       }
     }
   }
 
   tc_fence_before_sync();
-  if constexpr (kCtas == 1) __syncthreads();
-  else cluster_sync_all();              // no CTA of the pair may exit while its partner can still signal it
+  cluster_sync_all();              // no CTA of the pair may exit while its partner can still signal it
   if (warp == kEpiWarps + 1) {
     tc_fence_after_sync();
     __syncwarp();
-    if constexpr (kCtas == 1) tmem_dealloc(tmem_base, 512);
-    else tmem_dealloc_pair(tmem_base, 512);
+    tmem_dealloc_pair(tmem_base, 512);
   }
 }
 
@@ -839,7 +860,7 @@ extern "C" int nsff_field_pack(const nsff_field_desc* desc, const nsff_field_par
     if (i == 4) trunk_layer(L_S1 + i, prm->static_w[i], prm->static_b[i], 319, 63, 1, pre_pe);
     else trunk_layer(L_S1 + i, prm->static_w[i], prm->static_b[i], 256, 0, 0, nullptr);
   }
-  for (int h = 0; h < 4; ++h) wjob(L_SSIG, h, prm->static_sigma_w, 256, 0, 1, h * 64, 64);
+  for (int h = 0; h < 4; ++h) wjob(L_SSIG, 3 - h, prm->static_sigma_w, 256, 0, 1, h * 64, 64);   // K-chunk order H3..H0
   bjob(L_SSIG, 0, prm->static_sigma_b, 1);
   trunk_layer(L_SFIN, prm->static_final_w, prm->static_final_b, 256, 0, 0, nullptr);
   const int pre_dir_a[2][2] = {{256, 27}, {283, 48}};
@@ -847,7 +868,7 @@ extern "C" int nsff_field_pack(const nsff_field_desc* desc, const nsff_field_par
     if (desc->in_a > 0) trunk_layer(L_SDIR, prm->static_dir_w, prm->static_dir_b, 283 + 48, 0, 2, pre_dir_a);
     else trunk_layer(L_SDIR, prm->static_dir_w, prm->static_dir_b, 283, 0, 1, pre_dir);
   }
-  for (int h = 0; h < 4; ++h) wjob(L_SRGB, h, prm->static_rgb_w, 256, 0, 3, h * 64, 64);
+  for (int h = 0; h < 4; ++h) wjob(L_SRGB, 3 - h, prm->static_rgb_w, 256, 0, 3, h * 64, 64);
   bjob(L_SRGB, 0, prm->static_rgb_b, 3);
   if (desc->has_transient) {   // nerf.py:93-116
     trunk_layer(L_T1, prm->trans_w[0], prm->trans_b[0], 111, -1, 2, pre_pe_t);
@@ -858,11 +879,11 @@ extern "C" int nsff_field_pack(const nsff_field_desc* desc, const nsff_field_par
     trunk_layer(L_TFIN, prm->trans_final_w, prm->trans_final_b, 256, 0, 0, nullptr);
     // head block rows: 0-2 rgb, 3 sigma, 4-6 flow fw, 7-9 flow bw
     for (int h = 0; h < 4; ++h) {
-      wjob(L_THEAD, h, prm->trans_rgb_w, 256, 0, 3, h * 64, 64);
-      wjob(L_THEAD, h, prm->trans_sigma_w, 256, 3, 1, h * 64, 64);
+      wjob(L_THEAD, 3 - h, prm->trans_rgb_w, 256, 0, 3, h * 64, 64);
+      wjob(L_THEAD, 3 - h, prm->trans_sigma_w, 256, 3, 1, h * 64, 64);
       if (desc->has_flow) {
-        wjob(L_THEAD, h, prm->trans_fw_w, 256, 4, 3, h * 64, 64);
-        wjob(L_THEAD, h, prm->trans_bw_w, 256, 7, 3, h * 64, 64);
+        wjob(L_THEAD, 3 - h, prm->trans_fw_w, 256, 4, 3, h * 64, 64);
+        wjob(L_THEAD, 3 - h, prm->trans_bw_w, 256, 7, 3, h * 64, 64);
       }
     }
     bjob(L_THEAD, 0, prm->trans_rgb_b, 3);
@@ -883,38 +904,92 @@ extern "C" int nsff_field_pack(const nsff_field_desc* desc, const nsff_field_par
   return after_launch();
 }
 
-static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_mask, FwdParams& P, int* n_out_cols,
-                         const SaveLayout* SL) {
+// Builds the per-tile program: the sub-step table the epilogue warps walk and the flat K-chunk op list the producer
+// and the MMA issuer walk.  `split`: every 256-wide layer becomes two N = 128 sub-steps (see the file header).
+static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_mask, bool split, FwdParams& P,
+                         int* n_out_cols, const SaveLayout* SL) {
   const bool sigma_only = out_mask & NSFF_OUT_SIGMA_ONLY;
   const bool want_s = out_mask & NSFF_OUT_STATIC, want_t = out_mask & NSFF_OUT_TRANSIENT;
   const bool want_fw = out_mask & NSFF_OUT_FLOW_FW, want_bw = out_mask & NSFF_OUT_FLOW_BW;
   if (!want_s && !want_t) return NSFF_EINVAL;
   if (want_t && !d.has_transient) return NSFF_EINVAL;
   if ((want_fw || want_bw) && (!want_t || !d.has_flow || sigma_only)) return NSFF_EINVAL;
-  int n = 0, col = 0;
-  auto push = [&](int lid, uint8_t epi) -> Step& {
+  int n_subs = 0, n_ops = 0, col = 0;
+  int cur = -1;                        // region (0 = X, 1 = Y) that holds the current hidden activation; -1: none yet
+  bool overflow = false;
+  P.last_extra_sub = 0;
+  const uint32_t half_cols = split ? 128u : 64u;     // TMEM columns between the bf16 images of channels 0-127 / 128-255
+  auto push = [&](int lid, uint8_t epi) -> SubStep* {
     const PackLayer& pl = L.layer[lid];
-    Step& s = P.steps[n++];
-    s.w_off = pl.w_off;
-    s.bias_off = pl.bias_off;
-    s.n = (uint16_t)pl.n;
-    s.nchunks = (uint8_t)pl.nchunks;
-    s.epi = epi;
-    s.chunk_pack = s.kcnt_pack = 0;
-    for (int i = 0; i < kMaxChunks; ++i) {
-      s.chunk[i] = pl.chunk[i], s.kcnt[i] = pl.kcnt[i];
-      if (i < pl.nchunks) s.chunk_pack |= (uint32_t)pl.chunk[i] << (4 * i), s.kcnt_pack |= (uint32_t)pl.kcnt[i] << (4 * i);
+    const bool head = epi == EPI_HEAD;
+    const int parts = (!head && split) ? 2 : 1;
+    const int region = head ? cur : (cur < 0 ? 0 : 1 - cur);
+    if (head && cur < 0) { overflow = true; return nullptr; }
+    SubStep* first = nullptr;
+    for (int h = 0; h < parts; ++h) {
+      if (n_subs >= kMaxSubs) { overflow = true; return nullptr; }
+      SubStep& s = P.subs[n_subs];
+      if (!first) first = &s;
+      const int n = head ? pl.n : pl.n / parts;
+      s.bias_off = pl.bias_off + (uint32_t)(h * n);
+      s.n = (uint16_t)n;
+      s.epi = epi;
+      if (head) {
+        // free columns of the region that holds the input: above the two in-place bf16 images
+        s.d_col = (uint16_t)(region * 256 + (split ? 64 : 128));
+        s.acc_id = kHeadAcc;
+        s.slice0 = 0, s.nslices = 0;
+      } else {
+        s.d_col = (uint16_t)(region * 256 + h * 128);
+        s.acc_id = (uint8_t)(region * 2 + h);
+        s.slice0 = (uint8_t)(2 * h);
+        s.nslices = (uint8_t)(4 / parts);
+      }
+      for (int i = 0; i < 16; ++i) s.head_dst[i] = -1, s.head_act[i] = HA_NONE;
+      s.save_off = s.bits_off = kNoSave;
+      if (SL) {
+        if (lid >= L_S1 && lid <= L_S8) s.save_off = SL->s_h[lid - L_S1], s.bits_off = SL->s_hb[lid - L_S1];
+        else if (lid == L_SFIN) s.save_off = SL->s_feat;
+        else if (lid == L_SDIR) s.save_off = SL->s_dir, s.bits_off = SL->s_dirb;
+        else if (lid >= L_T1 && lid <= L_T8) s.save_off = SL->t_h[lid - L_T1], s.bits_off = SL->t_hb[lid - L_T1];
+        else if (lid == L_TFIN) s.save_off = SL->t_feat;
+      }
+      for (int kc = 0; kc < pl.nchunks; ++kc) {
+        if (n_ops >= kMaxOps) { overflow = true; return nullptr; }
+        ChunkOp& o = P.ops[n_ops++];
+        const int ch = pl.chunk[kc];
+        const uint32_t block_bytes = (uint32_t)pl.n * 128u;              // whole N x 64 block of this K-chunk
+        o.bytes = (uint16_t)((uint32_t)n * 128u / 2u);                   // this CTA's N/2 rows
+        o.w_src = pl.w_off + (uint32_t)kc * block_bytes + (uint32_t)h * (uint32_t)n * 128u;
+        o.d_col = s.d_col;
+        o.n16 = (uint8_t)(n / 16);
+        o.kcnt = pl.kcnt[kc];
+        o.acc_id = s.acc_id;
+        o.flags = 0;
+        o.wait_hid = 0;
+        o.wait_empty = 0;
+        if (ch < CH_PE) {
+          if (cur < 0) { overflow = true; return nullptr; }
+          o.flags |= OP_TS;
+          o.a = (uint16_t)(cur * 256 + (ch >> 1) * (int)half_cols + (ch & 1) * 8);
+          if (h == 0) o.wait_hid = (uint8_t)(1 + ch);                    // later uses in the same layer: already awaited
+        } else {
+          o.a = (uint16_t)((ch - CH_PE) * (int)(kChunkBytes >> 4));
+          P.last_extra_sub = n_subs;
+        }
+        if (kc == 0) {
+          o.flags |= OP_FIRST;
+          o.wait_empty = (uint8_t)((1u << s.acc_id) | (1u << kHeadAcc));
+        }
+        if (kc == pl.nchunks - 1) {
+          o.flags |= OP_LAST;
+          if (!head && h == parts - 1) o.flags |= OP_ADV_HID;
+        }
+      }
+      ++n_subs;
     }
-    for (int i = 0; i < 16; ++i) s.head_dst[i] = -1, s.head_act[i] = HA_NONE;
-    s.save_off = s.bits_off = kNoSave;
-    if (SL) {
-      if (lid >= L_S1 && lid <= L_S8) s.save_off = SL->s_h[lid - L_S1], s.bits_off = SL->s_hb[lid - L_S1];
-      else if (lid == L_SFIN) s.save_off = SL->s_feat;
-      else if (lid == L_SDIR) s.save_off = SL->s_dir, s.bits_off = SL->s_dirb;
-      else if (lid >= L_T1 && lid <= L_T8) s.save_off = SL->t_h[lid - L_T1], s.bits_off = SL->t_hb[lid - L_T1];
-      else if (lid == L_TFIN) s.save_off = SL->t_feat;
-    }
-    return s;
+    if (!head) cur = region;
+    return first;
   };
   P.need_dir = 0;
   P.need_t = 0;
@@ -922,20 +997,21 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
   if (want_s) {
     for (int i = L_S1; i <= L_S8; ++i) push(i, EPI_RELU_HID);
     if (sigma_only) {
-      Step& s = push(L_SSIG, EPI_HEAD);
-      s.head_dst[0] = (int8_t)col;
+      SubStep* s = push(L_SSIG, EPI_HEAD);
+      if (s) s->head_dst[0] = (int8_t)col;
       col += 1;
     } else {
-      Step& sg = push(L_SSIG, EPI_HEAD);
-      sg.head_dst[0] = (int8_t)(col + 3);
+      SubStep* sg = push(L_SSIG, EPI_HEAD);
+      if (sg) sg->head_dst[0] = (int8_t)(col + 3);
       push(L_SFIN, EPI_LIN_HID);
       if (d.use_viewdir) {
         push(L_SDIR, EPI_RELU_HID);
         P.need_dir = 1;
         P.need_a = d.in_a > 0;
       }
-      Step& rg = push(L_SRGB, EPI_HEAD);
-      for (int i = 0; i < 3; ++i) rg.head_dst[i] = (int8_t)(col + i), rg.head_act[i] = HA_SIGMOID;
+      SubStep* rg = push(L_SRGB, EPI_HEAD);
+      if (rg)
+        for (int i = 0; i < 3; ++i) rg->head_dst[i] = (int8_t)(col + i), rg->head_act[i] = HA_SIGMOID;
       col += 4;
     }
   }
@@ -943,32 +1019,36 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
     P.need_t = 1;
     for (int i = L_T1; i <= L_T8; ++i) push(i, EPI_RELU_HID);
     push(L_TFIN, EPI_LIN_HID);
-    Step& h = push(L_THEAD, EPI_HEAD);
-    if (sigma_only) {
-      h.head_dst[3] = (int8_t)col;
-      col += 1;
-    } else {
-      for (int i = 0; i < 3; ++i) h.head_dst[i] = (int8_t)(col + i), h.head_act[i] = HA_SIGMOID;
-      h.head_dst[3] = (int8_t)(col + 3);
-      col += 4;
-      if (want_fw) {
-        for (int i = 0; i < 3; ++i) h.head_dst[4 + i] = (int8_t)(col + i), h.head_act[4 + i] = HA_FLOW;
-        col += 3;
-      }
-      if (want_bw) {
-        for (int i = 0; i < 3; ++i) h.head_dst[7 + i] = (int8_t)(col + i), h.head_act[7 + i] = HA_FLOW;
-        col += 3;
+    SubStep* h = push(L_THEAD, EPI_HEAD);
+    if (h) {
+      if (sigma_only) {
+        h->head_dst[3] = (int8_t)col;
+        col += 1;
+      } else {
+        for (int i = 0; i < 3; ++i) h->head_dst[i] = (int8_t)(col + i), h->head_act[i] = HA_SIGMOID;
+        h->head_dst[3] = (int8_t)(col + 3);
+        col += 4;
+        if (want_fw) {
+          for (int i = 0; i < 3; ++i) h->head_dst[4 + i] = (int8_t)(col + i), h->head_act[4 + i] = HA_FLOW;
+          col += 3;
+        }
+        if (want_bw) {
+          for (int i = 0; i < 3; ++i) h->head_dst[7 + i] = (int8_t)(col + i), h->head_act[7 + i] = HA_FLOW;
+          col += 3;
+        }
       }
     }
   }
-  if (n > kMaxSteps) return NSFF_EUNSUPPORTED;
-  P.n_steps = n;
-  P.last_extra_step = 0;
-  for (int i = 0; i < n; ++i)
-    for (int kc = 0; kc < P.steps[i].nchunks; ++kc)
-      if (P.steps[i].chunk[kc] >= CH_PE) P.last_extra_step = i;
+  if (overflow) return NSFF_EUNSUPPORTED;
+  P.n_subs = n_subs;
+  P.n_ops = n_ops;
   *n_out_cols = col;
   return NSFF_OK;
+}
+
+static bool env_flag(const char* name, bool dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) != 0 : dflt;
 }
 
 static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdParams& P, int out_mask, int64_t B,
@@ -986,7 +1066,8 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
     SL = save_layout(desc, B, out_mask);
     P.save_base = static_cast<uint8_t*>(save);
   }
-  rc = build_program(*desc, L, out_mask, P, &ncols, save ? &SL : nullptr);
+  // NSFF_TC_SPLIT=0 selects whole-layer accumulators (N = 256 MMAs; A/B experiments)
+  rc = build_program(*desc, L, out_mask, env_flag("NSFF_TC_SPLIT", true), P, &ncols, save ? &SL : nullptr);
   if (rc != NSFF_OK) return rc;
   if (out_ld < ncols) return NSFF_EINVAL;
   int dev = 0, major = 0, sms = 0;
@@ -1000,18 +1081,12 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
   P.out_ld = out_ld;
   P.n_tiles = (int)cdiv64(B, kTileM);
   P.flow_scale = desc->flow_scale;
-  // CTA pairs (cta_group::2) are the default; NSFF_TC_CTAS=1 selects the single-CTA kernel (A/B experiments).
-  int ctas = 2;
-  if (const char* e = getenv("NSFF_TC_CTAS")) ctas = atoi(e) == 1 ? 1 : 2;
   int max_ctas = sms;
   if (const char* cap = getenv("NSFF_MAX_CTAS")) {          // experiment knob: fewer resident CTAs
     int c = atoi(cap);
     if (c > 0 && c < max_ctas) max_ctas = c;
   }
   cudaStream_t st = (cudaStream_t)stream;
-#ifdef NSFF_EXPERIMENT
-  if (const char* xf = getenv("NSFF_EXP_FLAGS")) P.exp_flags = atoi(xf);
-#endif
 #ifdef NSFF_TIMELINE
   const char* tl_path = getenv("NSFF_TIMELINE_OUT");
   unsigned long long* tl_dev = nullptr;
@@ -1023,12 +1098,6 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
   }
 #endif
   const bool appear = P.need_a != 0;
-  auto launch_single = [&](auto kern, uint32_t smem) -> int {
-    NSFF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = P.n_tiles < max_ctas ? P.n_tiles : max_ctas;
-    kern<<<grid, kThreads, smem, st>>>(P);
-    return NSFF_OK;
-  };
   auto launch_pair = [&](auto kern, uint32_t smem) -> int {
     NSFF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int n_pairs = (P.n_tiles + 1) / 2;
@@ -1052,19 +1121,11 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
   };
   int lrc;
   if (save) {
-    if (ctas == 1) {
-      lrc = appear ? launch_single(field_forward_kernel<1, true, true>, Cfg<1, true>::kSmemTotal)
-                   : launch_single(field_forward_kernel<1, false, true>, Cfg<1, false>::kSmemTotal);
-    } else {
-      lrc = appear ? launch_pair(field_forward_kernel<2, true, true>, Cfg<2, true>::kSmemTotal)
-                   : launch_pair(field_forward_kernel<2, false, true>, Cfg<2, false>::kSmemTotal);
-    }
-  } else if (ctas == 1) {
-    lrc = appear ? launch_single(field_forward_kernel<1, true, false>, Cfg<1, true>::kSmemTotal)
-                 : launch_single(field_forward_kernel<1, false, false>, Cfg<1, false>::kSmemTotal);
+    lrc = appear ? launch_pair(field_forward_kernel<true, true>, Cfg<true>::kSmemTotal)
+                 : launch_pair(field_forward_kernel<false, true>, Cfg<false>::kSmemTotal);
   } else {
-    lrc = appear ? launch_pair(field_forward_kernel<2, true, false>, Cfg<2, true>::kSmemTotal)
-                 : launch_pair(field_forward_kernel<2, false, false>, Cfg<2, false>::kSmemTotal);
+    lrc = appear ? launch_pair(field_forward_kernel<true, false>, Cfg<true>::kSmemTotal)
+                 : launch_pair(field_forward_kernel<false, false>, Cfg<false>::kSmemTotal);
   }
   if (lrc != NSFF_OK) return lrc;
 #ifdef NSFF_TIMELINE

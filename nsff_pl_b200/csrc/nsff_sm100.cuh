@@ -40,6 +40,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Same for waits that are NOT on the tensor pipe's critical path (producer, relay): the try_wait carries a suspend-time
+// hint so the warp sleeps in hardware until the phase flips, and backs off between polls instead of spinning.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(20000u)
+        : "memory");
+    if (ok) return;
+    __nanosleep(64);
+  }
+}
+
 // Same, with cluster-scope acquire: for barriers that receive arrives from the partner CTA.
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -180,6 +197,37 @@ __device__ __forceinline__ void mma_commit_pair_mc(uint32_t bar, uint16_t cta_ma
       "h"(cta_mask)
       : "memory");
 }
+
+// ---- A operand from TMEM (.ts form): D[tmem] (+)= A[tmem, lanes = rows, 8 columns = 16 bf16 of K] * B[smem]^T ----
+// The hidden activation of a fused MLP stays in tensor memory between layers: the epilogue writes the bf16 rows with
+// tcgen05.st and the next layer's MMAs read them here - no st.shared, no fence.proxy.async, no smem A-operand fetch.
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// CTA pair: each CTA supplies its own 128 rows of A from its own tensor memory (same address in both CTAs)
+__device__ __forceinline__ void mma_bf16_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// registers -> TMEM: thread i of warp w writes lane 32*(w%4)+i, 8 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e,
+                                         uint32_t f, uint32_t g, uint32_t h) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(a),
+               "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- TMEM -> registers: warp w reads lanes 32*(w%4).., thread i gets lane i, N consecutive columns ----
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {

@@ -24,6 +24,6 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["impl"] == "reference" and d["higher_is_better"] is True and d["vs_baseline"] is None
     assert d["metric"].startswith("ray-samples/sec") and d["unit"] == "ray-samples/s" and d["value"] > 0
     assert d["config"]["workload"].startswith("full NSFF") and "BASELINE.json configs[1]" in d["config"]["workload"]
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["gpu_launches"] == 0
