@@ -11,7 +11,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnsff_b200.so")
+# NSFF_LIB: an alternative build of the same library (e.g. the -DNSFF_TIMELINE build of tools/timeline.py)
+LIB_PATH = os.environ.get("NSFF_LIB") or os.path.join(_HERE, "libnsff_b200.so")
 
 OUT_STATIC, OUT_TRANSIENT, OUT_FLOW_FW, OUT_FLOW_BW, OUT_SIGMA_ONLY = 1, 2, 4, 8, 16
 

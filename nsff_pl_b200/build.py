@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libnsff_b200.so")
+LIB = os.environ.get("NSFF_LIB_OUT") or os.path.join(HERE, "libnsff_b200.so")      # NSFF_LIB_OUT: side build (tools/timeline.py)
 STAMP = LIB + ".stamp"
 SOURCES = ["nsff_points.cu", "nsff_composite.cu", "nsff_composite_bwd.cu", "nsff_resample.cu", "nsff_interpolate.cu", "nsff_field_fp32.cu", "nsff_field_tc.cu", "nsff_field_bwd_tc.cu"]
 EXTRA = os.environ.get("NSFF_NVCC_EXTRA", "").split()      # e.g. -DNSFF_TIMELINE for tools/timeline.py
@@ -49,7 +49,7 @@ def build(force=False, verbose=False):
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+        obj = os.path.join(HERE, "build", ("x_" if os.environ.get("NSFF_LIB_OUT") else "") + src.replace(".cu", ".o"))
         cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas")

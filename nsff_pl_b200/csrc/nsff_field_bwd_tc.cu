@@ -195,17 +195,21 @@ struct EmbedImgArgs {
 // sin/cos of one frequency for the three components, written to columns 3+6f .. 3+6f+5 of a 64-wide row buffer
 template <int kNFreq>
 __device__ __forceinline__ void pe_row(const float (&b)[3], float (&row)[64]) {
+  // same evaluation as the forward prologue (nsff_field_tc.cu: one sincosf at octave 0, then the doubling recurrence)
+  float sn[3], cs[3];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) row[c] = b[c];
+  for (int c = 0; c < 3; ++c) {
+    row[c] = b[c];
+    sincosf(b[c], &sn[c], &cs[c]);                 // freqs = 2^linspace(0, N-1, N)  (nerf.py:13)
+  }
 #pragma unroll
   for (int f = 0; f < kNFreq; ++f) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      float sn, cs;
-      sincosf(__fmul_rn(exp2f((float)f), b[c]), &sn, &cs);       // freqs = 2^linspace(0, N-1, N)  (nerf.py:13)
-      row[3 + 6 * f + c] = sn;
-      row[3 + 6 * f + 3 + c] = cs;
+      row[3 + 6 * f + c] = sn[c];
+      row[3 + 6 * f + 3 + c] = cs[c];
     }
+    if (f + 1 < kNFreq) pe_next_octave(sn, cs);
   }
 }
 __global__ void __launch_bounds__(128) embed_img_kernel(const __grid_constant__ EmbedImgArgs E) {

@@ -71,7 +71,6 @@ struct PackLayer {
   int n;               // 256 or 16
   int nchunks;
   uint8_t chunk[kMaxChunks];
-  uint8_t kcnt[kMaxChunks];   // number of K=16 MMAs issued from this chunk
 };
 
 struct PackLayout {
@@ -95,7 +94,6 @@ static int build_layout(const nsff_field_desc& d, PackLayout& L) {
     p.nchunks = 0;
     for (uint8_t c : chunks) {
       p.chunk[p.nchunks] = c;
-      p.kcnt[p.nchunks] = (c == CH_T || c == CH_A) ? 3 : (c == CH_DIR) ? 2 : 4;
       ++p.nchunks;
     }
     p.w_off = off;
@@ -177,57 +175,67 @@ constexpr int kTileM = 128;
 constexpr int kEpiWarps = 16;        // 4 TMEM lane quadrants x 4 column parts
 constexpr int kThreads = (kEpiWarps + 2) * 32;
 constexpr uint32_t kChunkBytes = 128 * 128;          // 128 rows x 64 bf16
-constexpr uint32_t kStageBytes = 128 * 128;          // (256 / 2) rows x 64 bf16: this CTA's half of a 256-wide block
-constexpr int kBiasSlots = 4;
-constexpr uint32_t kSmemBias = kBiasSlots * 1024;    // fp32 bias rows of the sub-steps in flight
+constexpr uint32_t kSmemBias = 20 * 1024;            // the module's whole fp32 bias table (4912 floats), resident
 constexpr uint32_t kSmemBar = 512;
 constexpr int kMaxStages = 10;
 constexpr int kMaxSubs = 44;                         // sub-steps per tile (main pass, split: 19 x 2 + 3 heads = 41)
-constexpr int kMaxOps = 168;                         // K-chunk ops per tile (main pass, split, appearance: 164)
+constexpr int kMaxOps = 96;                          // ops per tile (main pass, split: 84)
 constexpr int kAccIds = 5;                           // accumulators with their own full/empty barriers: X.h0 X.h1 Y.h0 Y.h1 head
 constexpr int kHeadAcc = 4;
 
-// kAppear: one more prologue chunk (the 48-wide NeRF-W appearance code feeding the dir layer), paid for with one
-//          ring stage.
+#ifdef NSFF_TIMELINE
+constexpr uint32_t kSmemDbg = 3 * 512 * 8;    // shared-memory event log (tools/timeline.py)
+#else
+constexpr uint32_t kSmemDbg = 0;
+#endif
+
+// kAppear: one more prologue chunk (the 48-wide NeRF-W appearance code feeding the dir layer), paid for with ring space.
+// The ring is cut into stages of TWO weight pieces (the two K-chunks of one op): 2 x 16 KB per CTA for N = 256 ops
+// 2 x 8 KB per CTA for the N = 128 sub-steps (9 stages; 8 with the appearance chunk).
 template <bool kAppear>
 struct Cfg {
-  static constexpr int kStages = kAppear ? 9 : 10;
   static constexpr uint32_t kSmemA = (kAppear ? 4 : 3) * kChunkBytes;   // PE + T + DIR (+ A)
-  static constexpr uint32_t kSmemB = kStages * kStageBytes;
-  static constexpr uint32_t kSmemTotal = kSmemA + kSmemB + kSmemBias + kSmemBar + 1024;   // + alignment slack
+  static constexpr uint32_t kSmemB = (kAppear ? 8 : 9) * 16384;
+  static constexpr uint32_t kSmemTotal = kSmemA + kSmemB + kSmemBias + kSmemBar + kSmemDbg + 1024;   // + alignment slack
 };
 
-enum : uint8_t { OP_TS = 1, OP_FIRST = 2, OP_LAST = 4, OP_ADV_HID = 8 };
+enum : uint8_t { OP_TS = 1, OP_FIRST = 2, OP_LAST = 4, OP_ADV_HID = 8, OP_TWO = 16 };
 
-// One K-chunk (<= 4 tcgen05.mma of K = 16) of one sub-step: what the producer copies and what the issuer issues.
-struct ChunkOp {
-  uint32_t w_src;      // byte offset in the pack of the leader CTA's rows of this weight piece (peer: + bytes)
-  uint16_t a;          // OP_TS: TMEM column of K-step 0 (+16 per K-step); else smem offset / 16 of the extra chunk
+// One or two K-chunks (4 tcgen05.mma of K = 16 each) of one sub-step: what the issuer issues (first 16 bytes, one
+// constant load) and what the producer copies (second 16 bytes).
+struct alignas(16) ChunkOp {
+  uint32_t idesc;      // instruction descriptor (M = 256, this sub-step's N)
+  uint16_t a;          // OP_TS: TMEM column of K-step 0 of the first chunk (+16 per K-step); else smem offset / 16
+  uint16_t a2;         // same for the second chunk (OP_TWO)
   uint16_t d_col;      // TMEM column of the accumulator
-  uint16_t bytes;      // weight bytes per CTA = (N / 2) * 128
-  uint8_t n16;         // N / 16
-  uint8_t kcnt;        // K = 16 steps in this chunk (2..4)
+  uint16_t b2;         // descriptor units (16 B) between the two chunks' weight pieces inside the stage
   uint8_t flags;       // OP_*
-  uint8_t wait_hid;    // 1 + hidden-chunk barrier to wait for before issuing (0: none; only the first use in a layer)
+  uint8_t wait_hid;    // 1 + hidden-half barrier to wait for before issuing (0: none; only the first use in a layer)
   uint8_t acc_id;
-  uint8_t wait_empty;  // OP_FIRST: bit mask of accumulators that must have been drained
+  uint8_t wait_empty;  // OP_FIRST: accumulators (bit mask) whose drain is not implied by an earlier hidden-half wait
+  uint32_t w_src0;     // byte offset in the pack of the leader CTA's rows of the first weight piece (peer: + bytes)
+  uint32_t w_src1;     // ... of the second piece (OP_TWO)
+  uint32_t bytes;      // bytes per piece per CTA = (N / 2) * 128
+  uint32_t pad1;
 };
-static_assert(sizeof(ChunkOp) == 16, "ChunkOp is read with one 16-byte constant load");
+static_assert(sizeof(ChunkOp) == 32, "ChunkOp: 16 bytes for the issuer + 16 bytes for the producer");
 
-// One accumulator's worth of work for the epilogue warps (a whole layer, or one N = 128 half of it in split mode).
-struct SubStep {
-  uint32_t bias_off;       // float index of the first bias of this sub-step
-  uint16_t n;              // 256 / 128 (hidden) or 16 (head)
+// One accumulator's worth of work for the epilogue warps: one N = 128 half of a 256-wide layer, or a head block.
+struct alignas(16) SubStep {
+  // hot fields, read with one 8-byte constant load
   uint16_t d_col;          // TMEM column of the accumulator (and of the in-place bf16 image)
   uint8_t acc_id;
   uint8_t epi;
+  uint16_t bias_off;       // float index of this sub-step's first bias in the (shared-memory resident) bias table
   uint8_t slice0;          // first 64-column slice (= hidden chunk) this sub-step produces: 0 or 2
-  uint8_t nslices;         // 4, or 2 in split mode; 0 for heads
-  int8_t head_dst[16];
-  uint8_t head_act[16];
+  uint8_t arrive_empty;    // some op waits for this accumulator to be drained: arrive on its "empty" barrier
+  uint8_t head_tbl[16];    // heads: per column dst | act << 6 (0xFF: column not written)
   uint64_t save_off;       // training mode: byte offset of this layer's activation image in the save buffer (kNoSave: none)
   uint64_t bits_off;       // ... and of its ReLU bit plane
+  uint16_t n;              // 128 (hidden) or 16 (head)
+  uint8_t pad[6];
 };
+static_assert(sizeof(SubStep) == 48, "SubStep layout");
 
 struct FwdParams {
   const uint8_t* pack;
@@ -240,8 +248,11 @@ struct FwdParams {
   int32_t n_subs, n_ops;
   int32_t n_tiles;
   int32_t need_t, need_dir, need_a, c_a;
+  int32_t n_bias;           // floats in the bias table
   int32_t last_extra_sub;   // last sub-step whose K-chunks include PE / time code / PE(dir): once its accumulator is
                             // complete the prologue chunks are dead and the NEXT tile's prologue can be written early
+  uint32_t stage_bytes;     // weight-ring stage (two pieces): 32768, or 16384 in split mode
+  int32_t n_stages;
   float flow_scale;
   uint8_t* save_base;       // training mode (kSave kernels): activation save buffer, see nsff_field_save.cuh
   unsigned long long* dbg;  // NSFF_TIMELINE builds only: (tag, clock64) event log of CTA 0
@@ -249,34 +260,45 @@ struct FwdParams {
   ChunkOp ops[kMaxOps];
 };
 
-// Timeline instrumentation (compiled in only with -DNSFF_TIMELINE; see tools/timeline.py).
+// Timeline instrumentation (compiled in only with -DNSFF_TIMELINE; see tools/timeline.py).  Events go to a shared-memory
+// log (8 bytes: tag << 40 | clock) and are copied to global memory when the role ends, so that logging neither stalls on
+// global stores nor drags them into the release semantics of the next mbarrier arrive.
 #ifdef NSFF_TIMELINE
-constexpr int kDbgPerRole = 8192;
-#define NSFF_TL_DECL(role) unsigned long long* tl_ptr = (P.dbg && blockIdx.x == 0) ? P.dbg + (role) * 2 * kDbgPerRole : nullptr; int tl_n = 0
-#define NSFF_TL(tag)                                                          \
-  do {                                                                        \
-    if (tl_ptr && tl_n < kDbgPerRole && lane == 0) {                          \
-      tl_ptr[2 * tl_n] = (unsigned long long)(tag);                           \
-      tl_ptr[2 * tl_n + 1] = (unsigned long long)clock64();                   \
-      ++tl_n;                                                                 \
-    }                                                                         \
+constexpr int kDbgPerRole = 512;
+static_assert(kSmemDbg == 3 * kDbgPerRole * 8, "log size");
+#define NSFF_TL_DECL(role) const uint32_t tl_base = sDbg + (role) * kDbgPerRole * 8; const int tl_role = (role); int tl_n = 0; const bool tl_on = P.dbg && blockIdx.x == 0
+#define NSFF_TL(tag)                                                                                       \
+  do {                                                                                                     \
+    if (tl_on && tl_n < kDbgPerRole && lane == 0) {                                                        \
+      const unsigned long long tl_v = ((unsigned long long)(tag) << 40) | ((unsigned long long)clock64() & 0xFFFFFFFFFFull); \
+      asm volatile("st.shared.b64 [%0], %1;" ::"r"(tl_base + 8u * (uint32_t)tl_n), "l"(tl_v) : "memory");   \
+      ++tl_n;                                                                                              \
+    }                                                                                                      \
+  } while (0)
+#define NSFF_TL_DUMP()                                                                                     \
+  do {                                                                                                     \
+    if (tl_on && lane == 0)                                                                                \
+      for (int tl_i = 0; tl_i < tl_n; ++tl_i) {                                                            \
+        unsigned long long tl_v;                                                                           \
+        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(tl_v) : "r"(tl_base + 8u * (uint32_t)tl_i));         \
+        P.dbg[tl_role * kDbgPerRole + tl_i] = tl_v;                                                        \
+      }                                                                                                    \
   } while (0)
 #else
 #define NSFF_TL_DECL(role) do {} while (0)
 #define NSFF_TL(tag) do {} while (0)
+#define NSFF_TL_DUMP() do {} while (0)
 #endif
 
 // barrier slots (8 bytes each) inside the barrier region
 enum {
   BAR_W_FULL = 0,                           // [kMaxStages] weight stage landed (tx + partner relay)
   BAR_W_EMPTY = BAR_W_FULL + kMaxStages,    // [kMaxStages] MMAs that read the stage completed (commit)
-  BAR_HID_FULL = BAR_W_EMPTY + kMaxStages,  // [4]  bf16 hidden chunk written to TMEM (by both CTAs)
-  BAR_EXTRA_FULL = BAR_HID_FULL + 4,        // [1]  prologue chunks written
+  BAR_HID_FULL = BAR_W_EMPTY + kMaxStages,  // [2]  bf16 image of hidden channels 0-127 / 128-255 written to TMEM (both CTAs)
+  BAR_EXTRA_FULL = BAR_HID_FULL + 2,        // [1]  prologue chunks written
   BAR_ACC_FULL = BAR_EXTRA_FULL + 1,        // [kAccIds] accumulator complete (commit)
   BAR_ACC_EMPTY = BAR_ACC_FULL + kAccIds,   // [kAccIds] accumulator drained
-  BAR_BIAS_FULL = BAR_ACC_EMPTY + kAccIds,  // [kBiasSlots]
-  BAR_BIAS_EMPTY = BAR_BIAS_FULL + kBiasSlots,   // [kBiasSlots]
-  BAR_COUNT = BAR_BIAS_EMPTY + kBiasSlots
+  BAR_COUNT = BAR_ACC_EMPTY + kAccIds
 };
 static_assert(BAR_COUNT * 8 + 8 <= kSmemBar, "barrier region too small");
 
@@ -303,35 +325,30 @@ __device__ __forceinline__ void store_unit_at(uint32_t row_base, int rsw, int un
 }
 
 // column c (0..63) of the xyz encoding row [x, sin(2^0 x), cos(2^0 x), ...] (nerf.py:17-30); col 63 = pad
-template <int kNFreq>
-__device__ __forceinline__ float pe_col(int c, const float (&base)[3], const float (&sn)[kNFreq][3],
-                                        const float (&cs)[kNFreq][3], int f0) {
-  if (c < 3) return base[c];
-  int k = c - 3, f = k / 6, r = k % 6;
-  if (f - f0 < 0 || f - f0 >= kNFreq) return 0.f;
-  return r < 3 ? sn[f - f0][r] : cs[f - f0][r - 3];
-}
-
-// PE(xyz) columns [16*kPart, 16*kPart+16) of one row: the frequencies those columns touch are
-// part 0: 2^0..2^2, part 1: 2^2..2^4, part 2: 2^4..2^7, part 3: 2^7..2^9 (+ the zero pad column 63).
+// PE(xyz) columns [16*kPart, 16*kPart+16) of one row (nerf.py:17-30): col 0-2 = x, then per octave f: sin(2^f x) (3),
+// cos(2^f x) (3); col 63 is the zero pad.  One accurate sincosf at octave 0, doubling up to the octaves this part needs.
 template <int kPart>
 __device__ __forceinline__ void encode_pe_part(uint32_t chPE, int row, const float (&base)[3]) {
-  constexpr int f0 = kPart == 0 ? 0 : kPart == 1 ? 2 : kPart == 2 ? 4 : 7;
-  constexpr int nf = kPart == 2 ? 4 : 3;
-  float sn[nf][3], cs[nf][3];
+  constexpr int lo = 16 * kPart, hi = lo + 16;
+  constexpr int f_last = kPart == 0 ? 2 : kPart == 1 ? 4 : kPart == 2 ? 7 : 9;
+  float sn[3], cs[3], v[16];
 #pragma unroll
-  for (int f = 0; f < nf; ++f)
+  for (int c = 0; c < 3; ++c) sincosf(base[c], &sn[c], &cs[c]);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) sincosf(__fmul_rn((float)(1 << (f0 + f)), base[c]), &sn[f][c], &cs[f][c]);
+  for (int i = 0; i < 16; ++i) v[i] = (lo + i < 3) ? base[(lo + i) % 3] : 0.f;
+#pragma unroll
+  for (int f = 0; f <= f_last; ++f) {
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      const int col = 3 + 6 * f + r;
+      if (col >= lo && col < hi) v[col - lo] = r < 3 ? sn[r % 3] : cs[r % 3];
+    }
+    if (f < f_last) pe_next_octave(sn, cs);
+  }
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
-    float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = (kPart * 2 + u) * 8 + i;
-      v[i] = c == 63 ? 0.f : pe_col<nf>(c, base, sn, cs, f0);
-    }
-    store_unit(chPE, row, kPart * 2 + u, v);
+    const float w[8] = {v[8 * u], v[8 * u + 1], v[8 * u + 2], v[8 * u + 3], v[8 * u + 4], v[8 * u + 5], v[8 * u + 6], v[8 * u + 7]};
+    store_unit(chPE, row, kPart * 2 + u, w);
   }
 }
 
@@ -384,16 +401,20 @@ __device__ __forceinline__ void encode_tile_row(const FwdParams& P, uint32_t sA,
     }
     if (P.need_dir && part == 3) {
       float d[3] = {P.pts.dirs[ray * 3 + 0], P.pts.dirs[ray * 3 + 1], P.pts.dirs[ray * 3 + 2]};
-      float sn[4][3], cs[4][3];
+      float sn[3], cs[3], pe[32];
 #pragma unroll
-      for (int f = 0; f < 4; ++f)
+      for (int c = 0; c < 3; ++c) sincosf(d[c], &sn[c], &cs[c]);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) sincosf(__fmul_rn((float)(1 << f), d[c]), &sn[f][c], &cs[f][c]);
+      for (int i = 0; i < 32; ++i) pe[i] = i < 3 ? d[i % 3] : 0.f;
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) pe[3 + 6 * f + r] = r < 3 ? sn[r % 3] : cs[r % 3];
+        if (f < 3) pe_next_octave(sn, cs);
+      }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = (u * 8 + i >= 27) ? 0.f : pe_col<4>(u * 8 + i, d, sn, cs, 0);
+        const float v[8] = {pe[8 * u], pe[8 * u + 1], pe[8 * u + 2], pe[8 * u + 3], pe[8 * u + 4], pe[8 * u + 5], pe[8 * u + 6], pe[8 * u + 7]};
         store_unit(chD, row, u, v);
       }
     }
@@ -440,10 +461,52 @@ __device__ __forceinline__ void encode_tile_row(const FwdParams& P, uint32_t sA,
   }
 }
 
+
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr)
+               : "memory");
+}
+
+// two fp32 adds in one instruction (add.rn.f32x2, sm_100): same rounding as two FADDs
+__device__ __forceinline__ void add2(float a0, float a1, float b0, float b1, float& o0, float& o1) {
+  asm("{\n\t.reg .b64 a, b, d;\n\t"
+      "mov.b64 a, {%2, %3};\n\t"
+      "mov.b64 b, {%4, %5};\n\t"
+      "add.rn.f32x2 d, a, b;\n\t"
+      "mov.b64 {%0, %1}, d;\n\t}"
+      : "=f"(o0), "=f"(o1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
+// 16 accumulator columns of one row: + bias, (ReLU,) round to bf16, pack pairs -> 8 words = one K = 16 step of the next
+// layer's A operand
+__device__ __forceinline__ void bias_act_pack(const uint32_t (&v)[16], const float4 (&b)[4], bool relu, uint32_t (&w)[8]) {
+  float f[16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    add2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), b[i].x, b[i].y, f[4 * i], f[4 * i + 1]);
+    add2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]), b[i].z, b[i].w, f[4 * i + 2], f[4 * i + 3]);
+  }
+  if (relu) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2_relu(f[2 * i], f[2 * i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+  }
+}
+
+// tanh through one exp: |error| ~ 1e-7 (tanhf's branchy multi-range code costs ~3x the instructions)
+__device__ __forceinline__ float tanh_f(float x) {
+  const float e = __expf(-2.f * fabsf(x));
+  return copysignf(__fdividef(1.f - e, 1.f + e), x);
+}
+
 template <bool kAppear, bool kSave>
 __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid_constant__ FwdParams P) {
   using C = Cfg<kAppear>;
-  constexpr int kStages = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;                       // extra chunks
@@ -451,35 +514,49 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
   const uint32_t sBias = sB + C::kSmemB;
   const uint32_t sBar = sBias + kSmemBias;
   const uint32_t sTmemPtr = sBar + BAR_COUNT * 8;
+#ifdef NSFF_TIMELINE
+  const uint32_t sDbg = sBar + kSmemBar;
+#endif
   auto bar = [&](int i) { return sBar + (uint32_t)i * 8u; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();
   const bool leader = cta_rank == 0;
   // barriers the MMA issuer waits on live in the leader CTA; both CTAs of the pair arrive there
-  auto arrive_leader = [&](int i) { mbar_arrive_cluster(mapa_cluster(bar(i), 0)); };
+  // (the leader's own warps arrive locally: a shared::cluster arrive takes the DSMEM round trip even to oneself)
+  auto arrive_leader = [&](int i) {
+    if (leader) mbar_arrive(bar(i));
+    else mbar_arrive_cluster(mapa_cluster(bar(i), 0));
+  };
   const int group = blockIdx.x >> 1, n_groups = gridDim.x >> 1;
   const int n_units = (P.n_tiles + 1) >> 1;            // tile pairs
+  const int n_stages = P.n_stages;
+  const uint32_t stage_bytes = P.stage_bytes;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) {
-      // leader: own half (producer arrive + tx) AND the partner's relay arrive complete a stage
+    for (int i = 0; i < n_stages; ++i) {
+      // leader: own pieces (producer arrive + tx) AND the partner's relay arrive complete a stage
       mbar_init(bar(BAR_W_FULL + i), leader ? 2 : 1);
       mbar_init(bar(BAR_W_EMPTY + i), 1);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_HID_FULL + i), kEpiWarps * 2);
+    for (int i = 0; i < 2; ++i) mbar_init(bar(BAR_HID_FULL + i), kEpiWarps * 2);
     mbar_init(bar(BAR_EXTRA_FULL), kEpiWarps * 2);
     for (int i = 0; i < kAccIds; ++i) {
       mbar_init(bar(BAR_ACC_FULL + i), 1);
       mbar_init(bar(BAR_ACC_EMPTY + i), kEpiWarps * 2);
     }
-    for (int i = 0; i < kBiasSlots; ++i) {
-      mbar_init(bar(BAR_BIAS_FULL + i), 1);
-      mbar_init(bar(BAR_BIAS_EMPTY + i), kEpiWarps);
-    }
     fence_mbar_init();
   }
   if (warp == kEpiWarps + 1) tmem_alloc_pair(sTmemPtr, 512);
+  if (warp < kEpiWarps) {
+    // the extra chunks are zero-filled once: the prologue only ever writes their used columns (48 of 64 for the time /
+    // appearance code, 32 for PE(dir)), while every chunk is issued as four K = 16 steps against zero-padded weights
+    for (uint32_t o = threadIdx.x * 16u; o < C::kSmemA; o += kEpiWarps * 32u * 16u)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sA + o), "r"(0u) : "memory");
+    // the module's bias table stays in shared memory for the whole kernel (no per-layer copies, no barriers)
+    for (int i = threadIdx.x; i < P.n_bias; i += kEpiWarps * 32)
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(sBias + 4u * (uint32_t)i), "f"(__ldg(P.bias + i)) : "memory");
+  }
   tc_fence_before_sync();
   cluster_sync_all();              // also: the peer's barriers are initialised before any remote arrive
   tc_fence_after_sync();
@@ -493,39 +570,36 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
     uint32_t stage = 0, epar = 1, gsub = 0;        // epar: parity that means "stage is free" (fresh barrier: 1)
     NSFF_TL_DECL(0);
     for (int unit = group; unit < n_units; unit += n_groups) {
-      int sub = 0;
       for (int i = 0; i < n_ops; ++i) {
-        const ChunkOp op = P.ops[i];
-        if (op.flags & OP_FIRST) {
-          const SubStep& ss = P.subs[sub];
-          const uint32_t bslot = gsub & (kBiasSlots - 1), buse = gsub / kBiasSlots;
-          mbar_wait_sleep(bar(BAR_BIAS_EMPTY + bslot), (buse & 1u) ^ 1u);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(bar(BAR_BIAS_FULL + bslot), (uint32_t)ss.n * 4u);
-            bulk_g2s(sBias + bslot * 1024u, P.bias + ss.bias_off, (uint32_t)ss.n * 4u, bar(BAR_BIAS_FULL + bslot));
-          }
-          __syncwarp();
-          ++sub, ++gsub;
-        }
+        const uint4 raw = reinterpret_cast<const uint4*>(&P.ops[i])[0];
+        const uint4 src = reinterpret_cast<const uint4*>(&P.ops[i])[1];      // w_src0, w_src1, bytes
+        const uint32_t flags = raw.w & 0xFFu;
+        if (flags & OP_FIRST) ++gsub;
         mbar_wait_sleep(bar(BAR_W_EMPTY + stage), epar);
         NSFF_TL(((gsub - 1) << 8) | 1);                    // producer: stage free, issuing copy
         if (elect_one()) {
-          mbar_arrive_expect_tx(bar(BAR_W_FULL + stage), op.bytes);
-          bulk_g2s(sB + stage * kStageBytes, P.pack + op.w_src + cta_rank * op.bytes, op.bytes, bar(BAR_W_FULL + stage));
+          const uint32_t bytes = src.z, two = (flags & OP_TWO) ? 1u : 0u;
+          const uint32_t dst = sB + stage * stage_bytes, full = bar(BAR_W_FULL + stage);
+          mbar_arrive_expect_tx(full, bytes << two);
+          bulk_g2s(dst, P.pack + src.x + cta_rank * bytes, bytes, full);
+          if (two) bulk_g2s(dst + bytes, P.pack + src.y + cta_rank * bytes, bytes, full);
         }
-        if (++stage == (uint32_t)kStages) stage = 0, epar ^= 1u;
+        if (++stage == (uint32_t)n_stages) stage = 0, epar ^= 1u;
       }
     }
+    NSFF_TL_DUMP();
   } else if (warp == kEpiWarps + 1) {
     if (leader) {
       // ===================== MMA issuer =====================
       // One elected lane walks the flat op list (the other 31 park at the reconvergence point).  The loop body is the
-      // serial critical path of the kernel - one instruction stream feeds the tensor pipe, 64 cycles per MMA in split
-      // mode - so everything that can be precomputed lives in the 16-byte op, and the barrier probes of op i+1 are
-      // issued before the MMAs of op i so that their round trip overlaps the issue work.
+      // serial critical path of the kernel - one instruction stream feeds the tensor pipe - so an op carries up to
+      // eight MMAs (two K-chunks), everything that can be precomputed lives in its first 16 bytes, every chunk is four
+      // K-steps (no data-dependent branches around the MMAs), and the barrier probes of op i+1 are issued before the
+      // MMAs of op i so that their round trip overlaps the issue work.
       const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);          // SBO | version | SWIZZLE_128B
       const uint32_t a_lo0 = ((sA & 0x3FFFFu) >> 4) | (1u << 16);
       const uint32_t b_lo0 = ((sB & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t stage_units = stage_bytes >> 4;
       auto desc = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; };
       if (elect_one()) {
         uint32_t stage = 0, wpar = 0, hid_gen = 0, unit_iter = 0, gsub = 0;
@@ -534,76 +608,87 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
         for (int unit = group; unit < n_units; unit += n_groups, ++unit_iter) {
           mbar_wait(bar(BAR_EXTRA_FULL), unit_iter & 1u);
           NSFF_TL((gsub << 8) | 15);                           // mma: prologue chunks ready
-          ChunkOp op = P.ops[0];
-          bool hid_ok = op.wait_hid == 0 || mbar_try_wait(bar(BAR_HID_FULL + op.wait_hid - 1), (hid_gen - 1u) & 1u);
+          uint4 op = reinterpret_cast<const uint4*>(&P.ops[0])[0];
+          uint32_t wh = (op.w >> 8) & 0xFFu;
+          bool hid_ok = wh == 0 || mbar_try_wait(bar(BAR_HID_FULL + wh - 1), (hid_gen - 1u) & 1u);
           bool w_ok = mbar_try_wait(bar(BAR_W_FULL + stage), wpar);
-          int kc = 0;
           for (int i = 0; i < n_ops; ++i) {
-            if (op.flags & OP_FIRST) {
-              kc = 0;
-              uint32_t m = op.wait_empty;
-              while (m) {                                      // accumulators this sub-step overwrites: drained?
-                const int a = __ffs((int)m) - 1;
-                m &= m - 1u;
-                mbar_wait(bar(BAR_ACC_EMPTY + a), ((fill_par >> a) & 1u) ^ 1u);
-              }
-              NSFF_TL((gsub << 8) | 14);                       // mma: accumulator free
+            const uint4 cur = op;
+            const uint32_t flags = cur.w & 0xFFu, acc = (cur.w >> 16) & 0xFFu;
+            // the next op is fetched now; its barrier probes are issued BETWEEN the two MMA groups below, so neither the
+            // constant load nor the probes' round trips sit between the last MMA of this op and the first of the next
+            const int i_next = i + 1 < n_ops ? i + 1 : i;
+            op = reinterpret_cast<const uint4*>(&P.ops[i_next])[0];
+            uint32_t we = cur.w >> 24;
+            while (we) {
+              // accumulators this sub-step overwrites whose drain no earlier wait implies (head accumulators; rare)
+              const uint32_t a = (uint32_t)__ffs((int)we) - 1u;
+              we &= we - 1u;
+              mbar_wait(bar(BAR_ACC_EMPTY + a), ((fill_par >> a) & 1u) ^ 1u);
             }
-            NSFF_TL((gsub << 8) | (kc << 4) | 2);              // mma: chunk loop top
-            if (!hid_ok) mbar_wait(bar(BAR_HID_FULL + op.wait_hid - 1), (hid_gen - 1u) & 1u);
-            NSFF_TL((gsub << 8) | (kc << 4) | 3);              // mma: A chunk ready
+            if (!hid_ok) mbar_wait(bar(BAR_HID_FULL + wh - 1), (hid_gen - 1u) & 1u);
             if (!w_ok) mbar_wait(bar(BAR_W_FULL + stage), wpar);
-            NSFF_TL((gsub << 8) | (kc << 4) | 4);              // mma: weights ready -> issue
-            const ChunkOp cur = op;
-            const uint32_t b_lo = b_lo0 + stage * (kStageBytes >> 4);
+            NSFF_TL((gsub << 8) | 4);                          // mma: operands ready -> issue
+            const uint32_t b_lo = b_lo0 + stage * stage_units;
             const uint32_t empty_bar = bar(BAR_W_EMPTY + stage);
-            if (++stage == (uint32_t)kStages) stage = 0, wpar ^= 1u;
-            const uint32_t hid_next = hid_gen + ((cur.flags & OP_ADV_HID) ? 1u : 0u);
-            if (i + 1 < n_ops) {                               // early probes for the next op
-              op = P.ops[i + 1];
-              hid_ok = op.wait_hid == 0 || mbar_try_wait(bar(BAR_HID_FULL + op.wait_hid - 1), (hid_next - 1u) & 1u);
-              w_ok = mbar_try_wait(bar(BAR_W_FULL + stage), wpar);
-            }
+            if (++stage == (uint32_t)n_stages) stage = 0, wpar ^= 1u;
+            hid_gen += (flags & OP_ADV_HID) ? 1u : 0u;
             tc_fence_after_sync();
-            const uint32_t d_tmem = tmem_base + cur.d_col;
-            const uint32_t idesc = make_idesc_bf16(2 * kTileM, (uint32_t)cur.n16 * 16u);
-            const uint32_t acc0 = (cur.flags & OP_FIRST) ? 0u : 1u;
-            const uint32_t kcnt = cur.kcnt;
-            if (cur.flags & OP_TS) {
-              const uint32_t a_t = tmem_base + cur.a;          // 8 columns (16 bf16) per K-step, 16 columns apart
-              mma_bf16_ts_pair(d_tmem, a_t, desc(b_lo), idesc, acc0);
-              mma_bf16_ts_pair(d_tmem, a_t + 16, desc(b_lo + 2), idesc, 1u);
-              if (kcnt > 2) mma_bf16_ts_pair(d_tmem, a_t + 32, desc(b_lo + 4), idesc, 1u);
-              if (kcnt > 3) mma_bf16_ts_pair(d_tmem, a_t + 48, desc(b_lo + 6), idesc, 1u);
+            const uint32_t idesc = cur.x;
+            const uint32_t d_tmem = tmem_base + (cur.z & 0xFFFFu);
+            const uint32_t acc0 = (flags & OP_FIRST) ? 0u : 1u;
+            const uint32_t b_lo2 = b_lo + (cur.z >> 16);
+            const bool ts = flags & OP_TS, two = flags & OP_TWO;
+            const uint32_t a1 = (ts ? tmem_base : a_lo0) + (cur.y & 0xFFFFu), a2 = (ts ? tmem_base : a_lo0) + (cur.y >> 16);
+            if (ts) {
+              mma_bf16_ts_pair(d_tmem, a1, desc(b_lo), idesc, acc0);           // 8 columns (16 bf16) per K-step, 16 apart
+              mma_bf16_ts_pair(d_tmem, a1 + 16, desc(b_lo + 2), idesc, 1u);
+              mma_bf16_ts_pair(d_tmem, a1 + 32, desc(b_lo + 4), idesc, 1u);
+              mma_bf16_ts_pair(d_tmem, a1 + 48, desc(b_lo + 6), idesc, 1u);
             } else {
-              const uint32_t a_lo = a_lo0 + cur.a;             // +32 B per K-step inside the 128 B swizzle row
-              mma_bf16_ss_pair(d_tmem, desc(a_lo), desc(b_lo), idesc, acc0);
-              mma_bf16_ss_pair(d_tmem, desc(a_lo + 2), desc(b_lo + 2), idesc, 1u);
-              if (kcnt > 2) mma_bf16_ss_pair(d_tmem, desc(a_lo + 4), desc(b_lo + 4), idesc, 1u);
-              if (kcnt > 3) mma_bf16_ss_pair(d_tmem, desc(a_lo + 6), desc(b_lo + 6), idesc, 1u);
+              mma_bf16_ss_pair(d_tmem, desc(a1), desc(b_lo), idesc, acc0);     // +32 B per K-step inside the 128 B swizzle row
+              mma_bf16_ss_pair(d_tmem, desc(a1 + 2), desc(b_lo + 2), idesc, 1u);
+              mma_bf16_ss_pair(d_tmem, desc(a1 + 4), desc(b_lo + 4), idesc, 1u);
+              mma_bf16_ss_pair(d_tmem, desc(a1 + 6), desc(b_lo + 6), idesc, 1u);
+            }
+            // early probes for the next op (the tensor pipe is working through the MMAs just queued)
+            wh = (op.w >> 8) & 0xFFu;
+            hid_ok = wh == 0 || mbar_try_wait(bar(BAR_HID_FULL + wh - 1), (hid_gen - 1u) & 1u);
+            w_ok = mbar_try_wait(bar(BAR_W_FULL + stage), wpar);
+            if (two) {
+              if (ts) {
+                mma_bf16_ts_pair(d_tmem, a2, desc(b_lo2), idesc, 1u);
+                mma_bf16_ts_pair(d_tmem, a2 + 16, desc(b_lo2 + 2), idesc, 1u);
+                mma_bf16_ts_pair(d_tmem, a2 + 32, desc(b_lo2 + 4), idesc, 1u);
+                mma_bf16_ts_pair(d_tmem, a2 + 48, desc(b_lo2 + 6), idesc, 1u);
+              } else {
+                mma_bf16_ss_pair(d_tmem, desc(a2), desc(b_lo2), idesc, 1u);
+                mma_bf16_ss_pair(d_tmem, desc(a2 + 2), desc(b_lo2 + 2), idesc, 1u);
+                mma_bf16_ss_pair(d_tmem, desc(a2 + 4), desc(b_lo2 + 4), idesc, 1u);
+                mma_bf16_ss_pair(d_tmem, desc(a2 + 6), desc(b_lo2 + 6), idesc, 1u);
+              }
             }
             mma_commit_pair_mc(empty_bar, 3);                  // frees the stage in BOTH CTAs
-            if (cur.flags & OP_LAST) {
-              mma_commit_pair_mc(bar(BAR_ACC_FULL + cur.acc_id), 3);
-              fill_par ^= 1u << cur.acc_id;
+            if (flags & OP_LAST) {
+              mma_commit_pair_mc(bar(BAR_ACC_FULL + acc), 3);
+              fill_par ^= 1u << acc;
+              NSFF_TL((gsub << 8) | 11);                       // mma: sub-step committed
               ++gsub;
             }
-            NSFF_TL(((gsub - ((cur.flags & OP_LAST) ? 1u : 0u)) << 8) | (kc << 4) | 11);   // mma: committed
-            hid_gen = hid_next;
-            ++kc;
           }
         }
+        NSFF_TL_DUMP();
       }
       __syncwarp();
     } else {
-      // ===================== peer CTA: relay "my weight half has landed" to the leader ==============
+      // ===================== peer CTA: relay "my weight pieces have landed" to the leader ==============
       uint32_t stage = 0, wpar = 0;
       const uint32_t leader_w_full = mapa_cluster(bar(BAR_W_FULL), 0);
       for (int unit = group; unit < n_units; unit += n_groups) {
         for (int i = 0; i < n_ops; ++i) {
           mbar_wait_sleep(bar(BAR_W_FULL + stage), wpar);
           if (lane == 0) mbar_arrive_cluster(leader_w_full + stage * 8u);
-          if (++stage == (uint32_t)kStages) stage = 0, wpar ^= 1u;
+          if (++stage == (uint32_t)n_stages) stage = 0, wpar ^= 1u;
         }
       }
     }
@@ -617,8 +702,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
     uint32_t gsub = 0;
     uint32_t drain_par = 0;                        // bit a: (number of drains of accumulator a so far) & 1
 #ifdef NSFF_TIMELINE
-    unsigned long long* tl_ptr = (P.dbg && blockIdx.x == 0 && warp == 0) ? P.dbg + 2 * 2 * kDbgPerRole : nullptr;
+    const uint32_t tl_base = sDbg + 2 * kDbgPerRole * 8;
+    const int tl_role = 2;
     int tl_n = 0;
+    const bool tl_on = P.dbg && blockIdx.x == 0 && warp == 0;
 #endif
     // Prologue: encode a tile's inputs into the extra chunks.  Only the first tile pays for it up front; for every
     // later tile it is run during the previous tile, right after the last sub-step that reads those chunks
@@ -645,149 +732,123 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
       // ---------------- epilogues, one per sub-step ----------------
       for (int s = 0; s < n_subs; ++s, ++gsub) {
         const SubStep& ss = P.subs[s];
-        const uint32_t acc = ss.acc_id;
-        const uint32_t bslot = gsub & (kBiasSlots - 1);
-        mbar_wait(bar(BAR_BIAS_FULL + bslot), (gsub / kBiasSlots) & 1u);   // landed long ago: issued a sub-step ahead
-        const uint32_t s_bias = sBias + bslot * 1024u;
-        const uint32_t t_acc = tmem_base + lane_field + ss.d_col;
-        if (ss.epi != EPI_HEAD) {
+        // everything the hot path needs from the sub-step table comes with one 8-byte constant load
+        const uint2 hot = *reinterpret_cast<const uint2*>(&ss);
+        const uint32_t d_col = hot.x & 0xFFFFu, acc = (hot.x >> 16) & 0xFFu, epi = hot.x >> 24;
+        const uint32_t s_bias = sBias + 4u * (hot.y & 0xFFFFu);
+        const uint32_t half = ((hot.y >> 16) & 0xFFu) >> 1;
+        const bool arrive_empty = (hot.y >> 24) != 0;
+        const uint32_t t_acc = tmem_base + lane_field + d_col;
+        const uint32_t acc_full = bar(BAR_ACC_FULL + acc), acc_par = (drain_par >> acc) & 1u;
+        drain_par ^= 1u << acc;
+        if (epi != EPI_HEAD) {
+          // One N = 128 half of a 256-wide layer: two 64-column slices; this warp owns 16 columns of each.
+          const bool relu = epi == EPI_RELU_HID;
           // bias of the first slice is fetched before the accumulator is awaited: it is off the critical path
           float4 b[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) lds_v4(s_bias + (uint32_t)((part * 16 + i * 4) * 4), b[i]);
           NSFF_TL((gsub << 8) | 5);                            // epi: waiting for the accumulator
-          mbar_wait(bar(BAR_ACC_FULL + acc), (drain_par >> acc) & 1u);
+          mbar_wait(acc_full, acc_par);
           NSFF_TL((gsub << 8) | 6);                            // epi: accumulator complete
           tc_fence_after_sync();
-          const bool relu = ss.epi == EPI_RELU_HID;
-          const int nsl = ss.nslices;
-          // software pipeline over the 64-column slices: TMEM load of slice c+1 is in flight while slice c is biased /
-          // activated / packed / written back to TMEM as the next layer's A operand.
-          uint32_t v[2][16];
-          tmem_ld16(t_acc + (uint32_t)(part * 16), v[0]);
+          uint32_t v0[16], v1[16];
+          tmem_ld16(t_acc + (uint32_t)(part * 16), v0);        // both slices in flight together
+          tmem_ld16(t_acc + (uint32_t)(64 + part * 16), v1);
+          tmem_ld_wait();
+          // accumulator drained into registers: its columns may be overwritten by the layer after next (which cannot
+          // start before the bf16 image written below has been published and consumed)
+          if (arrive_empty) {                                  // (hidden accumulators: normally nobody waits, see build_program)
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) arrive_leader(BAR_ACC_EMPTY + acc);
+          }
+          uint32_t w0[8], w1[8];
+          float4 b1[4];                                        // bias of the second slice: in flight during the first
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (c < nsl) {
-              tmem_ld_wait();
-              if (c + 1 < nsl) {
-                tmem_ld16(t_acc + (uint32_t)((c + 1) * 64 + part * 16), v[(c + 1) & 1]);
-              } else {
-                // accumulator fully drained into registers: its columns may be overwritten by the layer after next
-                // (which cannot start before the bf16 image written below has been published and consumed)
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) arrive_leader(BAR_ACC_EMPTY + acc);
-              }
-              uint32_t w[8];
-              uint32_t pos16 = 0;
+          for (int i = 0; i < 4; ++i) lds_v4(s_bias + (uint32_t)((64 + part * 16 + i * 4) * 4), b1[i]);
+          bias_act_pack(v0, b, relu, w0);
+          // K-step `part` of hidden chunk slice0: 16 bf16 = 8 columns, in place (columns this warp has drained)
+          tmem_st8(t_acc + (uint32_t)(part * 16), w0[0], w0[1], w0[2], w0[3], w0[4], w0[5], w0[6], w0[7]);
+          bias_act_pack(v1, b1, relu, w1);
+          tmem_st8(t_acc + (uint32_t)(8 + part * 16), w1[0], w1[1], w1[2], w1[3], w1[4], w1[5], w1[6], w1[7]);
+          // both chunks of this 128-channel half are written: publish it to the MMA issuer
+          tmem_st_wait();
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) arrive_leader(BAR_HID_FULL + half);
+          NSFF_TL((gsub << 8) | 7);                            // epi: hidden half published
+          if constexpr (kSave) {
+            // training mode: the bf16 rows just written are also the backward's tile image (128B-swizzled chunk
+            // [tile][chunk][128 rows x 128 B]); this warp owns one aligned 32-byte sector of its row per chunk, and
+            // 16 ReLU bits per chunk (recomputed from the packed bf16 values: positive <=> non-zero after ReLU)
+            if (ss.save_off != kNoSave && tile < P.n_tiles) {
 #pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                float f[8];
+              for (int c = 0; c < 2; ++c) {
+                const uint32_t* w = c ? w1 : w0;
+                const int cg = (int)(2 * half) + c;
+                uint8_t* g = P.save_base + ss.save_off + (size_t)tile * kSaveImgPerTile + (size_t)cg * kChunkBytes +
+                             (row_off);
+                const bool swap = rsw & 1;
+                const uint4 lo = make_uint4(w[0], w[1], w[2], w[3]), hi = make_uint4(w[4], w[5], w[6], w[7]);
+                st_global_v8(g + ((((part * 2) ^ rsw) & 6) << 4), swap ? hi : lo, swap ? lo : hi);
+                if (relu) {
+                  uint32_t pos16 = 0;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float4 bb = b[u * 2 + (i >> 2)];
-                  const float bv = (i & 3) == 0 ? bb.x : (i & 3) == 1 ? bb.y : (i & 3) == 2 ? bb.z : bb.w;
-                  f[i] = __uint_as_float(v[c & 1][u * 8 + i]) + bv;
+                  for (int i = 0; i < 8; ++i)
+                    pos16 |= ((w[i] & 0x7FFFu) ? 1u : 0u) << (2 * i) | ((w[i] & 0x7FFF0000u) ? 1u : 0u) << (2 * i + 1);
+                  *reinterpret_cast<uint16_t*>(P.save_base + ss.bits_off + (size_t)tile * kSaveBitsPerTile +
+                                               ((size_t)(2 * cg + (part >> 1)) * 128 + row) * 4 + (part & 1) * 2) =
+                      (uint16_t)pos16;
                 }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  w[u * 4 + i] = relu ? pack_bf16x2_relu(f[2 * i], f[2 * i + 1]) : pack_bf16x2(f[2 * i], f[2 * i + 1]);
-                if constexpr (kSave) {
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) pos16 |= (f[i] > 0.f ? 1u : 0u) << (u * 8 + i);
-                }
-              }
-              // K-step `part` of hidden chunk slice0+c: 16 bf16 = 8 columns, in place (columns this warp has drained)
-              tmem_st8(t_acc + (uint32_t)(((c >> 1) << 6) + ((c & 1) << 3) + part * 16), w[0], w[1], w[2], w[3], w[4],
-                       w[5], w[6], w[7]);
-              tmem_st_wait();
-              tc_fence_before_sync();
-              __syncwarp();
-              if (lane == 0) arrive_leader(BAR_HID_FULL + ss.slice0 + c);
-              if constexpr (kSave) {
-                // training mode: the bf16 rows just published are also the backward's tile image (128B-swizzled chunk
-                // [tile][chunk][128 rows x 128 B]); this warp owns one aligned 32-byte sector of its row
-                if (ss.save_off != kNoSave && tile < P.n_tiles) {
-                  const int cg = ss.slice0 + c;
-                  uint8_t* g = P.save_base + ss.save_off + (size_t)tile * kSaveImgPerTile + (size_t)cg * kChunkBytes +
-                               (row_off);
-                  const bool swap = rsw & 1;
-                  const uint4 lo = make_uint4(w[0], w[1], w[2], w[3]), hi = make_uint4(w[4], w[5], w[6], w[7]);
-                  st_global_v8(g + ((((part * 2) ^ rsw) & 6) << 4), swap ? hi : lo, swap ? lo : hi);
-                  if (relu)
-                    *reinterpret_cast<uint16_t*>(P.save_base + ss.bits_off + (size_t)tile * kSaveBitsPerTile +
-                                                 ((size_t)(2 * cg + (part >> 1)) * 128 + row) * 4 + (part & 1) * 2) =
-                        (uint16_t)pos16;
-                }
-              }
-              NSFF_TL((gsub << 8) | (c << 4) | 7);             // epi: hidden chunk published
-              if (c + 1 < nsl) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) lds_v4(s_bias + (uint32_t)(((c + 1) * 64 + part * 16 + i * 4) * 4), b[i]);
-              } else {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar(BAR_BIAS_EMPTY + bslot));      // bias row fully consumed
               }
             }
           }
         } else {
-          mbar_wait(bar(BAR_ACC_FULL + acc), (drain_par >> acc) & 1u);
+          // Head block (N = 16): each of the four column-part warps of a lane quadrant owns 4 head columns.
+          const uint32_t tbl = reinterpret_cast<const uint32_t*>(ss.head_tbl)[part];   // 4 x (dst | act << 6)
+          float4 hb;
+          lds_v4(s_bias + (uint32_t)(part * 16), hb);
+          mbar_wait(acc_full, acc_par);
           tc_fence_after_sync();
-          uint32_t v[16];
-          float hb[16];
-          if (part == 0) {
-            tmem_ld16(t_acc, v);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float4 t4;
-              lds_v4(s_bias + (uint32_t)(i * 16), t4);
-              hb[4 * i] = t4.x, hb[4 * i + 1] = t4.y, hb[4 * i + 2] = t4.z, hb[4 * i + 3] = t4.w;
-            }
-            tmem_ld_wait();
-          }
+          uint32_t v[4];
+          tmem_ld4(t_acc + (uint32_t)(part * 4), v);
+          tmem_ld_wait();
           // accumulator and bias row are in registers: hand both back before the activations / global stores
           tc_fence_before_sync();
           __syncwarp();
-          if (lane == 0) {
-            arrive_leader(BAR_ACC_EMPTY + acc);
-            mbar_arrive(bar(BAR_BIAS_EMPTY + bslot));
-          }
-          if (part == 0 && valid) {
+          if (lane == 0) arrive_leader(BAR_ACC_EMPTY + acc);
+          if (valid) {
             float* orow = P.out + p * P.out_ld;
-            float fl[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // flow fw / bw = head columns 4..9 of the dynamic block
-            bool has_flow = false;
+            const float hbv[4] = {hb.x, hb.y, hb.z, hb.w};
+            const bool warp_pts = P.x_emb == nullptr && P.pts.offset == nullptr;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int dst = ss.head_dst[i];
-              if (dst < 0) continue;
-              float x = __uint_as_float(v[i]) + hb[i];
-              const int act = ss.head_act[i];
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t e = (tbl >> (8 * j)) & 0xFFu;
+              if (e == 0xFFu) continue;
+              const uint32_t dst = e & 63u, act = e >> 6;
+              float x = __uint_as_float(v[j]) + hbv[j];
               if (act == HA_SIGMOID) x = sigmoid_f(x);
               else if (act == HA_FLOW) {
-                x = (zrow > kZFar) ? 0.f : P.flow_scale * tanhf(x);
-                if (i >= 4 && i < 10) fl[i - 4] = x, has_flow = true;
+                x = (zrow > kZFar) ? 0.f : P.flow_scale * tanh_f(x);
+                // points of the warped passes, written here so those passes do not gather 12 B out of every output
+                // row: head columns 4..6 = flow fw, 7..9 = flow bw
+                const int hc = part * 4 + j;
+                if (warp_pts && hc >= 4 && hc < 10) {
+                  float* wp = hc < 7 ? P.pts.xyz_fw_out : P.pts.xyz_bw_out;
+                  const int cc = hc < 7 ? hc - 4 : hc - 7;
+                  if (wp) wp[p * 3 + cc] = __fadd_rn(P.pts.xyz[p * 3 + cc], x);
+                }
               }
               orow[dst] = x;
             }
-            // points of the warped passes, written here so those passes do not gather 12 B out of every output row
-            if (has_flow && P.x_emb == nullptr && P.pts.offset == nullptr) {
-              const float* x3 = P.pts.xyz + p * 3;
-              if (P.pts.xyz_fw_out) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) P.pts.xyz_fw_out[p * 3 + c] = __fadd_rn(x3[c], fl[c]);
-              }
-              if (P.pts.xyz_bw_out) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) P.pts.xyz_bw_out[p * 3 + c] = __fadd_rn(x3[c], fl[3 + c]);
-              }
-            }
           }
         }
-        drain_par ^= 1u << acc;
         // this sub-step's accumulator was complete => every MMA up to and including it has finished reading smem
         if (s == P.last_extra_sub && unit + n_groups < n_units) prologue(unit + n_groups);
       }
     }
+    NSFF_TL_DUMP();
   }
 
   tc_fence_before_sync();
@@ -918,34 +979,44 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
   int cur = -1;                        // region (0 = X, 1 = Y) that holds the current hidden activation; -1: none yet
   bool overflow = false;
   P.last_extra_sub = 0;
-  const uint32_t half_cols = split ? 128u : 64u;     // TMEM columns between the bf16 images of channels 0-127 / 128-255
+  const int half_cols = split ? 128 : 64;            // TMEM columns between the bf16 images of channels 0-127 / 128-255
+  auto a_of = [&](int ch) -> uint16_t {              // A-operand address of K-step 0 of chunk `ch`
+    if (ch < CH_PE) return (uint16_t)(cur * 256 + (ch >> 1) * half_cols + (ch & 1) * 8);     // TMEM column
+    return (uint16_t)((ch - CH_PE) * (int)(kChunkBytes >> 4));                                 // smem, 16-byte units
+  };
+  // host-only bookkeeping for the drain analysis below
+  struct OpMeta { int acc; bool first, head; int waits_half; };
+  OpMeta meta[kMaxOps];
   auto push = [&](int lid, uint8_t epi) -> SubStep* {
     const PackLayer& pl = L.layer[lid];
     const bool head = epi == EPI_HEAD;
     const int parts = (!head && split) ? 2 : 1;
     const int region = head ? cur : (cur < 0 ? 0 : 1 - cur);
     if (head && cur < 0) { overflow = true; return nullptr; }
-    SubStep* first = nullptr;
+    if (n_subs + parts > kMaxSubs) { overflow = true; return nullptr; }
+    SubStep* first = &P.subs[n_subs];
+    ChunkOp half_ops[2][kMaxChunks];
+    OpMeta half_meta[2][kMaxChunks];
+    int n_half = 0;
     for (int h = 0; h < parts; ++h) {
-      if (n_subs >= kMaxSubs) { overflow = true; return nullptr; }
-      SubStep& s = P.subs[n_subs];
-      if (!first) first = &s;
+      SubStep& s = P.subs[n_subs + h];
       const int n = head ? pl.n : pl.n / parts;
-      s.bias_off = pl.bias_off + (uint32_t)(h * n);
+      s.bias_off = (uint16_t)(pl.bias_off + (uint32_t)(h * n));
+      s.arrive_empty = head ? 1 : 0;
       s.n = (uint16_t)n;
       s.epi = epi;
       if (head) {
-        // free columns of the region that holds the input: above the two in-place bf16 images
+        // free columns of the region that holds the input: above the in-place bf16 image of channels 0-127
         s.d_col = (uint16_t)(region * 256 + (split ? 64 : 128));
         s.acc_id = kHeadAcc;
-        s.slice0 = 0, s.nslices = 0;
+        s.slice0 = 0;
       } else {
         s.d_col = (uint16_t)(region * 256 + h * 128);
         s.acc_id = (uint8_t)(region * 2 + h);
         s.slice0 = (uint8_t)(2 * h);
-        s.nslices = (uint8_t)(4 / parts);
       }
-      for (int i = 0; i < 16; ++i) s.head_dst[i] = -1, s.head_act[i] = HA_NONE;
+      memset(s.head_tbl, 0xFF, sizeof(s.head_tbl));
+      memset(s.pad, 0, sizeof(s.pad));
       s.save_off = s.bits_off = kNoSave;
       if (SL) {
         if (lid >= L_S1 && lid <= L_S8) s.save_off = SL->s_h[lid - L_S1], s.bits_off = SL->s_hb[lid - L_S1];
@@ -954,55 +1025,71 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
         else if (lid >= L_T1 && lid <= L_T8) s.save_off = SL->t_h[lid - L_T1], s.bits_off = SL->t_hb[lid - L_T1];
         else if (lid == L_TFIN) s.save_off = SL->t_feat;
       }
-      for (int kc = 0; kc < pl.nchunks; ++kc) {
-        if (n_ops >= kMaxOps) { overflow = true; return nullptr; }
-        ChunkOp& o = P.ops[n_ops++];
+      const uint32_t block_bytes = (uint32_t)pl.n * 128u;                // whole N x 64 block of one K-chunk
+      const uint32_t piece = (uint32_t)n * 128u / 2u;                    // this CTA's N/2 rows of it
+      int k = 0;
+      for (int kc = 0; kc < pl.nchunks; ++k) {
+        ChunkOp& o = half_ops[h][k];
+        OpMeta& m = half_meta[h][k];
+        memset(&o, 0, sizeof(o));
         const int ch = pl.chunk[kc];
-        const uint32_t block_bytes = (uint32_t)pl.n * 128u;              // whole N x 64 block of this K-chunk
-        o.bytes = (uint16_t)((uint32_t)n * 128u / 2u);                   // this CTA's N/2 rows
-        o.w_src = pl.w_off + (uint32_t)kc * block_bytes + (uint32_t)h * (uint32_t)n * 128u;
+        const bool hidden = ch < CH_PE;
+        if (hidden && cur < 0) { overflow = true; return nullptr; }
+        // two consecutive K-chunks of the same kind share an op: (H0,H1) (H2,H3) / (H3,H2) (H1,H0) / (PE,T) / (DIR,A)
+        const bool two = kc + 1 < pl.nchunks && ((pl.chunk[kc + 1] < CH_PE) == hidden) &&
+                         (hidden ? (pl.chunk[kc + 1] >> 1) == (ch >> 1) : pl.chunk[kc + 1] == ch + 1);
+        o.idesc = make_idesc_bf16(2 * kTileM, (uint32_t)n);
+        o.a = a_of(ch);
         o.d_col = s.d_col;
-        o.n16 = (uint8_t)(n / 16);
-        o.kcnt = pl.kcnt[kc];
         o.acc_id = s.acc_id;
-        o.flags = 0;
-        o.wait_hid = 0;
-        o.wait_empty = 0;
-        if (ch < CH_PE) {
-          if (cur < 0) { overflow = true; return nullptr; }
-          o.flags |= OP_TS;
-          o.a = (uint16_t)(cur * 256 + (ch >> 1) * (int)half_cols + (ch & 1) * 8);
-          if (h == 0) o.wait_hid = (uint8_t)(1 + ch);                    // later uses in the same layer: already awaited
+        o.bytes = piece;
+        o.w_src0 = pl.w_off + (uint32_t)kc * block_bytes + (uint32_t)h * (uint32_t)n * 128u;
+        o.flags = hidden ? OP_TS : 0;
+        if (two) {
+          o.flags |= OP_TWO;
+          o.a2 = a_of(pl.chunk[kc + 1]);
+          o.b2 = (uint16_t)(piece >> 4);
+          o.w_src1 = o.w_src0 + block_bytes;
+        }
+        m.acc = s.acc_id, m.first = kc == 0, m.head = head, m.waits_half = -1;
+        if (hidden) {
+          if (h == 0) o.wait_hid = (uint8_t)(1 + (ch >> 1)), m.waits_half = ch >> 1;   // h = 1 issues later: already awaited
         } else {
-          o.a = (uint16_t)((ch - CH_PE) * (int)(kChunkBytes >> 4));
-          P.last_extra_sub = n_subs;
+          P.last_extra_sub = n_subs + h;
         }
-        if (kc == 0) {
-          o.flags |= OP_FIRST;
-          o.wait_empty = (uint8_t)((1u << s.acc_id) | (1u << kHeadAcc));
-        }
-        if (kc == pl.nchunks - 1) {
-          o.flags |= OP_LAST;
-          if (!head && h == parts - 1) o.flags |= OP_ADV_HID;
-        }
+        if (kc == 0) o.flags |= OP_FIRST;
+        kc += two ? 2 : 1;
+        if (kc == pl.nchunks) o.flags |= OP_LAST;
       }
-      ++n_subs;
+      n_half = k;
     }
+    // Issue order inside a layer: op k of half 0, op k of half 1, op k+1 of half 0, ... - the ops that read channels
+    // 0-127 of the previous layer run for BOTH halves (2 x 8 MMAs) before anything needs channels 128-255, which the
+    // epilogue of the previous layer's second half is still producing.
+    for (int k = 0; k < n_half; ++k)
+      for (int h = 0; h < parts; ++h) {
+        if (n_ops >= kMaxOps) { overflow = true; return nullptr; }
+        meta[n_ops] = half_meta[h][k];
+        P.ops[n_ops++] = half_ops[h][k];
+      }
+    if (!head) P.ops[n_ops - 1].flags |= OP_ADV_HID;
+    n_subs += parts;
     if (!head) cur = region;
     return first;
   };
   P.need_dir = 0;
   P.need_t = 0;
   P.need_a = 0;
+  auto head_col = [](SubStep* s, int i, int dst, int act) {
+    if (s) s->head_tbl[i] = (uint8_t)(dst | (act << 6));
+  };
   if (want_s) {
     for (int i = L_S1; i <= L_S8; ++i) push(i, EPI_RELU_HID);
     if (sigma_only) {
-      SubStep* s = push(L_SSIG, EPI_HEAD);
-      if (s) s->head_dst[0] = (int8_t)col;
+      head_col(push(L_SSIG, EPI_HEAD), 0, col, HA_NONE);
       col += 1;
     } else {
-      SubStep* sg = push(L_SSIG, EPI_HEAD);
-      if (sg) sg->head_dst[0] = (int8_t)(col + 3);
+      head_col(push(L_SSIG, EPI_HEAD), 0, col + 3, HA_NONE);
       push(L_SFIN, EPI_LIN_HID);
       if (d.use_viewdir) {
         push(L_SDIR, EPI_RELU_HID);
@@ -1010,8 +1097,7 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
         P.need_a = d.in_a > 0;
       }
       SubStep* rg = push(L_SRGB, EPI_HEAD);
-      if (rg)
-        for (int i = 0; i < 3; ++i) rg->head_dst[i] = (int8_t)(col + i), rg->head_act[i] = HA_SIGMOID;
+      for (int i = 0; i < 3; ++i) head_col(rg, i, col + i, HA_SIGMOID);
       col += 4;
     }
   }
@@ -1020,35 +1106,65 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
     for (int i = L_T1; i <= L_T8; ++i) push(i, EPI_RELU_HID);
     push(L_TFIN, EPI_LIN_HID);
     SubStep* h = push(L_THEAD, EPI_HEAD);
-    if (h) {
-      if (sigma_only) {
-        h->head_dst[3] = (int8_t)col;
-        col += 1;
-      } else {
-        for (int i = 0; i < 3; ++i) h->head_dst[i] = (int8_t)(col + i), h->head_act[i] = HA_SIGMOID;
-        h->head_dst[3] = (int8_t)(col + 3);
-        col += 4;
-        if (want_fw) {
-          for (int i = 0; i < 3; ++i) h->head_dst[4 + i] = (int8_t)(col + i), h->head_act[4 + i] = HA_FLOW;
-          col += 3;
-        }
-        if (want_bw) {
-          for (int i = 0; i < 3; ++i) h->head_dst[7 + i] = (int8_t)(col + i), h->head_act[7 + i] = HA_FLOW;
-          col += 3;
-        }
+    if (sigma_only) {
+      head_col(h, 3, col, HA_NONE);
+      col += 1;
+    } else {
+      for (int i = 0; i < 3; ++i) head_col(h, i, col + i, HA_SIGMOID);
+      head_col(h, 3, col + 3, HA_NONE);
+      col += 4;
+      if (want_fw) {
+        for (int i = 0; i < 3; ++i) head_col(h, 4 + i, col + i, HA_FLOW);
+        col += 3;
+      }
+      if (want_bw) {
+        for (int i = 0; i < 3; ++i) head_col(h, 7 + i, col + i, HA_FLOW);
+        col += 3;
       }
     }
   }
   if (overflow) return NSFF_EUNSUPPORTED;
+  // Which accumulators must the issuer explicitly wait to be drained before overwriting them?  The drain of a hidden
+  // accumulator (region r, half h) is implied once any op has waited for "hidden half h of the layer stored there
+  // published" (the epilogue reads the accumulator before it publishes), which the next layer always does; what is
+  // left are the head accumulators (inside the first half of a region) and whatever the walk below finds uncovered.
+  // The table is the same for every tile, so the walk covers two consecutive tiles and keeps the union.
+  {
+    int stored[kAccIds], waited[2] = {-1, -1}, layer = 0, cur_layer = -1;
+    for (int i = 0; i < kAccIds; ++i) stored[i] = -1;
+    bool head_pending = false;
+    int head_region = -1;
+    for (int pass = 0; pass < 2; ++pass)
+      for (int i = 0; i < n_ops; ++i) {
+        ChunkOp& o = P.ops[i];
+        const OpMeta& m = meta[i];
+        if (m.waits_half >= 0) waited[m.waits_half] = cur_layer;
+        if (m.first) {
+          uint8_t mask = 0;
+          if (m.head) {
+            if (head_pending) mask |= 1u << kHeadAcc;            // previous head accumulator (same barrier pair)
+            head_pending = true;
+            head_region = (o.d_col >> 8) & 1;
+          } else {
+            const int h = m.acc & 1, r = m.acc >> 1;
+            if (stored[m.acc] >= 0 && waited[h] < stored[m.acc]) mask |= 1u << m.acc;
+            if (head_pending && h == 0 && r == head_region) mask |= 1u << kHeadAcc, head_pending = false;
+            stored[m.acc] = layer;
+          }
+          o.wait_empty |= mask;
+        }
+        if (o.flags & OP_ADV_HID) cur_layer = layer++;
+      }
+  }
+  {
+    uint32_t waited_accs = 0;
+    for (int i = 0; i < n_ops; ++i) waited_accs |= P.ops[i].wait_empty;
+    for (int i = 0; i < n_subs; ++i) P.subs[i].arrive_empty = (waited_accs >> P.subs[i].acc_id) & 1u;
+  }
   P.n_subs = n_subs;
   P.n_ops = n_ops;
   *n_out_cols = col;
   return NSFF_OK;
-}
-
-static bool env_flag(const char* name, bool dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) != 0 : dflt;
 }
 
 static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdParams& P, int out_mask, int64_t B,
@@ -1066,8 +1182,8 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
     SL = save_layout(desc, B, out_mask);
     P.save_base = static_cast<uint8_t*>(save);
   }
-  // NSFF_TC_SPLIT=0 selects whole-layer accumulators (N = 256 MMAs; A/B experiments)
-  rc = build_program(*desc, L, out_mask, env_flag("NSFF_TC_SPLIT", true), P, &ncols, save ? &SL : nullptr);
+  const bool split = true;       // every 256-wide layer = two N = 128 sub-steps (file header)
+  rc = build_program(*desc, L, out_mask, split, P, &ncols, save ? &SL : nullptr);
   if (rc != NSFF_OK) return rc;
   if (out_ld < ncols) return NSFF_EINVAL;
   int dev = 0, major = 0, sms = 0;
@@ -1077,10 +1193,13 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
   NSFF_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   P.pack = static_cast<const uint8_t*>(pack);
   P.bias = reinterpret_cast<const float*>(P.pack + L.bias_base);
+  P.n_bias = (int32_t)L.n_bias;
+  if ((uint32_t)P.n_bias * 4u > kSmemBias) return NSFF_EUNSUPPORTED;
   P.out = out;
   P.out_ld = out_ld;
   P.n_tiles = (int)cdiv64(B, kTileM);
   P.flow_scale = desc->flow_scale;
+  P.stage_bytes = split ? 16384u : 32768u;
   int max_ctas = sms;
   if (const char* cap = getenv("NSFF_MAX_CTAS")) {          // experiment knob: fewer resident CTAs
     int c = atoi(cap);
@@ -1090,7 +1209,7 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
 #ifdef NSFF_TIMELINE
   const char* tl_path = getenv("NSFF_TIMELINE_OUT");
   unsigned long long* tl_dev = nullptr;
-  const size_t tl_bytes = (size_t)3 * 2 * kDbgPerRole * sizeof(unsigned long long);
+  const size_t tl_bytes = (size_t)3 * kDbgPerRole * sizeof(unsigned long long);
   if (tl_path) {
     NSFF_CUDA_TRY(cudaMalloc(&tl_dev, tl_bytes));
     NSFF_CUDA_TRY(cudaMemsetAsync(tl_dev, 0, tl_bytes, st));
@@ -1098,6 +1217,7 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
   }
 #endif
   const bool appear = P.need_a != 0;
+  P.n_stages = (int)((appear ? Cfg<true>::kSmemB : Cfg<false>::kSmemB) / P.stage_bytes);
   auto launch_pair = [&](auto kern, uint32_t smem) -> int {
     NSFF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int n_pairs = (P.n_tiles + 1) / 2;

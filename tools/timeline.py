@@ -1,9 +1,12 @@
 #!/usr/bin/env python
 """In-kernel timeline of field_forward_kernel (CTA 0), for finding what the tensor pipe waits on.
 
-  here:   NSFF_NVCC_EXTRA=-DNSFF_TIMELINE python -m nsff_pl_b200.build     (then rebuild normally afterwards!)
-  gpu:    python tools/timeline.py run gpurun_out/tl          -> gpurun_out/tl.<launch>.bin
-  here:   python tools/timeline.py show gpurun_out/tl.0.bin [first_step last_step]
+  here:   NSFF_LIB_OUT=$PWD/nsff_pl_b200/libnsff_b200_tl.so NSFF_NVCC_EXTRA=-DNSFF_TIMELINE python -m nsff_pl_b200.build
+  gpu:    NSFF_LIB=$PWD/nsff_pl_b200/libnsff_b200_tl.so python tools/timeline.py run gpurun_out/tl    -> gpurun_out/tl.<launch>.bin
+  here:   python tools/timeline.py show gpurun_out/tl.0.bin [first_sub last_sub]
+
+Events are logged to shared memory (8 bytes: tag << 40 | clock) and dumped when each role ends; 512 events per role
+(0 = producer, 1 = MMA issuer, 2 = epilogue warp 0).  tag = global sub-step index << 8 | slice << 4 | event.
 """
 import os
 import struct
@@ -12,10 +15,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-PER = 8192
-EV = {1: "prod: stage free, copy issued", 2: "mma: chunk top", 3: "mma: A chunk ready", 4: "mma: weights ready, issue",
-      8: "mma: elected", 9: "mma: 1st issued", 10: "mma: all issued", 11: "mma: committed", 5: "epi: wait acc", 6: "epi: acc complete", 7: "epi: hidden chunk published", 12: "epi: prologue published",
-      13: "epi: tile start", 14: "mma: acc slot free", 15: "mma: prologue ready"}
+PER = 512
+EV = {1: "prod: stage free, copy issued", 3: "mma: A ready", 4: "mma: weights ready, issue", 11: "mma: sub-step committed",
+      5: "epi: wait acc", 6: "epi: acc complete", 7: "epi: hidden half published", 13: "epi: tile start",
+      14: "mma: accumulators free", 15: "mma: prologue ready"}
 
 
 def run(prefix):
@@ -37,11 +40,11 @@ def load(path):
     vals = struct.unpack(f"<{len(raw) // 8}Q", raw)
     ev = []
     for role in range(3):
-        base = role * 2 * PER
         for i in range(PER):
-            tag, clk = vals[base + 2 * i], vals[base + 2 * i + 1]
-            if clk == 0:
+            v = vals[role * PER + i]
+            if v == 0:
                 break
+            tag, clk = v >> 40, v & 0xFFFFFFFFFF
             ev.append((clk, role, tag >> 8, (tag >> 4) & 15, tag & 15))
     ev.sort()
     return ev
@@ -56,16 +59,11 @@ def show(path, s0=0, s1=10**9):
             continue
         d = clk - last.get(role, clk)
         last[role] = clk
-        print(f"{clk - t0:9d}  (+{d:6d})  step {step:3d} kc {kc}  {EV.get(e, e)}")
-    # per-step summary: mma first issue -> next step first issue
-    issues = [(clk, step, kc) for clk, role, step, kc, e in ev if e == 4]
-    per_step = {}
-    for clk, step, kc in issues:
-        per_step.setdefault(step, []).append(clk)
-    steps = sorted(per_step)
-    print("\nstep: first-issue -> last-issue span, gap to next step's first issue")
-    for a, b in zip(steps, steps[1:]):
-        print(f"  step {a:3d}: chunks {len(per_step[a])}  span {per_step[a][-1] - per_step[a][0]:6d}  next-first - this-first {per_step[b][0] - per_step[a][0]:6d}")
+        print(f"{clk - t0:9d}  (+{d:6d})  sub {step:3d} sl {kc}  {EV.get(e, e)}")
+    commits = [(clk, step) for clk, role, step, kc, e in ev if e == 11]
+    print("\nsub-step: commit -> next commit")
+    for (c0, a), (c1, b) in zip(commits, commits[1:]):
+        print(f"  sub {a:3d}: {c1 - c0:6d}")
 
 
 if __name__ == "__main__":

@@ -147,7 +147,7 @@ int main() {
   unsigned int* d_it;
   cudaMalloc(&d_it, 148 * sizeof(unsigned int));
   for (int traffic = 1; traffic < 2; ++traffic)
-    for (int n : {256, 128})
+    for (int n : {256, 128, 64, 32, 16})
       for (int ts = 0; ts < 2; ++ts) {
         run<1>(n, ts, traffic, d_cyc, d_it);
         run<2>(n, ts, traffic, d_cyc, d_it);
