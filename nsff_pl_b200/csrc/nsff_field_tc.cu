@@ -177,9 +177,9 @@ constexpr int kThreads = (kEpiWarps + 2) * 32;
 constexpr uint32_t kChunkBytes = 128 * 128;          // 128 rows x 64 bf16
 constexpr uint32_t kSmemBias = 20 * 1024;            // the module's whole fp32 bias table (4912 floats), resident
 constexpr uint32_t kSmemBar = 512;
-constexpr int kMaxStages = 10;
+constexpr int kMaxStages = 18;
 constexpr int kMaxSubs = 44;                         // sub-steps per tile (main pass, split: 19 x 2 + 3 heads = 41)
-constexpr int kMaxOps = 96;                          // ops per tile (main pass, split: 84)
+constexpr int kMaxOps = 176;                         // ops per tile (main pass, one K-chunk per op: 164 with the appearance chunk)
 constexpr int kAccIds = 5;                           // accumulators with their own full/empty barriers: X.h0 X.h1 Y.h0 Y.h1 head
 constexpr int kHeadAcc = 4;
 
@@ -608,17 +608,17 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
         for (int unit = group; unit < n_units; unit += n_groups, ++unit_iter) {
           mbar_wait(bar(BAR_EXTRA_FULL), unit_iter & 1u);
           NSFF_TL((gsub << 8) | 15);                           // mma: prologue chunks ready
+          // Software pipeline: while the tensor pipe works through the first MMA group of op i, the stage of op i-1 is
+          // released, op i+1 is fetched and decoded and its barriers are probed; between the last MMA of op i and the
+          // first MMA of op i+1 only the probe results are looked at.
           uint4 op = reinterpret_cast<const uint4*>(&P.ops[0])[0];
           uint32_t wh = (op.w >> 8) & 0xFFu;
-          bool hid_ok = wh == 0 || mbar_try_wait(bar(BAR_HID_FULL + wh - 1), (hid_gen - 1u) & 1u);
-          bool w_ok = mbar_try_wait(bar(BAR_W_FULL + stage), wpar);
+          bool hid_ok = wh == 0 || mbar_test(bar(BAR_HID_FULL + wh - 1), (hid_gen - 1u) & 1u);
+          bool w_ok = mbar_test(bar(BAR_W_FULL + stage), wpar);
+          uint32_t pending_empty = 0;                          // W_EMPTY barrier of the previous op, committed late
           for (int i = 0; i < n_ops; ++i) {
             const uint4 cur = op;
             const uint32_t flags = cur.w & 0xFFu, acc = (cur.w >> 16) & 0xFFu;
-            // the next op is fetched now; its barrier probes are issued BETWEEN the two MMA groups below, so neither the
-            // constant load nor the probes' round trips sit between the last MMA of this op and the first of the next
-            const int i_next = i + 1 < n_ops ? i + 1 : i;
-            op = reinterpret_cast<const uint4*>(&P.ops[i_next])[0];
             uint32_t we = cur.w >> 24;
             while (we) {
               // accumulators this sub-step overwrites whose drain no earlier wait implies (head accumulators; rare)
@@ -651,10 +651,14 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
               mma_bf16_ss_pair(d_tmem, desc(a1 + 4), desc(b_lo + 4), idesc, 1u);
               mma_bf16_ss_pair(d_tmem, desc(a1 + 6), desc(b_lo + 6), idesc, 1u);
             }
-            // early probes for the next op (the tensor pipe is working through the MMAs just queued)
+            // the previous op's weight stage (its MMAs precede the ones just issued: released at most four MMAs late)
+            if (pending_empty) mma_commit_pair_mc(pending_empty, 3);
+            // next op: fetch, probe (the tensor pipe is working through the MMAs just queued)
+            const int i_next = i + 1 < n_ops ? i + 1 : i;
+            op = reinterpret_cast<const uint4*>(&P.ops[i_next])[0];
             wh = (op.w >> 8) & 0xFFu;
-            hid_ok = wh == 0 || mbar_try_wait(bar(BAR_HID_FULL + wh - 1), (hid_gen - 1u) & 1u);
-            w_ok = mbar_try_wait(bar(BAR_W_FULL + stage), wpar);
+            hid_ok = wh == 0 || mbar_test(bar(BAR_HID_FULL + wh - 1), (hid_gen - 1u) & 1u);
+            w_ok = mbar_test(bar(BAR_W_FULL + stage), wpar);
             if (two) {
               if (ts) {
                 mma_bf16_ts_pair(d_tmem, a2, desc(b_lo2), idesc, 1u);
@@ -668,14 +672,15 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
                 mma_bf16_ss_pair(d_tmem, desc(a2 + 6), desc(b_lo2 + 6), idesc, 1u);
               }
             }
-            mma_commit_pair_mc(empty_bar, 3);                  // frees the stage in BOTH CTAs
+            pending_empty = empty_bar;
             if (flags & OP_LAST) {
-              mma_commit_pair_mc(bar(BAR_ACC_FULL + acc), 3);
+              mma_commit_pair_mc(bar(BAR_ACC_FULL + acc), 3);  // (the epilogue is waiting for this one: not deferred)
               fill_par ^= 1u << acc;
               NSFF_TL((gsub << 8) | 11);                       // mma: sub-step committed
               ++gsub;
             }
           }
+          if (pending_empty) mma_commit_pair_mc(pending_empty, 3);
         }
         NSFF_TL_DUMP();
       }
@@ -967,7 +972,7 @@ extern "C" int nsff_field_pack(const nsff_field_desc* desc, const nsff_field_par
 
 // Builds the per-tile program: the sub-step table the epilogue warps walk and the flat K-chunk op list the producer
 // and the MMA issuer walk.  `split`: every 256-wide layer becomes two N = 128 sub-steps (see the file header).
-static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_mask, bool split, FwdParams& P,
+static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_mask, bool split, bool fine, FwdParams& P,
                          int* n_out_cols, const SaveLayout* SL) {
   const bool sigma_only = out_mask & NSFF_OUT_SIGMA_ONLY;
   const bool want_s = out_mask & NSFF_OUT_STATIC, want_t = out_mask & NSFF_OUT_TRANSIENT;
@@ -985,7 +990,7 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
     return (uint16_t)((ch - CH_PE) * (int)(kChunkBytes >> 4));                                 // smem, 16-byte units
   };
   // host-only bookkeeping for the drain analysis below
-  struct OpMeta { int acc; bool first, head; int waits_half; };
+  struct OpMeta { int acc; bool first, head; int waits_half; bool needs_hi; };
   OpMeta meta[kMaxOps];
   auto push = [&](int lid, uint8_t epi) -> SubStep* {
     const PackLayer& pl = L.layer[lid];
@@ -996,6 +1001,7 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
     if (n_subs + parts > kMaxSubs) { overflow = true; return nullptr; }
     SubStep* first = &P.subs[n_subs];
     ChunkOp half_ops[2][kMaxChunks];
+    bool seen_half[2] = {false, false};
     OpMeta half_meta[2][kMaxChunks];
     int n_half = 0;
     for (int h = 0; h < parts; ++h) {
@@ -1036,7 +1042,7 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
         const bool hidden = ch < CH_PE;
         if (hidden && cur < 0) { overflow = true; return nullptr; }
         // two consecutive K-chunks of the same kind share an op: (H0,H1) (H2,H3) / (H3,H2) (H1,H0) / (PE,T) / (DIR,A)
-        const bool two = kc + 1 < pl.nchunks && ((pl.chunk[kc + 1] < CH_PE) == hidden) &&
+        const bool two = !(fine && !head) && kc + 1 < pl.nchunks && ((pl.chunk[kc + 1] < CH_PE) == hidden) &&
                          (hidden ? (pl.chunk[kc + 1] >> 1) == (ch >> 1) : pl.chunk[kc + 1] == ch + 1);
         o.idesc = make_idesc_bf16(2 * kTileM, (uint32_t)n);
         o.a = a_of(ch);
@@ -1052,8 +1058,10 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
           o.w_src1 = o.w_src0 + block_bytes;
         }
         m.acc = s.acc_id, m.first = kc == 0, m.head = head, m.waits_half = -1;
+        m.needs_hi = hidden && (ch >> 1) == 1;
         if (hidden) {
-          if (h == 0) o.wait_hid = (uint8_t)(1 + (ch >> 1)), m.waits_half = ch >> 1;   // h = 1 issues later: already awaited
+          // only the first op of the layer that reads a hidden half waits for it (half 1's ops issue later)
+          if (h == 0 && !seen_half[ch >> 1]) o.wait_hid = (uint8_t)(1 + (ch >> 1)), m.waits_half = ch >> 1, seen_half[ch >> 1] = true;
         } else {
           P.last_extra_sub = n_subs + h;
         }
@@ -1063,15 +1071,34 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
       }
       n_half = k;
     }
-    // Issue order inside a layer: op k of half 0, op k of half 1, op k+1 of half 0, ... - the ops that read channels
-    // 0-127 of the previous layer run for BOTH halves (2 x 8 MMAs) before anything needs channels 128-255, which the
-    // epilogue of the previous layer's second half is still producing.
-    for (int k = 0; k < n_half; ++k)
-      for (int h = 0; h < parts; ++h) {
-        if (n_ops >= kMaxOps) { overflow = true; return nullptr; }
-        meta[n_ops] = half_meta[h][k];
-        P.ops[n_ops++] = half_ops[h][k];
+    // Issue order inside a layer.  The ops that read channels 0-127 of the previous layer run before anything needs
+    // channels 128-255, which the epilogue of the previous layer's second half is still producing; and half 0 of THIS
+    // layer finishes while three ops of half 1 are still to come, so that its epilogue (whose result the next layer's
+    // first ops need) has cover too:      a0 b0 a1 | a2 a3 | b1 b2 b3        (a = half 0, b = half 1, one K-chunk each).
+    // With two-chunk ops (fine = false) this degenerates to a01 b01 a23 b23.
+    auto emit = [&](int h, int k) {
+      if (n_ops >= kMaxOps) { overflow = true; return; }
+      meta[n_ops] = half_meta[h][k];
+      P.ops[n_ops++] = half_ops[h][k];
+    };
+    if (parts == 1) {
+      for (int k = 0; k < n_half; ++k) emit(0, k);
+    } else {
+      int n_pre = 0;
+      while (n_pre < n_half && !half_meta[0][n_pre].needs_hi) ++n_pre;
+      const int hold = (fine && n_pre < n_half && n_pre > 0) ? 1 : 0;     // ops of half 1 kept back to cover half 0's epilogue
+      for (int k = 0; k < n_pre; ++k) {
+        emit(0, k);
+        if (k < n_pre - hold) emit(1, k);
       }
+      if (fine) {
+        for (int k = n_pre; k < n_half; ++k) emit(0, k);
+        for (int k = n_pre - hold; k < n_half; ++k) emit(1, k);
+      } else {
+        for (int k = n_pre; k < n_half; ++k) emit(0, k), emit(1, k);
+      }
+    }
+    if (overflow) return nullptr;
     if (!head) P.ops[n_ops - 1].flags |= OP_ADV_HID;
     n_subs += parts;
     if (!head) cur = region;
@@ -1183,7 +1210,11 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
     P.save_base = static_cast<uint8_t*>(save);
   }
   const bool split = true;       // every 256-wide layer = two N = 128 sub-steps (file header)
-  rc = build_program(*desc, L, out_mask, split, P, &ncols, save ? &SL : nullptr);
+  // default: two K-chunks (8 MMAs) per op, issue order a01 b01 a23 b23.  NSFF_TC_FINE=1: one K-chunk per op, order
+  // a0 b0 a1 | a2 a3 | b1 b2 b3 (more cover for the first half's epilogue, but twice the per-op issue overhead: measured slower)
+  const char* fe = getenv("NSFF_TC_FINE");
+  const bool fine = fe ? atoi(fe) != 0 : false;
+  rc = build_program(*desc, L, out_mask, split, fine, P, &ncols, save ? &SL : nullptr);
   if (rc != NSFF_OK) return rc;
   if (out_ld < ncols) return NSFF_EINVAL;
   int dev = 0, major = 0, sms = 0;
@@ -1199,7 +1230,7 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
   P.out_ld = out_ld;
   P.n_tiles = (int)cdiv64(B, kTileM);
   P.flow_scale = desc->flow_scale;
-  P.stage_bytes = split ? 16384u : 32768u;
+  P.stage_bytes = fine ? 8192u : 16384u;          // one or two 8 KB weight pieces per op
   int max_ctas = sms;
   if (const char* cap = getenv("NSFF_MAX_CTAS")) {          // experiment knob: fewer resident CTAs
     int c = atoi(cap);

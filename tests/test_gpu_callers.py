@@ -1,0 +1,139 @@
+"""GPU: the reference's two callers, driven over `install_as_reference_modules()`:
+
+  * eval.f (eval.py:81-110): test_time=True, ragged last chunk, per-chunk view_dir slices, EVERY value .cpu()'d and
+    concatenated - against the unmodified reference's render_rays run on the CPU on the whole batch;
+  * NSFFSystem.forward + training_step (train.py:99-123,178-198): chunked train-mode forward, the reference's NeRFWLoss
+    (losses.py:31-171, unmodified, staged in baseline/_ref) on OUR result dict on the GPU, loss.backward() through the
+    hand-written backward - every parameter gradient against the reference's own autograd (reference render_rays +
+    the same loss on the CPU).
+"""
+import sys
+
+import pytest
+import torch
+
+from oracle import ref_loader
+from parity_util import build_fields, compare_dicts, synthetic_rays
+from tolerances import FP32_TOL, FP32_WARP_TOL
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not (ref_loader.available() or ref_loader.stage()), reason="reference not staged")]
+
+TRAIN_KW = dict(output_transient=True, output_transient_flow=["fw", "bw", "disocc"])
+
+
+@pytest.fixture()
+def installed():
+    import nsff_pl_b200
+    saved = {k: sys.modules.get(k) for k in ("models", "models.nerf", "models.rendering")}
+    for k in saved:
+        sys.modules.pop(k, None)
+    nsff_pl_b200.install_as_reference_modules()
+    from models.rendering import render_rays          # what train.py / eval.py import
+    assert render_rays.__module__ == "nsff_pl_b200.models.rendering"
+    yield render_rays
+    for k, v in saved.items():
+        if v is None:
+            sys.modules.pop(k, None)
+        else:
+            sys.modules[k] = v
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_eval_f_over_the_installed_modules(installed, precision):
+    import ref_harness as H
+    from tolerances import BF16_TOL
+    ref = ref_loader.load()
+    models, emb, _, _ = build_fields(W=256, seed=21, precision=precision, n_frames=8)
+    rmodels, remb = ref_loader.build_reference_fields(models, emb)
+    rays, ts = synthetic_rays(37, n_frames=8, seed=22)
+    view_dir = torch.nn.functional.normalize(torch.randn(37, 3, generator=torch.Generator().manual_seed(1)), dim=-1)
+    kw = dict(output_transient_flow=["fw", "bw"])
+    got = H.eval_f(installed, models, emb, rays.cuda(), ts.cuda(), 7, 24, 0, 16, view_dir=view_dir.cuda(), **kw)
+    want = H.eval_f(ref.rendering.render_rays, rmodels, remb, rays, ts, 7, 24, 0, 64, view_dir=view_dir, **kw)
+    assert all(v.device.type == "cpu" for v in got.values())            # eval.py:106-107
+    tol, default = (FP32_WARP_TOL, FP32_TOL) if precision == "fp32" else (BF16_TOL, None)
+    compare_dicts(got, want, tol, default_tol=default)
+
+
+def test_eval_f_hierarchical_fp32(installed):
+    """coarse + fine (eval.py's default N_importance > 0 path): keys, shapes, host tensors; per-ray outputs close."""
+    import ref_harness as H
+    ref = ref_loader.load()
+    models, emb, _, _ = build_fields(W=256, coarse=True, seed=23, precision="fp32", n_frames=8)
+    rmodels, remb = ref_loader.build_reference_fields(models, emb)
+    rays, ts = synthetic_rays(21, n_frames=8, seed=24)
+    got = H.eval_f(installed, models, emb, rays.cuda(), ts.cuda(), 7, 16, 8, 8, output_transient_flow=["fw", "bw"])
+    want = H.eval_f(ref.rendering.render_rays, rmodels, remb, rays, ts, 7, 16, 8, 64, output_transient_flow=["fw", "bw"])
+    assert list(got) == list(want)
+    for k in want:
+        assert got[k].shape == want[k].shape and got[k].device.type == "cpu", k
+    for k in ("rgb_fine", "depth_fine", "transient_flow_fw"):
+        assert float((got[k] - want[k]).abs().max()) <= 2e-2, k          # resampling is ill-conditioned
+
+
+def _grad_errors(models, rmodels, emb, remb):
+    errs = {}
+    for key, m in models.items():
+        ref_params = dict(rmodels[key].named_parameters())
+        for name, p in m.named_parameters():
+            rg = ref_params[name].grad
+            if rg is None:
+                assert p.grad is None or float(p.grad.abs().max()) == 0.0, f"{key}.{name}: unexpected gradient"
+                continue
+            assert p.grad is not None, f"{key}.{name}: missing gradient"
+            g, r = p.grad.detach().cpu().double(), rg.double()
+            errs[f"{key}.{name}"] = float((g - r).norm() / (r.norm() + 1e-12))
+    g, r = emb["t"].weight.grad.cpu().double(), remb["t"].weight.grad.double()
+    errs["embedding_t"] = float((g - r).norm() / (r.norm() + 1e-12))
+    return errs
+
+
+@pytest.mark.parametrize("precision,tol,median_tol", [("fp32", 2e-2, 2e-3), ("bf16", 0.25, None)])
+def test_training_step_with_the_reference_loss(installed, precision, tol, median_tol):
+    """SURVEY section 8d cfg 3: the reference's loss, unchanged, on our result dict; gradients vs the reference's
+    autograd.  fp32 = verification path (<= 2e-2, median <= 2e-3: ReLU masks of units within rounding of zero differ);
+    bf16 = tensor-core forward + tensor-core backward on default-initialised weights (documented envelope of
+    tests/test_gpu_backward.py: 0.2 per tensor; 0.25 here because the loss adds |.|-type terms)."""
+    import parity_util
+    import ref_harness as H
+    ref = ref_loader.load()
+    real = parity_util.energise_
+    if precision == "bf16":
+        parity_util.energise_ = lambda m, **k: m
+    try:
+        models, emb, _, _ = build_fields(W=256, seed=31, precision=precision, n_frames=8)
+    finally:
+        parity_util.energise_ = real
+    rmodels, remb = ref_loader.build_reference_fields(models, emb)
+    for mm in (models, rmodels):
+        for m in mm.values():
+            m.requires_grad_(True)
+    emb["t"].weight.requires_grad_(True)
+    remb["t"].weight.requires_grad_(True)
+    R, S = 40, 24
+    rays, ts = synthetic_rays(R, n_frames=8, seed=32)
+    batch = H.make_batch(rays, ts, img_wh=(64, 36), seed=33)
+    kwargs = dict(epoch=4, **TRAIN_KW)
+
+    res = H.system_forward(installed, models, emb, rays.cuda(), ts.cuda(), 8, S, 0, 0, 0, 16, **kwargs)   # chunks 16,16,8
+    loss_fn = H.make_loss(ref, 8, img_wh=(64, 36), device="cuda")
+    terms = loss_fn(res, H.to_device(batch, "cuda"), **kwargs)
+    loss = sum(terms.values())
+    loss.backward()
+    torch.cuda.synchronize()
+
+    rres = H.system_forward(ref.rendering.render_rays, rmodels, remb, rays, ts, 8, S, 0, 0, 0, 64, **kwargs)
+    rterms = H.make_loss(ref, 8, img_wh=(64, 36))(rres, batch, **kwargs)
+    rloss = sum(rterms.values())
+    rloss.backward()
+
+    assert set(terms) == set(rterms)
+    for k in rterms:
+        assert abs(float(terms[k]) - float(rterms[k])) <= (2e-3 if precision == "fp32" else 5e-2) * max(1.0, abs(float(rterms[k]))), k
+    errs = _grad_errors(models, rmodels, emb, remb)
+    bad = {k: v for k, v in errs.items() if v > tol}
+    assert not bad, f"relative gradient errors above {tol}: {bad}"
+    if median_tol is not None:
+        med = sorted(errs.values())[len(errs) // 2]
+        assert med <= median_tol, f"median relative gradient error {med:.3e}"
