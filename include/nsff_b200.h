@@ -120,7 +120,11 @@ enum {
   NSFF_OUT_TRANSIENT   = 2,   /* transient rgb(3) + raw sigma(1)                            */
   NSFF_OUT_FLOW_FW     = 4,   /* + flow_scale*tanh fw(3)                                    */
   NSFF_OUT_FLOW_BW     = 8,   /* + flow_scale*tanh bw(3)                                    */
-  NSFF_OUT_SIGMA_ONLY  = 16   /* coarse@test: raw sigmas only (static [, transient])        */
+  NSFF_OUT_SIGMA_ONLY  = 16,  /* coarse@test: raw sigmas only (static [, transient])        */
+  NSFF_OUT_EVERY_LAYER = 32   /* evaluate xyz_encoding_final as its own layer (training forward: its output is an
+                                 activation the backward differentiates).  Without it the tensor-core path folds
+                                 that activation-free layer into the one after it (same function, one bf16
+                                 rounding less); the fp32 path ignores the flag. */
 };
 
 /* Per-point inputs for the fused renderer entry (PE computed in-kernel; rendering.py:164-175,

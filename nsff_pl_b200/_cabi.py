@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # NSFF_LIB: an alternative build of the same library (e.g. the -DNSFF_TIMELINE build of tools/timeline.py)
 LIB_PATH = os.environ.get("NSFF_LIB") or os.path.join(_HERE, "libnsff_b200.so")
 
-OUT_STATIC, OUT_TRANSIENT, OUT_FLOW_FW, OUT_FLOW_BW, OUT_SIGMA_ONLY = 1, 2, 4, 8, 16
+OUT_STATIC, OUT_TRANSIENT, OUT_FLOW_FW, OUT_FLOW_BW, OUT_SIGMA_ONLY, OUT_EVERY_LAYER = 1, 2, 4, 8, 16, 32
 
 _lib = None
 

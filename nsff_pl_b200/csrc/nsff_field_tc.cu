@@ -57,7 +57,9 @@ using namespace sm100;
 enum ChunkId : uint8_t { CH_H0 = 0, CH_H1, CH_H2, CH_H3, CH_PE, CH_T, CH_DIR, CH_A, CH_NONE = 255 };
 enum LayerId {
   L_S1 = 0, L_S2, L_S3, L_S4, L_S5, L_S6, L_S7, L_S8, L_SSIG, L_SFIN, L_SDIR, L_SRGB,
-  L_T1, L_T2, L_T3, L_T4, L_T5, L_T6, L_T7, L_T8, L_TFIN, L_THEAD, L_COUNT
+  L_T1, L_T2, L_T3, L_T4, L_T5, L_T6, L_T7, L_T8, L_TFIN, L_THEAD,
+  // inference-only blocks with the activation-free 256x256 "final" layer folded in (see build_layout)
+  L_SDIRM, L_SRGBM, L_THEADM, L_COUNT
 };
 enum Epi : uint8_t { EPI_RELU_HID = 0, EPI_LIN_HID = 1, EPI_HEAD = 2 };
 enum HeadAct : uint8_t { HA_NONE = 0, HA_SIGMOID = 1, HA_FLOW = 2 };
@@ -79,6 +81,10 @@ struct PackLayout {
   uint32_t n_bias;      // floats
   size_t bytes;
 };
+// fp32 scratch behind the image (and the job table) for the folded products: dir layer (256 x 331 + 256), transient
+// heads (16 x 256 + 16), static rgb head without view directions (16 x 256 + 16)
+constexpr size_t kMergeScratchFloats = 256 * 331 + 256 + 2 * (16 * 256 + 16);
+
 
 static int build_layout(const nsff_field_desc& d, PackLayout& L) {
   if (d.W != 256 || d.D != 8 || d.skip != 4 || d.in_xyz != 63) return NSFF_EUNSUPPORTED;
@@ -125,6 +131,18 @@ static int build_layout(const nsff_field_desc& d, PackLayout& L) {
     add(L_TFIN, 256, {CH_H0, CH_H1, CH_H2, CH_H3});
     add(L_THEAD, 16, {CH_H3, CH_H2, CH_H1, CH_H0});
   }
+  // Folded blocks (inference).  xyz_encoding_final has no activation (nerf.py:84,107), so the layer after it can
+  // absorb it exactly:  W2 (Wf h + bf) + b2 = (W2 Wf) h + (b2 + W2 bf).  The static dir layer (or, without view
+  // directions, the rgb head) and the transient head block then read the trunk's last hidden layer directly: one
+  // 256x256 layer less per branch (65,536 of 630,016 / 583,680 MACs per point).  nsff_field_pack() computes the
+  // products in fp32 on the device and rounds them to bf16 once, like every other weight.
+  if (d.use_viewdir) {
+    if (d.in_a > 0) add(L_SDIRM, 256, {CH_DIR, CH_A, CH_H0, CH_H1, CH_H2, CH_H3});
+    else add(L_SDIRM, 256, {CH_DIR, CH_H0, CH_H1, CH_H2, CH_H3});
+  } else {
+    add(L_SRGBM, 16, {CH_H3, CH_H2, CH_H1, CH_H0});
+  }
+  if (d.has_transient) add(L_THEADM, 16, {CH_H3, CH_H2, CH_H1, CH_H0});
   L.bias_base = off;
   L.n_bias = boff;
   L.bytes = (size_t)off + (size_t)boff * 4;
@@ -144,7 +162,7 @@ struct PackJob {
   int32_t cols;       // valid source columns (the rest of the 64 are zero)
   int32_t is_bias;
 };
-constexpr int kMaxPackJobs = 160;
+constexpr int kMaxPackJobs = 200;
 struct PackJobs {
   PackJob job[kMaxPackJobs];
 };
@@ -168,6 +186,43 @@ __global__ void pack_kernel(const PackJobs* __restrict__ jobs_dev, uint8_t* __re
   }
 }
 
+
+// out[n, k] = sum_j A[n, j] * B[j, k]   (n < rows, j < 256, k < 256),  out_bias[n] = a_bias[n] + sum_j A[n, j] * b_bias[j]:
+// a linear layer (B, b_bias) folded into the rows of the layer after it (A, a_bias); fp32, one block per output row.
+struct MergeJob {
+  const float* A;        // (rows, lda): the columns that multiply the folded layer's output
+  const float* a_bias;   // (rows)
+  const float* B;        // (256, 256) row-major (out, in) weight of the folded layer
+  const float* b_bias;   // (256)
+  float* out;            // (rows, ldo)
+  float* out_bias;       // (rows)
+  int32_t lda, ldo, rows;
+};
+constexpr int kMaxMergeJobs = 8;
+struct MergeJobs {
+  MergeJob job[kMaxMergeJobs];
+};
+__global__ void __launch_bounds__(256) merge_linear_kernel(const __grid_constant__ MergeJobs JJ) {
+  const MergeJob& J = JJ.job[blockIdx.y];
+  const int n = blockIdx.x, k = threadIdx.x;
+  if (n >= J.rows) return;
+  __shared__ float a_row[256];
+  __shared__ float red[256];
+  a_row[k] = J.A[(int64_t)n * J.lda + k];
+  __syncthreads();
+  float acc = 0.f;
+#pragma unroll 8
+  for (int j = 0; j < 256; ++j) acc = fmaf(a_row[j], J.B[j * 256 + k], acc);
+  J.out[(int64_t)n * J.ldo + k] = acc;
+  red[k] = a_row[k] * J.b_bias[k];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (k < s) red[k] += red[k + s];
+    __syncthreads();
+  }
+  if (k == 0) J.out_bias[n] = J.a_bias[n] + red[0];
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward kernel
 // ---------------------------------------------------------------------------------------------
@@ -175,7 +230,7 @@ constexpr int kTileM = 128;
 constexpr int kEpiWarps = 16;        // 4 TMEM lane quadrants x 4 column parts
 constexpr int kThreads = (kEpiWarps + 2) * 32;
 constexpr uint32_t kChunkBytes = 128 * 128;          // 128 rows x 64 bf16
-constexpr uint32_t kSmemBias = 20 * 1024;            // the module's whole fp32 bias table (4912 floats), resident
+constexpr uint32_t kSmemBias = 21 * 1024;            // the module's whole fp32 bias table (<= 5200 floats), resident
 constexpr uint32_t kSmemBar = 512;
 constexpr int kMaxStages = 18;
 constexpr int kMaxSubs = 44;                         // sub-steps per tile (main pass, split: 19 x 2 + 3 heads = 41)
@@ -877,7 +932,7 @@ extern "C" int nsff_field_pack_bytes(const nsff_field_desc* desc, size_t* bytes)
   int rc = build_layout(*desc, L);
   if (rc != NSFF_OK) return rc;
   // the job table of nsff_field_pack() is staged right after the image
-  *bytes = ((L.bytes + 1023) & ~(size_t)1023) + sizeof(PackJobs);
+  *bytes = ((L.bytes + 1023) & ~(size_t)1023) + ((sizeof(PackJobs) + 1023) & ~(size_t)1023) + kMergeScratchFloats * sizeof(float);
   return NSFF_OK;
 }
 
@@ -889,8 +944,11 @@ extern "C" int nsff_field_pack(const nsff_field_desc* desc, const nsff_field_par
   int rc = build_layout(*desc, L);
   if (rc != NSFF_OK) return rc;
   const size_t jobs_off = (L.bytes + 1023) & ~(size_t)1023;
-  if (pack_bytes < jobs_off + sizeof(PackJobs)) return NSFF_EINVAL;
+  const size_t scratch_off = jobs_off + ((sizeof(PackJobs) + 1023) & ~(size_t)1023);
+  if (pack_bytes < scratch_off + kMergeScratchFloats * sizeof(float)) return NSFF_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* p8 = static_cast<uint8_t*>(pack);
+  float* scratch = reinterpret_cast<float*>(p8 + scratch_off);
 
   static thread_local PackJobs jobs;   // host staging; copied synchronously w.r.t. the host below
   int nj = 0;
@@ -959,10 +1017,52 @@ extern "C" int nsff_field_pack(const nsff_field_desc* desc, const nsff_field_par
       bjob(L_THEAD, 7, prm->trans_bw_b, 3);
     }
   }
+  // ---- folded blocks: products in fp32 scratch first, then packed like any other weight ----
+  MergeJobs mj;
+  int nm = 0;
+  auto merge = [&](const float* A, int lda, int rows, const float* a_bias, const float* B, const float* b_bias, float* out,
+                   int ldo, float* out_bias) {
+    if (!A || !a_bias || !B || !b_bias) { missing = true; return; }
+    MergeJob& m = mj.job[nm++];
+    m.A = A, m.lda = lda, m.rows = rows, m.a_bias = a_bias, m.B = B, m.b_bias = b_bias;
+    m.out = out, m.ldo = ldo, m.out_bias = out_bias;
+  };
+  float* m_dir = scratch;                          // (256, 331): [folded 256 | dir 27 | a 48] like static_dir_encoding
+  float* m_dir_b = m_dir + 256 * 331;
+  float* m_th = m_dir_b + 256;                     // (16, 256): rows 0-2 rgb, 3 sigma, 4-6 fw, 7-9 bw
+  float* m_th_b = m_th + 16 * 256;
+  float* m_rgb = m_th_b + 16;                      // (16, 256): rows 0-2 static rgb (no view directions)
+  float* m_rgb_b = m_rgb + 16 * 256;
+  if (desc->use_viewdir) {
+    const int ld = 283 + (desc->in_a > 0 ? 48 : 0);
+    merge(prm->static_dir_w, ld, 256, prm->static_dir_b, prm->static_final_w, prm->static_final_b, m_dir, 331, m_dir_b);
+    const int pre_m[2][2] = {{256, 27}, {283, 48}};
+    int kc = 0;
+    // the dir / appearance columns are taken from the original weight; the hidden columns from the product
+    for (int i = 0; i < (desc->in_a > 0 ? 2 : 1); ++i, ++kc) wjob(L_SDIRM, kc, prm->static_dir_w, ld, 0, 256, pre_m[i][0], pre_m[i][1]);
+    for (int h = 0; h < 4; ++h, ++kc) wjob(L_SDIRM, kc, m_dir, 331, 0, 256, h * 64, 64);
+    bjob(L_SDIRM, 0, m_dir_b, 256);
+  } else {
+    merge(prm->static_rgb_w, 256, 3, prm->static_rgb_b, prm->static_final_w, prm->static_final_b, m_rgb, 256, m_rgb_b);
+    for (int h = 0; h < 4; ++h) wjob(L_SRGBM, 3 - h, m_rgb, 256, 0, 3, h * 64, 64);
+    bjob(L_SRGBM, 0, m_rgb_b, 3);
+  }
+  if (desc->has_transient) {
+    merge(prm->trans_rgb_w, 256, 3, prm->trans_rgb_b, prm->trans_final_w, prm->trans_final_b, m_th, 256, m_th_b);
+    merge(prm->trans_sigma_w, 256, 1, prm->trans_sigma_b, prm->trans_final_w, prm->trans_final_b, m_th + 3 * 256, 256, m_th_b + 3);
+    if (desc->has_flow) {
+      merge(prm->trans_fw_w, 256, 3, prm->trans_fw_b, prm->trans_final_w, prm->trans_final_b, m_th + 4 * 256, 256, m_th_b + 4);
+      merge(prm->trans_bw_w, 256, 3, prm->trans_bw_b, prm->trans_final_w, prm->trans_final_b, m_th + 7 * 256, 256, m_th_b + 7);
+    }
+    const int nrow = desc->has_flow ? 10 : 4;
+    for (int h = 0; h < 4; ++h) wjob(L_THEADM, 3 - h, m_th, 256, 0, nrow, h * 64, 64);
+    bjob(L_THEADM, 0, m_th_b, nrow);
+  }
   if (missing) return NSFF_EINVAL;
-  if (nj > kMaxPackJobs) return NSFF_EUNSUPPORTED;
+  if (nj > kMaxPackJobs || nm > kMaxMergeJobs) return NSFF_EUNSUPPORTED;
 
-  uint8_t* p8 = static_cast<uint8_t*>(pack);
+  merge_linear_kernel<<<dim3(256, nm), 256, 0, st>>>(mj);
+  if (int lrc = after_launch()) return lrc;
   NSFF_CUDA_TRY(cudaMemsetAsync(p8, 0, jobs_off, st));   // zero padding rows/cols and unused bias slots
   NSFF_CUDA_TRY(cudaMemcpyAsync(p8 + jobs_off, &jobs, sizeof(PackJob) * nj, cudaMemcpyHostToDevice, st));
   // (pageable-source cudaMemcpyAsync returns once `jobs` has been staged, so the host copy may be reused)
@@ -972,7 +1072,8 @@ extern "C" int nsff_field_pack(const nsff_field_desc* desc, const nsff_field_par
 
 // Builds the per-tile program: the sub-step table the epilogue warps walk and the flat K-chunk op list the producer
 // and the MMA issuer walk.  `split`: every 256-wide layer becomes two N = 128 sub-steps (see the file header).
-static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_mask, bool split, bool fine, FwdParams& P,
+static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_mask, bool split, bool fine, bool fuse,
+                         FwdParams& P,
                          int* n_out_cols, const SaveLayout* SL) {
   const bool sigma_only = out_mask & NSFF_OUT_SIGMA_ONLY;
   const bool want_s = out_mask & NSFF_OUT_STATIC, want_t = out_mask & NSFF_OUT_TRANSIENT;
@@ -1117,13 +1218,13 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
       col += 1;
     } else {
       head_col(push(L_SSIG, EPI_HEAD), 0, col + 3, HA_NONE);
-      push(L_SFIN, EPI_LIN_HID);
+      if (!fuse) push(L_SFIN, EPI_LIN_HID);
       if (d.use_viewdir) {
-        push(L_SDIR, EPI_RELU_HID);
+        push(fuse ? L_SDIRM : L_SDIR, EPI_RELU_HID);
         P.need_dir = 1;
         P.need_a = d.in_a > 0;
       }
-      SubStep* rg = push(L_SRGB, EPI_HEAD);
+      SubStep* rg = push((fuse && !d.use_viewdir) ? L_SRGBM : L_SRGB, EPI_HEAD);
       for (int i = 0; i < 3; ++i) head_col(rg, i, col + i, HA_SIGMOID);
       col += 4;
     }
@@ -1131,8 +1232,8 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
   if (want_t) {
     P.need_t = 1;
     for (int i = L_T1; i <= L_T8; ++i) push(i, EPI_RELU_HID);
-    push(L_TFIN, EPI_LIN_HID);
-    SubStep* h = push(L_THEAD, EPI_HEAD);
+    if (!fuse) push(L_TFIN, EPI_LIN_HID);
+    SubStep* h = push(fuse ? L_THEADM : L_THEAD, EPI_HEAD);
     if (sigma_only) {
       head_col(h, 3, col, HA_NONE);
       col += 1;
@@ -1214,7 +1315,11 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
   // a0 b0 a1 | a2 a3 | b1 b2 b3 (more cover for the first half's epilogue, but twice the per-op issue overhead: measured slower)
   const char* fe = getenv("NSFF_TC_FINE");
   const bool fine = fe ? atoi(fe) != 0 : false;
-  rc = build_program(*desc, L, out_mask, split, fine, P, &ncols, save ? &SL : nullptr);
+  // Inference folds the activation-free "final" layers into their successors (build_layout); the training forward keeps
+  // them (the backward needs their activations).  NSFF_TC_FUSE=0 disables the folding (A/B, parity experiments).
+  const char* fu = getenv("NSFF_TC_FUSE");
+  const bool fuse = !save && !(out_mask & NSFF_OUT_EVERY_LAYER) && (fu ? atoi(fu) != 0 : true);
+  rc = build_program(*desc, L, out_mask, split, fine, fuse, P, &ncols, save ? &SL : nullptr);
   if (rc != NSFF_OK) return rc;
   if (out_ld < ncols) return NSFF_EINVAL;
   int dev = 0, major = 0, sms = 0;

@@ -75,7 +75,7 @@ class FieldFn(torch.autograd.Function):
             if nbytes:
                 save = torch.empty(nbytes, dtype=torch.uint8, device=pos.device)
         with torch.no_grad():
-            model.run_field(mask, out, pts=pts, save=save)
+            model.run_field(mask, out, pts=pts, save=save, every_layer=True)
         ctx.saved_acts = save
         ctx.model, ctx.mask, ctx.S = model, mask, S
         ctx.save_for_backward(pos, t_code, a_code, dirs, zs, out)

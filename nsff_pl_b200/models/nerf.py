@@ -250,10 +250,25 @@ class NeRF(nn.Module):
                 "nsff_pl_b200: NeRF.forward on a pre-embedded row records no autograd graph - call it under "
                 "torch.no_grad(); training goes through render_rays (models/autograd.py), which is differentiable.")
 
-    def run_field(self, mask, out, pts=None, x=None, save=None):
+    def executed_macs_per_point(self, mask, every_layer=False):
+        """Multiply-accumulates per point the tensor-core kernel actually issues (unpadded): the inference program
+        folds the activation-free 256x256 `*_xyz_encoding_final` layers into their successors (nsff_field_tc.cu,
+        build_layout), i.e. 65,536 fewer per branch - except in sigma-only mode for the static branch (no final
+        layer there) and when every layer is evaluated (training forward)."""
+        n = self.macs_per_point(mask)
+        if every_layer or self.precision != "bf16":
+            return n
+        if (mask & _cabi.OUT_STATIC) and not (mask & _cabi.OUT_SIGMA_ONLY):
+            n -= 256 * 256
+        if mask & _cabi.OUT_TRANSIENT:
+            n -= 256 * 256
+        return n
+
+    def run_field(self, mask, out, pts=None, x=None, save=None, every_layer=False):
         """Launch the MLP on raw points (`pts`: _cabi.Points) or an embedded matrix `x` into `out` (B, C).
         `save` (uint8 CUDA tensor of nsff_field_save_bytes): training mode, the kernel also writes every hidden
-        activation for the tensor-core backward."""
+        activation for the tensor-core backward.  `every_layer`: evaluate the reference's layers one by one
+        (NSFF_OUT_EVERY_LAYER; forwards whose backward differentiates the un-folded network)."""
         L = _cabi.lib()
         desc = self.field_desc()
         _cabi.select_device(out)
@@ -265,19 +280,21 @@ class NeRF(nn.Module):
             if FIELD_EVENTS is not None:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record(torch.cuda.current_stream(out.device))
+            cmask = mask | (_cabi.OUT_EVERY_LAYER if every_layer else 0)
             if pts is not None and save is not None:
                 rc = L.nsff_field_forward_save(C.byref(desc), _cabi.ptr(pack), C.byref(pts), mask, _cabi.ptr(out),
                                                out.stride(0), _cabi.ptr(save), st)
             elif pts is not None:
-                rc = L.nsff_field_forward(C.byref(desc), _cabi.ptr(pack), C.byref(pts), mask, _cabi.ptr(out),
+                rc = L.nsff_field_forward(C.byref(desc), _cabi.ptr(pack), C.byref(pts), cmask, _cabi.ptr(out),
                                           out.stride(0), st)
             else:
-                rc = L.nsff_field_forward_embedded(C.byref(desc), _cabi.ptr(pack), _cabi.ptr(x), x.stride(0), B, mask,
+                rc = L.nsff_field_forward_embedded(C.byref(desc), _cabi.ptr(pack), _cabi.ptr(x), x.stride(0), B, cmask,
                                                    _cabi.ptr(out), out.stride(0), st)
             _cabi.check(rc, "nsff_field_forward")
             if ev is not None:
                 ev[1].record(torch.cuda.current_stream(out.device))
-                FIELD_EVENTS.append((ev[0], ev[1], 2.0 * B * self.macs_per_point(mask)))
+                FIELD_EVENTS.append((ev[0], ev[1], 2.0 * B * self.macs_per_point(mask),
+                                     2.0 * B * self.executed_macs_per_point(mask, every_layer or save is not None)))
         elif self.precision == "fp32":
             fp, keep = self.field_params()
             step = 1 << 16                       # bound the fp32 scratch (3 hidden planes per point)
