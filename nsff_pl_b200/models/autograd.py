@@ -207,12 +207,22 @@ def _composite_args(cfg, zs, xyz, noises, raw, raw_fw, raw_bw, xyz_fw, xyz_bw):
     return a
 
 
+MAX_TRAIN_SAMPLES = 256      # nsff_composite_bwd.cu: kMaxChunksBwd (8) x 32 lanes
+
+
 class CompositeFn(torch.autograd.Function):
     """All outputs of rendering.py:202-298 for the static+transient training composite."""
 
     @staticmethod
     def forward(ctx, cfg, zs, xyz, n_s, n_t, n_fw, n_bw, raw, raw_fw, raw_bw, xyz_fw, xyz_bw):
         R, S = zs.shape
+        if S > MAX_TRAIN_SAMPLES:
+            # nsff_composite_backward keeps a ray's samples in registers (32 lanes x 8 chunks): say so before the forward
+            # instead of failing inside loss.backward()
+            raise NotImplementedError(
+                f"nsff_pl_b200: training composites support at most {MAX_TRAIN_SAMPLES} samples per ray, got {S} "
+                f"(N_samples + 2*N_importance with a transient coarse model); render under torch.no_grad() or reduce "
+                f"N_samples / N_importance")
         dev = zs.device
         names = composite_outputs(cfg["has_flow"], cfg["warp"], cfg["disocc"], cfg.get("transient", True))
         a = _composite_args(cfg, zs, xyz, (n_s, n_t, n_fw, n_bw), raw, raw_fw, raw_bw, xyz_fw, xyz_bw)

@@ -45,6 +45,10 @@ class PosEmbedding(nn.Module):
 
     def forward(self, x):
         """x: (B, 3) CUDA fp32 -> (B, 6*N_freqs+3)   (reference nerf.py:17-30)."""
+        if isinstance(x, torch.Tensor) and x.requires_grad and torch.is_grad_enabled():
+            raise NotImplementedError(
+                "nsff_pl_b200: PosEmbedding.forward records no autograd graph - call it under torch.no_grad(); the "
+                "differentiable path is render_rays (models/autograd.py), which encodes positions inside the field kernel.")
         x = _cabi.dev_tensor(x.contiguous() if isinstance(x, torch.Tensor) else x, "x")
         if x.dim() != 2 or x.shape[1] != 3:
             raise ValueError(f"PosEmbedding expects (B, 3), got {tuple(x.shape)}")
@@ -298,6 +302,8 @@ class NeRF(nn.Module):
         elif self.precision == "fp32":
             fp, keep = self.field_params()
             step = 1 << 16                       # bound the fp32 scratch (3 hidden planes per point)
+            if pts is not None:                  # ... in whole rays (the per-ray code / direction rows are indexed by ray)
+                step = max(1, step // int(pts.S)) * int(pts.S)
             for b0 in range(0, B, step):
                 nb = min(step, B - b0)
                 scratch = torch.empty(L.nsff_field_fp32_scratch_floats(C.byref(desc), nb), device=out.device,

@@ -97,6 +97,16 @@ def _field_pass(results, model, embeddings, xyz, zs, dirs, ts, max_t, want_trans
     mask = NeRF.out_mask(sigma_only, True, want_transient, flow_heads)
     Cn = NeRF.out_channels(mask)
     raw = torch.empty(R, S, Cn, **f32)
+    t_weight = None
+    if want_transient and (t_embedded is None or (not test_time and bool(flow_heads))):   # (warp passes always gather)
+        # the kernel gathers rows clamp(ts + shift, 0, max_t) of the time-code table itself: check what nn.Embedding
+        # would have checked (device, dtype, layout, row count) instead of reading out of bounds on the device
+        t_weight = _cabi.dev_tensor(embeddings["t"].weight.data, "embeddings['t'].weight")
+        if t_weight.device != dev:
+            raise ValueError(f"embeddings['t'].weight is on {t_weight.device}, the rays are on {dev}")
+        if t_weight.dim() != 2 or t_weight.shape[1] != model.in_channels_t or t_weight.shape[0] <= int(max_t):
+            raise IndexError(f"embeddings['t'].weight has shape {tuple(t_weight.shape)}; render_rays needs "
+                             f"(> max_t = {int(max_t)}, {model.in_channels_t})")
 
     def points(xyz_in, offset=None, offset_ld=0, xyz_out=None, t_shift=0, use_t_embedded=True):
         p = _cabi.Points()
@@ -112,7 +122,7 @@ def _field_pass(results, model, embeddings, xyz, zs, dirs, ts, max_t, want_trans
             if use_t_embedded and t_embedded is not None:     # kwargs['t_embedded'] (R, N_tau): row r = ray r
                 p.t_table, p.t_index = t_embedded.data_ptr(), None
             else:
-                p.t_table, p.t_index = embeddings["t"].weight.data_ptr(), ts.data_ptr()
+                p.t_table, p.t_index = t_weight.data_ptr(), ts.data_ptr()
         if model.encode_appearance:
             p.a_table, p.a_index = a_embedded.data_ptr(), None
         return p
@@ -375,6 +385,19 @@ def interpolate(results_t, results_tp1, dt, K, c2w, img_wh):
     output_transient_flow=['fw','bw']) of the SAME rays at frames t and t+1; returns ((h,w,3) rgb, (h,w) depth) at
     time t+dt.  All S sample planes are splatted and composited on the device in two launches."""
     L = _cabi.lib()
+    # eval.py:106-107 moves every value of both dicts to the host before calling interpolate() and then calls .numpy() on
+    # the results (eval.py:201-225): host dicts are staged onto the current CUDA device and the outputs returned on the
+    # device the inputs came from.  (The kernels themselves never run on the CPU.)
+    host_inputs = not results_t["xyzs_fine"].is_cuda
+    if host_inputs:
+        if not torch.cuda.is_available():
+            raise NotImplementedError("interpolate: nsff_pl_b200 kernels are CUDA-only (no CPU fallback)")
+        dev_in = torch.device("cuda", torch.cuda.current_device())
+        keys_t = ("xyzs_fine", "zs_fine", "static_rgbs_fine", "transient_rgbs_fine", "transient_flows_fw",
+                  "static_alphas_fine", "transient_alphas_fine")
+        keys_p = ("transient_rgbs_fine", "transient_flows_bw", "transient_alphas_fine")
+        results_t = {k: results_t[k].to(dev_in, non_blocking=True) for k in keys_t}
+        results_tp1 = {k: results_tp1[k].to(dev_in, non_blocking=True) for k in keys_p}
     xyzs = _cabi.dev_tensor(results_t["xyzs_fine"].contiguous(), "xyzs_fine")
     R, S = xyzs.shape[:2]
     w, h = int(img_wh[0]), int(img_wh[1])
@@ -417,4 +440,6 @@ def interpolate(results_t, results_tp1, dt, K, c2w, img_wh):
     _cabi.select_device(xyzs)
     _cabi.check(L.nsff_interpolate(C.byref(a), _cabi.ptr(scratch), _cabi.ptr(rgb), _cabi.ptr(depth),
                                    _cabi.stream_ptr(dev)), "nsff_interpolate")
+    if host_inputs:
+        return rgb.cpu(), depth.cpu()
     return rgb, depth
