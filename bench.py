@@ -8,10 +8,16 @@ A "step" = one render_rays forward over one frame per GPU (weak scaling: N GPUs 
 rank r renders frame index r) followed by ONE all-gather of the packed per-ray pixels (rgb, depth, flows).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scaling weak|strong]
+                    [--workload render|train|sequence] [--no-sub-records] [--no-cpu-baseline]
 
 `value`  : ray-samples/s with rays/ts already resident in HBM, CUDA-event timed, max over ranks.
 `e2e`    : same metric through the public API from pinned HOST buffers (H2D of rays+ts and D2H of the
            gathered pixels inside the timed region).
+`parity` : PSNR / max-abs of our render against the CPU leg's render_rays output on the same rays of the timed frame.
+`sub`    : bounded records of the other BASELINE.json configurations, so that one driver-run line carries them:
+           `train` (configs[2]: 1024x128 training step, the reference's NeRFWLoss, Adam), `sequence` (configs[4]:
+           hierarchical frames + time interpolation) and, for N > 1, `strong` (configs[3]: ONE frame sharded over the
+           ranks, in-place pixel all-gather overlapped with the next frame, the collective also timed alone).
 `--impl reference`: the reference's own CPU implementation of this path: the UNMODIFIED models/rendering.py +
 models/nerf.py, staged by build() into git-ignored baseline/_ref/ (oracle/ref_loader.py; it travels with the gpurun
 snapshot) and run on torch CPU with the fastest thread count up to os.cpu_count(), on a bounded ray sample of the
@@ -123,11 +129,17 @@ def _cpu_setup(n_rays):
     return "port", render, rays, ts
 
 
+LAST_CPU_RESULT = {}
+
+
 def _cpu_render(render, rays, ts):
     t0 = time.perf_counter()
     with torch.no_grad():
-        render(rays, ts)
-    return time.perf_counter() - t0
+        res = render(rays, ts)
+    dt = time.perf_counter() - t0
+    LAST_CPU_RESULT.clear()
+    LAST_CPU_RESULT.update(res=res, rays=rays, ts=ts)
+    return dt
 
 
 def pick_cpu_threads(render, rays, ts):
@@ -181,22 +193,37 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def run_train(args, rank, local_rank, world):
-    """BASELINE.json configs[2]: training step, 1024-ray batch x 128 samples, bf16 tensor-core forward, CUDA backward,
-    surrogate photometric + warped-photometric + cycle + flow-regulariser loss (the reference's NeRFWLoss needs
-    kornia and dataset tensors), Adam step and bf16 re-pack inside the timed region; gradients all-reduced over ranks."""
+def _init_dist(local_rank, world):
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    return dev
+
+
+def _max_over_ranks(ms, dev, world):
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def train_record(args, rank, local_rank, world, steps, warmup):
+    """BASELINE.json configs[2]: training step, 1024-ray batch x 128 samples per GPU, full NSFF + warp, bf16 tensor-core
+    forward (every layer evaluated, activations saved), tensor-core backward, the reference's NeRFWLoss (losses.py:31-171,
+    unmodified, staged in baseline/_ref; photometric + flow + cycle + regularisers) on our result dict, Adam step and bf16
+    re-pack inside the timed region; gradients all-reduced over ranks (one flat bucket)."""
     import torch.distributed as dist
     from nsff_pl_b200 import _cabi, parallel
     from nsff_pl_b200.models.rendering import render_rays
     from parity_util import build_fields, synthetic_rays
-    torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
     R, S = 1024, 128
     models, emb, _, _ = build_fields(W=256, seed=0, n_frames=N_FRAMES, device=dev, precision="bf16")
-    import scenes
     for m in models.values():
         m.requires_grad_(True)
         m.grad_precision = args.grad_precision
@@ -207,12 +234,23 @@ def run_train(args, rank, local_rank, world):
     phase = {}
     rays, ts = synthetic_rays(R, n_frames=N_FRAMES, seed=100 + rank)
     rays, ts = rays.to(dev), ts.to(dev)
-    target = torch.rand(R, 3, device=dev)
     kw = dict(N_samples=S, perturb=1.0, noise_std=1.0, N_importance=0, test_time=False,
               output_transient_flow=["fw", "bw", "disocc"])
+    loss_kind = "surrogate"
+    loss_fn = batch = None
+    try:
+        from oracle import ref_loader
+        if ref_loader.available():
+            import ref_harness as H
+            loss_fn = H.make_loss(ref_loader.load(), N_FRAMES, img_wh=IMG_WH, device=dev)
+            batch = H.to_device(H.make_batch(rays.cpu(), ts.cpu(), img_wh=IMG_WH, seed=7 + rank), dev)
+            loss_kind = "reference NeRFWLoss (losses.py:31-171, unmodified)"
+    except Exception as e:  # the staged reference is optional on a box that never ran build()
+        loss_kind = f"surrogate ({type(e).__name__}: reference loss unavailable)"
+    target = torch.rand(R, 3, device=dev)
 
     def mark(name):
-        if phase is not None and "on" in phase:
+        if "on" in phase:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
             phase.setdefault("ev", []).append((name, ev))
@@ -221,13 +259,17 @@ def run_train(args, rank, local_rank, world):
         mark("start")
         opt.zero_grad(set_to_none=True)
         res = render_rays(models, emb, rays, ts, N_FRAMES - 1, **kw)
-        loss = ((res["rgb_fine"] - target) ** 2).mean()
-        loss = loss + (res["disocc_fw"] * (res["rgb_fw"] - target) ** 2).mean() + (res["disocc_bw"] * (res["rgb_bw"] - target) ** 2).mean()
-        loss = loss + (res["disoccs_fw"] * (res["xyzs_fw_bw"] - res["xyzs_fine"]).abs()).mean()
-        loss = loss + (res["disoccs_bw"] * (res["xyzs_bw_fw"] - res["xyzs_fine"]).abs()).mean()
-        loss = loss + 0.1 * (res["transient_flows_fw"].abs().mean() + res["transient_flows_bw"].abs().mean())
-        loss = loss + 0.01 * (res["transient_weights_fine"] * res["static_weights_fine"]).mean()
-        mark("forward+loss")
+        mark("forward")
+        if loss_fn is not None:
+            loss = sum(loss_fn(res, batch, epoch=5, output_transient=True,
+                               output_transient_flow=["fw", "bw", "disocc"]).values())
+        else:
+            loss = ((res["rgb_fine"] - target) ** 2).mean()
+            loss = loss + (res["disocc_fw"] * (res["rgb_fw"] - target) ** 2).mean() + (res["disocc_bw"] * (res["rgb_bw"] - target) ** 2).mean()
+            loss = loss + (res["disoccs_fw"] * (res["xyzs_fw_bw"] - res["xyzs_fine"]).abs()).mean()
+            loss = loss + (res["disoccs_bw"] * (res["xyzs_bw_fw"] - res["xyzs_fine"]).abs()).mean()
+            loss = loss + 0.1 * (res["transient_flows_fw"].abs().mean() + res["transient_flows_bw"].abs().mean())
+        mark("loss")
         loss.backward()
         mark("backward")
         if world > 1:
@@ -236,58 +278,50 @@ def run_train(args, rank, local_rank, world):
         mark("allreduce+adam")
         return loss
 
-    for _ in range(max(3, args.warmup)):
+    for _ in range(max(3, warmup)):
         step()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     n0 = _cabi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     e0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         loss = step()
         marks[i].record()
     e1.record()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    per_step = sorted(([e0] + marks)[i].elapsed_time(marks[i]) for i in range(args.steps))
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    # one more instrumented step for the phase split (not part of the timed region)
-    phase["on"] = True
+    ms = _max_over_ranks(e0.elapsed_time(e1), dev, world)
+    per_step = sorted(([e0] + marks)[i].elapsed_time(marks[i]) for i in range(steps))
+    launches = int(_cabi.launch_count() - n0)
+    phase["on"] = True                       # one more instrumented step for the phase split (outside the timed region)
     step()
     torch.cuda.synchronize()
     evs = phase["ev"]
     split = {evs[i][0]: round(evs[i - 1][1].elapsed_time(evs[i][1]), 3) for i in range(1, len(evs))}
-    if rank == 0:
-        value = R * S * world * args.steps / (ms * 1e-3)
-        tc = args.grad_precision == "bf16"
-        print(json.dumps({"metric": "ray-samples/sec (training step fwd+bwd+Adam)", "value": value, "unit": "ray-samples/s",
-                          "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                          "dtype": "bf16" if tc else "bf16 fwd / f32 bwd", "data": "synthetic",
-                          "config": {"workload": "training step, 1024 rays x 128 samples per GPU, full NSFF + warp, surrogate "
-                                                 "photometric/cycle/flow loss, Adam (BASELINE.json configs[2])",
-                                     "backward": (("bf16 tcgen05 GEMMs over tile images (dgrad + wgrad per layer; activations "
-                                                   + ("recomputed" if args.bwd_recompute else "saved by the forward kernel") + ")")
-                                                  if tc else "fp32 CUDA-core kernels (verification path)")},
-                          "phase_ms": split,
-                          "step_ms": {"min": round(per_step[0], 3), "median": round(per_step[len(per_step) // 2], 3),
-                                      "max": round(per_step[-1], 3)},
-                          "algorithmic_tflop_per_step": round(R * S * 14.28e6 / 1e12, 3),
-                          "tflops_whole_step": R * S * world * 14.28e6 / (ms / args.steps * 1e-3) / 1e12,
-                          "frac_of_bf16_peak": R * S * 14.28e6 / (ms / args.steps * 1e-3) / 1e12 / measured_peaks()["tflops"],
-                          "gpu_launches": int(_cabi.launch_count() - n0), "final_loss": float(loss)}), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    tc = args.grad_precision == "bf16"
+    return {"metric": "ray-samples/sec (training step fwd+bwd+Adam)", "value": R * S * world * steps / (ms * 1e-3),
+            "unit": "ray-samples/s", "n_gpus": world, "steps": steps, "warmup": max(3, warmup), "ms_per_step": ms / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if tc else "bf16 fwd / f32 bwd", "data": "synthetic",
+            "config": {"workload": "training step, 1024 rays x 128 samples per GPU, full NSFF + warp, Adam "
+                                   "(BASELINE.json configs[2])", "loss": loss_kind,
+                       "backward": (("bf16 tcgen05 GEMMs over tile images (dgrad + wgrad per layer; activations "
+                                     + ("recomputed" if args.bwd_recompute else "saved by the forward kernel") + ")")
+                                    if tc else "fp32 CUDA-core kernels (verification path)")},
+            "phase_ms": split,
+            "step_ms": {"min": round(per_step[0], 3), "median": round(per_step[len(per_step) // 2], 3),
+                        "max": round(per_step[-1], 3)},
+            "algorithmic_tflop_per_step": round(R * S * 14.28e6 / 1e12, 3),
+            "tflops_whole_step": R * S * world * 14.28e6 / (ms / steps * 1e-3) / 1e12,
+            "frac_of_bf16_peak": R * S * 14.28e6 / (ms / steps * 1e-3) / 1e12 / measured_peaks()["tflops"],
+            "gpu_launches": launches, "final_loss": float(loss)}
 
 
-def run_sequence(args, rank, local_rank, world):
+def sequence_record(args, rank, local_rank, world, steps, warmup):
     """BASELINE.json configs[4]: coarse + fine hierarchical render (64 + 64 importance samples -> 192 fine samples per
     ray, test_time=True, flows on) of consecutive frames of a 30-frame sequence at a fixed pose, each followed by one
     time-interpolated frame (rendering.py:365-460: softmax-splat of every sample plane + MPI composite) between the
@@ -300,11 +334,7 @@ def run_sequence(args, rank, local_rank, world):
     from nsff_pl_b200.models.rendering import interpolate, render_rays
     from parity_util import build_fields
     from scenes import FakeDataset
-    torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
     w, h = IMG_WH
     R = w * h
     models, emb, _, _ = build_fields(W=256, coarse=True, seed=0, n_frames=N_FRAMES, device=dev, precision="bf16")
@@ -320,17 +350,17 @@ def run_sequence(args, rank, local_rank, world):
 
     t0 = rank
     prev = render(t0)
-    for i in range(max(3, args.warmup)):
+    for i in range(max(3, warmup)):
         cur = render(t0 + 1)
         interpolate(prev, cur, 0.5, K, c2w, IMG_WH)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     n0 = _cabi.launch_count()
-    nerf_mod.FIELD_EVENTS = []
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+    saved_events, nerf_mod.FIELD_EVENTS = nerf_mod.FIELD_EVENTS, []
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps + 1)]
     ev[0].record()
-    for i in range(args.steps):
+    for i in range(steps):
         cur = render(t0 + (i + 1) * world)
         ev[2 * i + 1].record()
         rgb, depth = interpolate(prev, cur, 0.5, K, c2w, IMG_WH)
@@ -339,42 +369,86 @@ def run_sequence(args, rank, local_rank, world):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    field_ev, nerf_mod.FIELD_EVENTS = nerf_mod.FIELD_EVENTS, None
-    ms = ev[0].elapsed_time(ev[-1])
-    render_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)) / args.steps
-    interp_ms = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)) / args.steps
+    field_ev, nerf_mod.FIELD_EVENTS = nerf_mod.FIELD_EVENTS, saved_events
+    ms = _max_over_ranks(ev[0].elapsed_time(ev[-1]), dev, world)
+    render_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(steps)) / steps
+    interp_ms = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(steps)) / steps
     field_ms = sum(e[0].elapsed_time(e[1]) for e in field_ev)
     field_flop = sum(e[2] for e in field_ev)
     field_flop_exec = sum(e[3] for e in field_ev)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    if rank == 0:
-        s_fine = cur["zs_fine"].shape[1]
-        peaks = measured_peaks()
-        print(json.dumps({"metric": "ray-samples/sec (hierarchical render_rays + time interpolation)",
-                          "value": R * s_fine * world * args.steps / (ms * 1e-3), "unit": "ray-samples/s",
-                          "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-                          "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                          "dtype": "bf16", "data": "synthetic",
-                          "config": {"workload": "coarse+fine hierarchical (64 + 64 importance samples per pdf -> "
-                                                 f"{s_fine} fine samples/ray), 512x288 frames of a 30-frame sequence at a "
-                                                 "fixed pose + one interpolated frame (dt=0.5) per rendered frame "
-                                                 "(BASELINE.json configs[4])",
-                                     "rays_per_frame": R, "fine_samples_per_ray": int(s_fine)},
-                          "render_ms_per_frame": render_ms, "interpolate_ms_per_frame": interp_ms,
-                          "field_kernel": {"ms_per_frame": field_ms / args.steps,
-                                           "tflops": field_flop / (field_ms * 1e-3) / 1e12 if field_ms else None,
-                                           "frac_of_peak": (field_flop / (field_ms * 1e-3) / 1e12 / peaks["tflops"])
-                                           if field_ms else None,
-                                           "frac_of_peak_executed": (field_flop_exec / (field_ms * 1e-3) / 1e12 / peaks["tflops"])
-                                           if field_ms else None, "peak_source": peaks["source"]},
-                          "gpu_launches": int(_cabi.launch_count() - n0),
-                          "image_checksum": float(rgb.double().sum()), "depth_checksum": float(depth.double().sum())}),
-              flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    s_fine = cur["zs_fine"].shape[1]
+    peaks = measured_peaks()
+    return {"metric": "ray-samples/sec (hierarchical render_rays + time interpolation)",
+            "value": R * s_fine * world * steps / (ms * 1e-3), "unit": "ray-samples/s",
+            "n_gpus": world, "steps": steps, "warmup": max(3, warmup),
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "coarse+fine hierarchical (64 + 64 importance samples per pdf -> "
+                                   f"{s_fine} fine samples/ray), 512x288 frames of a 30-frame sequence at a "
+                                   "fixed pose + one interpolated frame (dt=0.5) per rendered frame "
+                                   "(BASELINE.json configs[4])",
+                       "rays_per_frame": R, "fine_samples_per_ray": int(s_fine)},
+            "render_ms_per_frame": render_ms, "interpolate_ms_per_frame": interp_ms,
+            "field_kernel": {"ms_per_frame": field_ms / steps,
+                             "tflops": field_flop / (field_ms * 1e-3) / 1e12 if field_ms else None,
+                             "frac_of_peak": (field_flop / (field_ms * 1e-3) / 1e12 / peaks["tflops"]) if field_ms else None,
+                             "frac_of_peak_executed": (field_flop_exec / (field_ms * 1e-3) / 1e12 / peaks["tflops"])
+                             if field_ms else None, "peak_source": peaks["source"]},
+            "gpu_launches": int(_cabi.launch_count() - n0),
+            "image_checksum": float(rgb.double().sum()), "depth_checksum": float(depth.double().sum())}
+
+
+def strong_record(args, rank, local_rank, world, steps, warmup, models, emb):
+    """BASELINE.json configs[3]: ONE 512x288x128 frame sharded over the ranks (contiguous ray blocks), per-ray pixels
+    all-gathered in place on a side stream (parallel.PixelGather) so the collective of frame i overlaps the field kernel
+    of frame i+1.  value = frame ray-samples / time per frame (max over ranks); the collective is also timed on its own."""
+    import torch.distributed as dist
+    from nsff_pl_b200 import parallel
+    from nsff_pl_b200.models.rendering import render_rays
+    from parity_util import synthetic_rays
+    dev = torch.device("cuda", local_rank)
+    R_frame = IMG_WH[0] * IMG_WH[1]
+    rays_f, ts_f = synthetic_rays(R_frame, n_frames=N_FRAMES, seed=1, img_wh=IMG_WH, frame=8)
+    lo, hi = parallel.shard_bounds(R_frame, rank, world)
+    rays, ts = rays_f[lo:hi].contiguous().to(dev), ts_f[lo:hi].contiguous().to(dev)
+    gather = parallel.PixelGather(R_frame, dev)
+
+    def frame():
+        with torch.no_grad():
+            return gather.submit(render_rays(models, emb, rays, ts, N_FRAMES - 1, **RENDER_KW))
+
+    for _ in range(max(3, warmup)):
+        buf = frame()
+    gather.wait()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        buf = frame()
+    gather.wait()
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = _max_over_ranks(e0.elapsed_time(e1), dev, world)
+    # the collective on its own (same buffers, nothing else running)
+    mine = buf[lo:hi]
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        dist.all_gather_into_tensor(buf, mine)
+    torch.cuda.synchronize()
+    c0.record()
+    for _ in range(20):
+        dist.all_gather_into_tensor(buf, mine)
+    c1.record()
+    torch.cuda.synchronize()
+    coll_us = _max_over_ranks(c0.elapsed_time(c1) / 20 * 1e3, dev, world)
+    return {"metric": "ray-samples/sec (render_rays fwd, one frame sharded over the ranks)",
+            "value": R_frame * N_SAMPLES * steps / (ms * 1e-3), "unit": "ray-samples/s", "n_gpus": world, "steps": steps,
+            "ms_per_frame": ms / steps, "scaling": "strong", "rays_per_rank": int(hi - lo),
+            "all_gather": {"bytes": int(buf.numel() * 4), "us": coll_us,
+                           "how": "in-place all_gather_into_tensor on a side stream, overlapped with the next frame"},
+            "checksum": float(buf.double().sum())}
 
 
 def workload_config(args, world):
@@ -386,6 +460,22 @@ def workload_config(args, world):
             "l2": "per-step outputs (~3.5 GB/GPU) exceed the 126 MB L2; no explicit flush needed"}
 
 
+def parity_block(models, emb, dev):
+    """BASELINE metric, second half: PSNR / max-abs of our render against the CPU reference on the rays the CPU leg has
+    just rendered (the first CPU_SAMPLE_RAYS rays of the timed frame)."""
+    from nsff_pl_b200.models.rendering import render_rays
+    from parity_util import max_abs, psnr
+    if not LAST_CPU_RESULT:
+        return None
+    want, rays, ts = LAST_CPU_RESULT["res"], LAST_CPU_RESULT["rays"], LAST_CPU_RESULT["ts"]
+    with torch.no_grad():
+        got = render_rays(models, emb, rays.to(dev), ts.to(dev), N_FRAMES - 1, **RENDER_KW)
+    return {"rays": int(rays.shape[0]), "psnr_rgb_db": psnr(got["rgb_fine"], want["rgb_fine"]),
+            "max_abs": {k: max_abs(got[k], want[k]) for k in ("rgb_fine", "depth_fine", "transient_flow_fw",
+                                                              "transient_flow_bw", "rgb_fw", "rgb_bw")},
+            "against": "the CPU leg's render_rays output on the same rays (energised weights: gains amplify bf16 rounding ~30x)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -395,13 +485,15 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--precision", default="bf16", choices=["bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub-records", action="store_true",
+                    help="render workload: skip the train / sequence / strong sub-records of the JSON line")
     ap.add_argument("--grad-precision", default="bf16", choices=["bf16", "fp32"],
                     help="train workload: tensor-core backward (default) or the fp32 verification backward")
     ap.add_argument("--bwd-recompute", action="store_true",
                     help="train workload: re-evaluate the layers in the backward instead of saving them in the forward")
     ap.add_argument("--workload", default="render", choices=["render", "train", "sequence"],
-                    help="render = BASELINE.json metric (default, what the driver runs); train = configs[2] step; "
-                         "sequence = configs[4] hierarchical frames + time interpolation")
+                    help="render = BASELINE.json metric (default, what the driver runs; its line also carries bounded "
+                         "train / sequence / strong sub-records); train = configs[2] step; sequence = configs[4]")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -411,27 +503,24 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
-    if args.workload == "sequence":
-        run_sequence(args, rank, local_rank, world)
-        return
-    if args.workload == "train":
-        run_train(args, rank, local_rank, world)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (the nsff_pl_b200 path has no CPU fallback)")
+    import torch.distributed as dist
+    dev = _init_dist(local_rank, world)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+    if args.workload in ("train", "sequence"):
+        fn = train_record if args.workload == "train" else sequence_record
+        rec = fn(args, rank, local_rank, world, args.steps, args.warmup)
+        if rank == 0:
+            print(json.dumps(rec), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
         return
 
-    import torch.distributed as dist
     from nsff_pl_b200 import _cabi, parallel
     from nsff_pl_b200.models import nerf as nerf_mod
     from nsff_pl_b200.models.rendering import render_rays
     from parity_util import build_fields, synthetic_rays
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a GPU (the nsff_pl_b200 path has no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
 
     models, emb, _, _ = build_fields(W=256, seed=0, n_frames=N_FRAMES, device=dev, precision=args.precision)
     R_frame = IMG_WH[0] * IMG_WH[1]
@@ -449,6 +538,7 @@ def main():
     rays_d, ts_d = rays_h.to(dev), ts_h.to(dev)
     n_gather = R * world
     pix_host = torch.empty(n_gather, 10, dtype=torch.float32).pin_memory()
+    full_buf = torch.empty(n_gather, 10, device=dev) if world > 1 else None     # gather target, allocated once
 
     field_events = []
 
@@ -457,9 +547,8 @@ def main():
             res = render_rays(models, emb, rays, ts, N_FRAMES - 1, **RENDER_KW)
             pix = parallel.pack_pixels(res)
             if world > 1:
-                full = torch.empty(n_gather, pix.shape[1], device=dev)
-                dist.all_gather_into_tensor(full, pix)
-                pix = full
+                dist.all_gather_into_tensor(full_buf, pix)
+                pix = full_buf
         return pix
 
     def barrier():
@@ -475,12 +564,7 @@ def main():
             fn()
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return _max_over_ranks(e0.elapsed_time(e1), dev, world)
 
     for _ in range(args.warmup):
         step(rays_d, ts_d)
@@ -511,6 +595,15 @@ def main():
     ms_e2e = timed(e2e_step, args.steps)
     e2e_value = units_per_step * args.steps / (ms_e2e * 1e-3)
 
+    # ---- bounded sub-records: the other BASELINE.json configurations, so that the driver's record carries them ----
+    sub = {}
+    if not args.no_sub_records:
+        torch.cuda.synchronize()
+        if world > 1 and R_frame % world == 0:
+            sub["strong"] = strong_record(args, rank, local_rank, world, args.steps, args.warmup, models, emb)
+        sub["train"] = train_record(args, rank, local_rank, world, 20, 5)
+        sub["sequence"] = sequence_record(args, rank, local_rank, world, 3, 3)
+
     if rank == 0:
         peaks = measured_peaks()
         torch.cuda.synchronize()
@@ -540,12 +633,13 @@ def main():
                               "launches_timed": len(comp_ms), "avg_launch_ms": sum(comp_ms) / max(1, len(comp_ms)),
                               "kernel_share_of_step": (sum(comp_ms) / ms) if comp_ms else None,
                               "algorithmic_bytes_per_launch": (sum(comp_bytes) / len(comp_bytes)) if comp_bytes else None}
-        cpu = None
-        if not args.no_cpu_baseline and world >= 1:
+        cpu = parity = None
+        if not args.no_cpu_baseline:
             v, times, cores, kind = cpu_throughput(CPU_SAMPLE_RAYS, reps=2)
             cpu = {"value": v, "unit": "ray-samples/s", "cores": cores, "kind": kind, "host_cores": os.cpu_count(),
                    "sample": f"{CPU_SAMPLE_RAYS} rays x {N_SAMPLES} samples of the same frame, best of 2 "
                              f"({', '.join(f'{t:.1f}s' for t in times)})"}
+            parity = parity_block(models, emb, dev)
         line = {"metric": "ray-samples/sec (render_rays fwd)", "value": value, "unit": "ray-samples/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16",
@@ -553,8 +647,9 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "ray-samples/s", "h2d_bytes_per_step": int(rays_pin.numel() * 4 + ts_pin.numel() * 8),
                         "d2h_bytes_per_step": int(pix_host.numel() * 4), "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_composite": roofline_composite,
-                "cpu_baseline": cpu,
-                "tflops_whole_step": units_per_step * FLOP_PER_POINT / (ms / args.steps * 1e-3) / 1e12 / world}
+                "cpu_baseline": cpu, "parity": parity,
+                "tflops_whole_step": units_per_step * FLOP_PER_POINT / (ms / args.steps * 1e-3) / 1e12 / world,
+                "sub": sub}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -60,6 +60,67 @@ def all_gather_pixels(local: torch.Tensor, n_rays_total: int, group=None) -> tor
     return torch.cat([gathered[r * m:r * m + lens[r]] for r in range(world)], 0)
 
 
+class PixelGather:
+    """Pre-allocated, double-buffered all-gather of a frame's packed per-ray outputs (config 4: ONE frame sharded
+    over the ranks).  Each rank writes its pixel columns straight into its own rows of the full-frame buffer (no
+    torch.cat, no per-step allocation) and the collective runs in place on a side stream, so the all-gather of frame i
+    overlaps the field kernel of frame i+1; `wait()` makes the current stream wait for a frame's gather.
+
+        g = PixelGather(n_rays_total, device)
+        for frame ...:
+            res = render_rays(...rays[lo:hi]...)
+            buf = g.submit(res)          # returns immediately; buf is valid after g.wait(buf)
+        g.wait(buf)
+    """
+
+    def __init__(self, n_rays_total: int, device, keys: Sequence[str] = PIXEL_KEYS, n_cols: int = 10, group=None,
+                 depth: int = 2):
+        self.group, self.keys, self.n_total = group, tuple(keys), int(n_rays_total)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.lo, self.hi = shard_bounds(self.n_total, self.rank, self.world)
+        lens = [b - a for a, b in (shard_bounds(self.n_total, r, self.world) for r in range(self.world))]
+        if len(set(lens)) != 1:
+            raise ValueError("PixelGather needs equal ray blocks (n_rays_total divisible by the world size); "
+                             "use all_gather_pixels() for ragged shards")
+        self.bufs = [torch.empty(self.n_total, n_cols, device=device, dtype=torch.float32) for _ in range(depth)]
+        self.done = [None] * depth
+        self.i = 0
+        self.cuda = torch.device(device).type == "cuda"
+        self.stream = torch.cuda.Stream(device=device) if self.cuda else None
+
+    def submit(self, results: Dict[str, torch.Tensor]) -> torch.Tensor:
+        slot = self.i % len(self.bufs)
+        self.i += 1
+        full = self.bufs[slot]
+        if self.cuda and self.done[slot] is not None:
+            torch.cuda.current_stream().wait_event(self.done[slot])       # the slot's previous gather has finished
+        mine, c0 = full[self.lo:self.hi], 0
+        for k in self.keys:                                                # pixel columns, in place
+            v = results[k].reshape(results[k].shape[0], -1)
+            mine[:, c0:c0 + v.shape[1]].copy_(v)
+            c0 += v.shape[1]
+        if not self.cuda:
+            dist.all_gather_into_tensor(full, mine, group=self.group)
+            return full
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            dist.all_gather_into_tensor(full, mine, group=self.group)     # in place: `mine` is this rank's block of `full`
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.done[slot] = ev
+        return full
+
+    def wait(self, full: torch.Tensor = None):
+        """Current stream waits for the gather of `full` (default: every gather in flight)."""
+        if not self.cuda:
+            return
+        for b, ev in zip(self.bufs, self.done):
+            if ev is not None and (full is None or b is full):
+                torch.cuda.current_stream().wait_event(ev)
+
+
 def render_frame_sharded(render_fn, rays: torch.Tensor, ts, keys: Sequence[str] = PIXEL_KEYS, group=None):
     """Config 4: every rank renders its contiguous ray block with `render_fn(rays_block, ts_block) -> dict`
     and all ranks end up with the whole frame's per-ray outputs."""

@@ -102,3 +102,42 @@ def test_gradient_all_reduce_averages_over_ranks():
         assert torch.allclose(got[0], sum(want0) / world) and torch.allclose(got[1], sum(want1) / world)
         assert got[2] is None
         assert torch.allclose(got[3], sum(want3) / world)
+
+
+def _gather_worker(rank, world, port, ret):
+    for p in (ROOT, HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from nsff_pl_b200 import parallel
+        n = 12
+        g = parallel.PixelGather(n, "cpu")
+        ok = True
+        for frame in range(3):                       # double-buffered: three frames reuse slot 0
+            full_res = {"rgb_fine": torch.arange(n * 3, dtype=torch.float32).view(n, 3) + 100 * frame,
+                        "depth_fine": torch.arange(n, dtype=torch.float32) * 0.5 + frame,
+                        "transient_flow_fw": torch.ones(n, 3) * frame, "transient_flow_bw": -torch.ones(n, 3) * frame}
+            lo, hi = parallel.shard_bounds(n, rank, world)
+            buf = g.submit({k: v[lo:hi] for k, v in full_res.items()})
+            g.wait(buf)
+            back = parallel.unpack_pixels(buf, full_res)
+            ok = ok and all(torch.equal(back[k], full_res[k]) for k in parallel.PIXEL_KEYS)
+        if rank == 0:
+            ret["ok"] = ok
+            try:
+                parallel.PixelGather(13, "cpu")
+                ret["ragged_raises"] = False
+            except ValueError:
+                ret["ragged_raises"] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_pixel_gather_in_place_double_buffered():
+    """config 4 plumbing: each rank writes its rows of the pre-allocated frame buffer, in-place all-gather."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_gather_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    assert ret["ok"] is True and ret["ragged_raises"] is True
