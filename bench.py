@@ -451,6 +451,38 @@ def strong_record(args, rank, local_rank, world, steps, warmup, models, emb):
             "checksum": float(buf.double().sum())}
 
 
+def eval_record(args, rank, local_rank, world, models, emb, frames=2):
+    """eval.py's caller loop (eval.f, eval.py:81-110) over OUR render_rays on one 512x288x128 frame: chunks of 32768
+    rays, test_time=True, flows on, EVERY value of every chunk's dict moved to the host (v.cpu()) and concatenated -
+    once as the reference does it (full dict: ~1.7 GB per frame over PCIe into pageable memory) and once with the
+    `keys=` output selection (SURVEY section 8f #3) passed through eval.f's **kwargs."""
+    import ref_harness as H
+    from nsff_pl_b200.models.rendering import PER_RAY_KEYS, render_rays
+    from parity_util import synthetic_rays
+    dev = torch.device("cuda", local_rank)
+    R_frame = IMG_WH[0] * IMG_WH[1]
+    rays, ts = synthetic_rays(R_frame, n_frames=N_FRAMES, seed=1, img_wh=IMG_WH, frame=8)
+    rays, ts = rays.to(dev), ts.to(dev)
+    out = {}
+    for name, extra in (("full_dict", {}), ("selected_keys", {"keys": PER_RAY_KEYS})):
+        def frame():
+            return H.eval_f(render_rays, models, emb, rays, ts, N_FRAMES - 1, N_SAMPLES, 0, 32768,
+                            output_transient_flow=["fw", "bw"], **extra)
+        res = frame()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(frames):
+            res = frame()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / frames
+        nbytes = sum(v.numel() * v.element_size() for v in res.values())
+        out[name] = {"ms_per_frame": dt * 1e3, "value": R_frame * N_SAMPLES / dt, "unit": "ray-samples/s",
+                     "d2h_bytes_per_frame": int(nbytes), "keys": len(res)}
+    out["workload"] = ("eval.f over one 512x288x128 frame, test_time=True (no warp passes), chunk 32768, host wall clock "
+                       "incl. every .cpu() and torch.cat")
+    return out
+
+
 def workload_config(args, world):
     return {"workload": "full NSFF static+dynamic+flow-warp +-1, 512x288 frame x 128 samples/ray, inference "
                         "(BASELINE.json configs[1])",
@@ -601,6 +633,8 @@ def main():
         torch.cuda.synchronize()
         if world > 1 and R_frame % world == 0:
             sub["strong"] = strong_record(args, rank, local_rank, world, args.steps, args.warmup, models, emb)
+        if rank == 0:
+            sub["eval"] = eval_record(args, rank, local_rank, world, models, emb)
         sub["train"] = train_record(args, rank, local_rank, world, 20, 5)
         sub["sequence"] = sequence_record(args, rank, local_rank, world, 3, 3)
 

@@ -21,6 +21,9 @@ __all__ = ["render_rays", "sample_pdf", "interpolate"]
 # Optional profiling hook (bench.py): when a list, every inference composite launch appends
 # (start_event, end_event, algorithmic_hbm_bytes) recorded on the launching stream.
 COMPOSITE_EVENTS = None
+# per-ray outputs of the fine pass (what eval.py's image / depth / flow writers read)
+PER_RAY_KEYS = ("rgb_fine", "depth_fine", "transient_alpha_fine", "transient_rgb_fine", "_static_rgb_fine",
+                "_static_depth_fine", "xyz_fine", "transient_flow_fw", "transient_flow_bw")
 _PER_SAMPLE_OUT = {"static_sigmas": 1, "transient_sigmas": 1, "static_weights": 1, "transient_weights": 1, "weights": 1,
                    "static_alphas": 1, "transient_alphas": 1, "xyzs_fw_bw": 3, "xyzs_bw_fw": 3, "disoccs_fw": 1,
                    "disoccs_bw": 1}
@@ -261,6 +264,11 @@ def render_rays(models, embeddings, rays, ts, max_t, N_samples=64, perturb=0, no
     models: {'fine'[, 'coarse']: NeRF}; embeddings: {'xyz','dir'[, 't','a']}; rays (R,6) fp32 CUDA;
     ts (R,) int64 or None.  kwargs honoured: output_transient, output_transient_flow, view_dir,
     t_embedded, a_embedded, dataset (eval-only visibility); everything else is ignored like the reference.
+
+    Extension: `keys=[...]` returns only the named result keys, in the reference's order.
+    eval.f / the validation loop .cpu() EVERY value of the dict (eval.py:106-107, train.py:119-121): ~1.7 GB per
+    512x288x128 frame, almost all of it per-sample tensors the caller never reads; passing e.g.
+    keys=PER_RAY_KEYS through eval.f's **kwargs leaves 0.1 % of that to copy.  Unknown names raise KeyError.
     """
     L = _cabi.lib()
     rays = _cabi.dev_tensor(rays if rays.is_contiguous() else rays.contiguous(), "rays")
@@ -366,6 +374,13 @@ def render_rays(models, embeddings, rays, ts, max_t, N_samples=64, perturb=0, no
     else:
         _field_pass(results, model, embeddings, xyz, zs, dirs, ts, max_t, want_transient, flow_heads, test_time,
                     noise_std, t_embedded, a_embedded, kwargs)
+    keys = kwargs.get("keys", None)
+    if keys is not None:
+        missing = [k for k in keys if k not in results]
+        if missing:
+            raise KeyError(f"render_rays(keys=...): {missing} not produced in this mode; available: {list(results)}")
+        wanted = set(keys)
+        results = {k: v for k, v in results.items() if k in wanted}
     return results
 
 

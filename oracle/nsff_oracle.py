@@ -405,6 +405,10 @@ def render_rays(models: Dict[str, FieldSpec], enc: Encoders, rays: torch.Tensor,
             if test_time:
                 results["transient_zs_fine"] = zs_trans
         zs = torch.sort(torch.cat(merged, -1), -1)[0]
+        if "_zs_fine" in kwargs:
+            # TEST HOOK (not in the reference): evaluate the fine pass on externally supplied depths, so that a bf16
+            # implementation whose resampled depths differ in the last bits can still be compared sample by sample
+            zs = kwargs["_zs_fine"]
 
     spec = models["fine"]                                                      # :350-360
     if spec.encode_appearance:

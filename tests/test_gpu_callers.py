@@ -137,3 +137,74 @@ def test_training_step_with_the_reference_loss(installed, precision, tol, median
     if median_tol is not None:
         med = sorted(errs.values())[len(errs) // 2]
         assert med <= median_tol, f"median relative gradient error {med:.3e}"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# bf16 accuracy statement (SURVEY section 8c / BASELINE section 4): the tensor-core path against the INTRINSIC bf16
+# envelope of the reference itself - the unmodified reference under torch.autocast('cpu', bfloat16) vs itself in fp32,
+# same energised weights, same rays.  Measured (profiles/r02q_bf16_envelope.txt): forward keys 0.5-1.2 x the envelope,
+# parameter gradients through NeRFWLoss 0.3-1.5 x (two bias gradients with tiny norms: 3-5 x, below the absolute floor).
+# ---------------------------------------------------------------------------------------------------------------------
+ENV_KW = dict(N_samples=64, perturb=0, noise_std=0, N_importance=0, test_time=False,
+              output_transient_flow=["fw", "bw", "disocc"])
+
+
+@pytest.mark.parametrize("seed", [6, 16])
+def test_bf16_forward_error_is_within_twice_the_reference_autocast_envelope(installed, seed):
+    from parity_util import max_abs
+    ref = ref_loader.load()
+    models, emb, _, _ = build_fields(W=256, seed=seed, precision="bf16", n_frames=8)
+    rmodels, remb = ref_loader.build_reference_fields(models, emb)
+    rays, ts = synthetic_rays(96, n_frames=8, seed=seed + 1)
+    with torch.no_grad():
+        want = ref.rendering.render_rays(rmodels, remb, rays, ts, 7, **ENV_KW)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            env = ref.rendering.render_rays(rmodels, remb, rays, ts, 7, **ENV_KW)
+        got = installed(models, emb, rays.cuda(), ts.cuda(), 7, **ENV_KW)
+    assert list(got) == list(want)
+    bad = []
+    for k in want:
+        ours, envelope = max_abs(got[k], want[k]), max_abs(env[k].float(), want[k])
+        floor = 2e-6 * max(1.0, float(want[k].abs().max()))          # fp32-exact keys (depths, points): rounding only
+        if ours > 2.0 * envelope + floor:
+            bad.append(f"{k}: ours {ours:.3e} > 2 x envelope {envelope:.3e}")
+    assert not bad, "\n".join(bad)
+
+
+def test_bf16_gradients_are_within_the_reference_autocast_envelope(installed):
+    """Every parameter gradient through the reference's NeRFWLoss: relative L2 error vs the fp32 reference autograd
+    <= 2.5 x the error of the reference's own autograd under bf16 autocast + 2e-2 (energised weights: the hard case)."""
+    import ref_harness as H
+    ref = ref_loader.load()
+    models, emb, _, _ = build_fields(W=256, seed=31, precision="bf16", n_frames=8)
+    R, S = 40, 24
+    rays, ts = synthetic_rays(R, n_frames=8, seed=32)
+    batch = H.make_batch(rays, ts, img_wh=(64, 36), seed=33)
+    kwargs = dict(epoch=4, **TRAIN_KW)
+
+    def ref_grads(autocast):
+        rm, re = ref_loader.build_reference_fields(models, emb)
+        for m in rm.values():
+            m.requires_grad_(True)
+        with torch.autocast("cpu", dtype=torch.bfloat16, enabled=autocast):
+            res = H.system_forward(ref.rendering.render_rays, rm, re, rays, ts, 8, S, 0, 0, 0, 64, **kwargs)
+        res = {k: v.float() for k, v in res.items()}
+        sum(H.make_loss(ref, 8, img_wh=(64, 36))(res, batch, **kwargs).values()).backward()
+        return {f"{key}.{n}": p.grad.double() for key, m in rm.items() for n, p in m.named_parameters() if p.grad is not None}
+
+    g32, g16 = ref_grads(False), ref_grads(True)
+    for m in models.values():
+        m.requires_grad_(True)
+    res = H.system_forward(installed, models, emb, rays.cuda(), ts.cuda(), 8, S, 0, 0, 0, 64, **kwargs)
+    sum(H.make_loss(ref, 8, img_wh=(64, 36), device="cuda")(res, H.to_device(batch, "cuda"), **kwargs).values()).backward()
+    bad = []
+    for key, m in models.items():
+        for n, p in m.named_parameters():
+            r = g32.get(f"{key}.{n}")
+            if r is None:
+                continue
+            ours = float((p.grad.cpu().double() - r).norm() / (r.norm() + 1e-12))
+            envelope = float((g16[f"{key}.{n}"] - r).norm() / (r.norm() + 1e-12))
+            if ours > 2.5 * envelope + 2e-2:
+                bad.append(f"{n}: ours {ours:.3e} > 2.5 x envelope {envelope:.3e} + 2e-2")
+    assert not bad, "\n".join(bad)

@@ -256,6 +256,13 @@ def test_render_hierarchical_bf16():
     assert bool((got["zs_fine"][:, 1:] >= got["zs_fine"][:, :-1]).all()), "merged depths must be sorted"
     _compare_hierarchical(got, want, coarse_tol=3e-2, ray_tol=1.5e-2, zs_tol=None)
     assert psnr(got["rgb_fine"], want["rgb_fine"]) >= 45.0
+    # Inverse-CDF resampling is ill-conditioned where the coarse pdf ~ 0, so the bf16 path's resampled depths differ in
+    # a few places and per-sample fine tensors cannot be compared index by index above.  Re-run the oracle's fine pass on
+    # the depths the GPU actually used (oracle test hook `_zs_fine`): now EVERY fine-pass tensor is comparable.
+    want2 = O.render_rays(specs, enc, rays, ts, 7, N_samples=64, N_importance=64, test_time=True,
+                          output_transient_flow=["fw", "bw"], _zs_fine=got["zs_fine"].cpu())
+    fine = {k: v for k, v in got.items() if k.endswith("_fine") and not k.endswith("zs_fine")}
+    compare_dicts(fine, {k: want2[k] for k in fine}, BF16_TOL, default_tol=None, check_order=False)
 
 
 @pytest.mark.parametrize("R,S", [(64, 128), (5, 77), (300, 128)])

@@ -68,3 +68,19 @@ def test_pos_embedding_refuses_to_drop_a_graph():
         PosEmbedding(9, 10)(x)
     with torch.no_grad():
         assert PosEmbedding(9, 10)(x).shape == (4, 63)
+
+
+def test_keys_selects_outputs_in_reference_order():
+    """SURVEY section 8f #3: render_rays(keys=...) drops the per-sample tensors eval.f would otherwise .cpu()."""
+    from nsff_pl_b200.models.rendering import PER_RAY_KEYS, render_rays
+    models, emb, _, _ = build_fields(W=256, seed=13, precision="bf16", n_frames=8)
+    rays, ts = synthetic_rays(16, n_frames=8, seed=14)
+    kw = dict(N_samples=16, test_time=True, output_transient_flow=["fw", "bw"])
+    with torch.no_grad():
+        full = render_rays(models, emb, rays.cuda(), ts.cuda(), 7, **kw)
+        some = render_rays(models, emb, rays.cuda(), ts.cuda(), 7, keys=PER_RAY_KEYS, **kw)
+        with pytest.raises(KeyError):
+            render_rays(models, emb, rays.cuda(), ts.cuda(), 7, keys=["rgb_fine", "rgb_fw"], **kw)   # no warp at test time
+    assert list(some) == [k for k in full if k in PER_RAY_KEYS] and len(some) == len(PER_RAY_KEYS)
+    assert all(torch.equal(some[k], full[k]) for k in some)
+    assert sum(v.numel() for v in some.values()) * 8 < sum(v.numel() for v in full.values())     # (x 60 at 128 samples)
