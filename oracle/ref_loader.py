@@ -52,6 +52,53 @@ def stage(force=False):
     return True
 
 
+
+def _nvrtc_compile_with_cache(source):
+    """What models/softsplat.py:200-202 asks of cupy: compile a CUDA source string and hand back an object whose
+    get_function(name) returns a callable launched as f(grid=..., block=..., args=[...]).  Implemented with NVRTC and
+    the driver API from cuda-python, so that the reference's OWN splat kernel string (softsplat.py:6-44, specialised by
+    its own cupy_kernel(), softsplat.py:148-196) can be executed unmodified on a GPU box that has no cupy
+    (tests/golden/make_splat_golden.py).  Only ever called when the reference's interpolate() runs on CUDA tensors."""
+    import ctypes
+    import torch
+    try:
+        from cuda.bindings import driver as cu, nvrtc
+    except ImportError:                               # older cuda-python layout
+        from cuda import cuda as cu, nvrtc
+
+    def ok(res):
+        err, *rest = res
+        if int(err) != 0:
+            raise RuntimeError(f"cuda-python call failed: {err}")
+        return rest[0] if len(rest) == 1 else rest
+
+    major, minor = torch.cuda.get_device_capability()
+    prog = ok(nvrtc.nvrtcCreateProgram(source.encode(), b"softsplat.cu", 0, [], []))
+    opts = [f"--gpu-architecture=compute_{major}{minor}".encode()]
+    res = nvrtc.nvrtcCompileProgram(prog, len(opts), opts)
+    if int(res[0]) != 0:
+        log = b" " * ok(nvrtc.nvrtcGetProgramLogSize(prog))
+        nvrtc.nvrtcGetProgramLog(prog, log)
+        raise RuntimeError("NVRTC failed:\n" + log.decode(errors="replace"))
+    ptx = b" " * ok(nvrtc.nvrtcGetPTXSize(prog))
+    ok(nvrtc.nvrtcGetPTX(prog, ptx))
+    module = ok(cu.cuModuleLoadData(ptx))
+
+    class _Module:
+        def get_function(self, name):
+            fn = ok(cu.cuModuleGetFunction(module, name.encode()))
+
+            def launch(grid, block, args):
+                vals = tuple(int(a) for a in args)
+                types_ = tuple([ctypes.c_int] + [ctypes.c_void_p] * (len(vals) - 1))   # (n, pointers...)
+                stream = torch.cuda.current_stream().cuda_stream
+                ok(cu.cuLaunchKernel(fn, grid[0], grid[1], grid[2], block[0], block[1], block[2], 0, stream,
+                                     (vals, types_), 0))
+            return launch
+
+    return _Module()
+
+
 def _shims():
     import torch
     import torch.nn.functional as F
@@ -85,7 +132,7 @@ def _shims():
     cupy = types.ModuleType("cupy")
     cupy.memoize = lambda **kw: (lambda f: f)
     cupy.ndarray = type("ndarray", (), {})          # einops probes sys.modules['cupy'].ndarray
-    cupy.cuda = types.SimpleNamespace(compile_with_cache=None)
+    cupy.cuda = types.SimpleNamespace(compile_with_cache=_nvrtc_compile_with_cache)
     return {"kornia": kornia, "kornia.filters": filters, "cupy": cupy}
 
 

@@ -405,12 +405,15 @@ def test_interpolate_matches_oracle_and_reference_fixture():
     from our own render_rays(test_time=True) views (strided inputs), vs the oracle on the same results.
     Tolerance 2e-5: atomics make the splat accumulation order non-deterministic at the 1e-7 level."""
     from nsff_pl_b200.models.rendering import interpolate, render_rays
-    meta, a = golden_io.load("interpolate_w64")
-    rt = {k: a[f"t.{k}"].cuda() for k in meta["keys"]}
-    rp = {k: a[f"tp1.{k}"].cuda() for k in meta["keys"]}
-    for dt in meta["dts"]:
-        rgb, depth = interpolate(rt, rp, dt, a["K"], a["c2w"], tuple(meta["img_wh"]))
-        assert max_abs(rgb, a[f"out.rgb.{dt}"]) <= 2e-5 and max_abs(depth, a[f"out.depth.{dt}"]) <= 2e-5, dt
+    # interpolate_cuda_w64: the unmodified reference interpolate() INCLUDING its own CUDA splat kernel, run on a B200
+    # (tests/golden/make_splat_golden.py); interpolate_w64: the same with the splat op restated on the CPU (round 1)
+    for fixture in ("interpolate_cuda_w64", "interpolate_w64"):
+        meta, a = golden_io.load(fixture)
+        rt = {k: a[f"t.{k}"].cuda() for k in meta["keys"]}
+        rp = {k: a[f"tp1.{k}"].cuda() for k in meta["keys"]}
+        for dt in meta["dts"]:
+            rgb, depth = interpolate(rt, rp, dt, a["K"], a["c2w"], tuple(meta["img_wh"]))
+            assert max_abs(rgb, a[f"out.rgb.{dt}"]) <= 2e-5 and max_abs(depth, a[f"out.depth.{dt}"]) <= 2e-5, (fixture, dt)
     # end to end at W=256 on the tensor-core path
     models, emb, specs, enc = build_fields(W=256, seed=41, precision="bf16", n_frames=8)
     w, h = 24, 16
