@@ -212,7 +212,7 @@ def _max_over_ranks(ms, dev, world):
     return ms
 
 
-def train_record(args, rank, local_rank, world, steps, warmup):
+def train_record(args, rank, local_rank, world, steps, warmup, loss_impl="fused"):
     """BASELINE.json configs[2]: training step, 1024-ray batch x 128 samples per GPU, full NSFF + warp, bf16 tensor-core
     forward (every layer evaluated, activations saved), tensor-core backward, the reference's NeRFWLoss (losses.py:31-171,
     unmodified, staged in baseline/_ref; photometric + flow + cycle + regularisers) on our result dict, Adam step and bf16
@@ -236,17 +236,30 @@ def train_record(args, rank, local_rank, world, steps, warmup):
     rays, ts = rays.to(dev), ts.to(dev)
     kw = dict(N_samples=S, perturb=1.0, noise_std=1.0, N_importance=0, test_time=False,
               output_transient_flow=["fw", "bw", "disocc"])
+    # loss: the fused drop-in (nsff_pl_b200.losses.NeRFWLoss, csrc/nsff_loss.cu; parity-tested term by term and gradient by
+    # gradient against the reference class in tests/test_gpu_loss.py) or, with --loss reference, the UNMODIFIED reference
+    # class (losses.py:31-171, staged in baseline/_ref) on our result dict
     loss_kind = "surrogate"
     loss_fn = batch = None
     try:
-        from oracle import ref_loader
-        if ref_loader.available():
-            import ref_harness as H
-            loss_fn = H.make_loss(ref_loader.load(), N_FRAMES, img_wh=IMG_WH, device=dev)
-            batch = H.to_device(H.make_batch(rays.cpu(), ts.cpu(), img_wh=IMG_WH, seed=7 + rank), dev)
-            loss_kind = "reference NeRFWLoss (losses.py:31-171, unmodified)"
+        import ref_harness as H
+        batch = H.to_device(H.make_batch(rays.cpu(), ts.cpu(), img_wh=IMG_WH, seed=7 + rank), dev)
+        Ks, Ps = H.make_cameras(N_FRAMES, IMG_WH, 0)
+        if loss_impl == "fused":
+            from nsff_pl_b200.losses import NeRFWLoss
+            loss_fn = NeRFWLoss()
+            loss_fn.register_buffer("Ks", Ks)
+            loss_fn.register_buffer("Ps", Ps)
+            loss_fn.max_t = N_FRAMES - 1
+            loss_fn = loss_fn.to(dev)
+            loss_kind = "nsff_pl_b200.losses.NeRFWLoss (fused drop-in for losses.py:31-171: 3 launches fwd + 1 bwd)"
+        else:
+            from oracle import ref_loader
+            if ref_loader.available():
+                loss_fn = H.make_loss(ref_loader.load(), N_FRAMES, img_wh=IMG_WH, device=dev)
+                loss_kind = "reference NeRFWLoss (losses.py:31-171, unmodified)"
     except Exception as e:  # the staged reference is optional on a box that never ran build()
-        loss_kind = f"surrogate ({type(e).__name__}: reference loss unavailable)"
+        loss_kind = f"surrogate ({type(e).__name__}: loss unavailable)"
     target = torch.rand(R, 3, device=dev)
 
     def mark(name):
@@ -521,6 +534,8 @@ def main():
                     help="render workload: skip the train / sequence / strong sub-records of the JSON line")
     ap.add_argument("--grad-precision", default="bf16", choices=["bf16", "fp32"],
                     help="train workload: tensor-core backward (default) or the fp32 verification backward")
+    ap.add_argument("--loss", default="fused", choices=["fused", "reference"],
+                    help="train workload: nsff_pl_b200.losses.NeRFWLoss (default) or the unmodified reference class")
     ap.add_argument("--bwd-recompute", action="store_true",
                     help="train workload: re-evaluate the layers in the backward instead of saving them in the forward")
     ap.add_argument("--workload", default="render", choices=["render", "train", "sequence"],
@@ -541,8 +556,10 @@ def main():
     dev = _init_dist(local_rank, world)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
     if args.workload in ("train", "sequence"):
-        fn = train_record if args.workload == "train" else sequence_record
-        rec = fn(args, rank, local_rank, world, args.steps, args.warmup)
+        if args.workload == "train":
+            rec = train_record(args, rank, local_rank, world, args.steps, args.warmup, loss_impl=args.loss)
+        else:
+            rec = sequence_record(args, rank, local_rank, world, args.steps, args.warmup)
         if rank == 0:
             print(json.dumps(rec), flush=True)
         if world > 1:
@@ -636,6 +653,9 @@ def main():
         if rank == 0:
             sub["eval"] = eval_record(args, rank, local_rank, world, models, emb)
         sub["train"] = train_record(args, rank, local_rank, world, 20, 5)
+        ref_loss = train_record(args, rank, local_rank, world, 10, 3, loss_impl="reference")
+        sub["train"]["with_reference_loss_class"] = {k: ref_loss[k] for k in ("ms_per_step", "value", "phase_ms")}
+        sub["train"]["with_reference_loss_class"]["loss"] = ref_loss["config"]["loss"]
         sub["sequence"] = sequence_record(args, rank, local_rank, world, 3, 3)
 
     if rank == 0:

@@ -370,6 +370,55 @@ NSFF_API int nsff_frame_rays(const float* K4 /*host*/, const float* c2w12 /*host
 NSFF_API int nsff_ndc_rays(const float* K4 /*host*/, float near, float shift_near, const float* rays_o,
                            const float* rays_d, int64_t n, float* out_o, float* out_d, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * f2  NeRFWLoss                                                     losses.py:8-29, 31-171
+ *     The training loss on the result dict of render_rays(test_time=False, output_transient_flow=['fw','bw','disocc']):
+ *     colour, shift/scale-invariant depth, entropy, static/dynamic cross-entropy, 2D-3D flow consistency, photometric
+ *     warp, cycle consistency and the three scene-flow regularisers - every term of losses.py:72-161 - in three
+ *     launches forward and one backward (the reference spends ~300 ATen kernels on it).  All tensors fp32 contiguous;
+ *     `medians` = {median(depth_fine), median(-disps), median(depth_coarse)} (torch.median, device floats);
+ *     `terms` receives the NSFF_LOSS_TERMS means in nsff_loss_term order (flow terms: mean over the rays whose
+ *     projected depth is positive and that have a neighbouring frame; 0 when there is none).  topk < 1 is not supported.
+ */
+enum nsff_loss_term {
+  NSFF_L_COL = 0, NSFF_L_DISP, NSFF_L_ENT, NSFF_L_CROSS, NSFF_L_FLOW_FW, NSFF_L_FLOW_BW, NSFF_L_PHO, NSFF_L_CYC,
+  NSFF_L_REG_TEMP, NSFF_L_REG_MIN, NSFF_L_REG_SP, NSFF_LOSS_TERMS
+};
+typedef struct {
+  int64_t R; int32_t S;
+  int32_t has_flow;            /* kwargs['output_transient_flow'] non-empty: all terms; else colour + depth only   */
+  int32_t thickness;           /* window of the zero-padded box filter over the transient weights (losses.py:63)   */
+  int32_t n_reg;               /* int(S * z_far): samples the regularisers see (losses.py:147)                     */
+  int32_t n_frames, max_t;
+  float lambda_geo_d, lambda_geo_f, lambda_reg, lambda_ent;
+  float cross_entropy_w;       /* lambda_ent/5 * min(epoch/10, 1)  (losses.py:90)                                  */
+  /* render_rays outputs */
+  const float *rgb_fine, *depth_fine, *rgb_coarse, *depth_coarse;       /* (R,3) (R); coarse pair may be NULL      */
+  const float *tw, *sw;                                                  /* transient / static weights (R,S)        */
+  const float *xyz_fw, *xyz_bw, *rgb_fw, *rgb_bw;                        /* (R,3)                                   */
+  const float *disocc_fw, *disocc_bw;                                    /* (R)    detached                         */
+  const float *disoccs_fw, *disoccs_bw;                                  /* (R,S)  detached                         */
+  const float *xyzs_fw_bw, *xyzs_bw_fw, *xyzs_fine, *xyzs_fw, *xyzs_bw;  /* (R,S,3)                                 */
+  /* targets (the training batch, datasets/monocular.py:240-249) and the buffers train.py:135-138 registers */
+  const float *rgbs, *disps, *uv_fw, *uv_bw;
+  const int64_t *cam_ids, *ts;
+  const float *Ks;             /* (n_cams, 3, 3)                                                                     */
+  const float *Ps;             /* (n_cams, n_frames, 3, 4)                                                           */
+  const float *ray_weights;    /* kwargs['weights'] (R) or NULL                                                      */
+  const float *medians;        /* 3 device floats, see above                                                         */
+  float *stats;                /* nsff_loss_stats_floats() floats, written by the forward, read by the backward      */
+  float *term_sums;            /* NSFF_LOSS_TERMS floats of scratch                                                  */
+  float *terms;                /* NSFF_LOSS_TERMS floats: the loss dict                                              */
+  /* backward: upstream gradient of every term and the gradients of their g-weighted sum (overwritten) */
+  const float *g_terms;
+  float *d_rgb_fine, *d_depth_fine, *d_rgb_coarse, *d_depth_coarse, *d_tw, *d_sw, *d_xyz_fw, *d_xyz_bw, *d_rgb_fw,
+        *d_rgb_bw, *d_xyzs_fw_bw, *d_xyzs_bw_fw, *d_xyzs_fw, *d_xyzs_bw;
+} nsff_loss_args;
+
+NSFF_API int nsff_loss_stats_floats(void);
+NSFF_API int nsff_nerfw_loss_forward(const nsff_loss_args* args /*host*/, void* stream);
+NSFF_API int nsff_nerfw_loss_backward(const nsff_loss_args* args /*host*/, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,6 +93,20 @@ class InterpolateArgs(C.Structure):
                 ("rgb_tp1", C.c_void_p), ("alpha_tp1", C.c_void_p), ("flow_bw", C.c_void_p), ("ld_tp1", C.c_int32)]
 
 
+class LossArgs(C.Structure):
+    _PTRS_IN = ("rgb_fine", "depth_fine", "rgb_coarse", "depth_coarse", "tw", "sw", "xyz_fw", "xyz_bw", "rgb_fw", "rgb_bw",
+                "disocc_fw", "disocc_bw", "disoccs_fw", "disoccs_bw", "xyzs_fw_bw", "xyzs_bw_fw", "xyzs_fine", "xyzs_fw",
+                "xyzs_bw", "rgbs", "disps", "uv_fw", "uv_bw", "cam_ids", "ts", "Ks", "Ps", "ray_weights", "medians",
+                "stats", "term_sums", "terms", "g_terms")
+    _PTRS_GRAD = ("d_rgb_fine", "d_depth_fine", "d_rgb_coarse", "d_depth_coarse", "d_tw", "d_sw", "d_xyz_fw", "d_xyz_bw",
+                  "d_rgb_fw", "d_rgb_bw", "d_xyzs_fw_bw", "d_xyzs_bw_fw", "d_xyzs_fw", "d_xyzs_bw")
+    _fields_ = ([("R", C.c_int64), ("S", C.c_int32), ("has_flow", C.c_int32), ("thickness", C.c_int32),
+                 ("n_reg", C.c_int32), ("n_frames", C.c_int32), ("max_t", C.c_int32),
+                 ("lambda_geo_d", C.c_float), ("lambda_geo_f", C.c_float), ("lambda_reg", C.c_float),
+                 ("lambda_ent", C.c_float), ("cross_entropy_w", C.c_float)]
+                + [(n, C.c_void_p) for n in _PTRS_IN] + [(n, C.c_void_p) for n in _PTRS_GRAD])
+
+
 class ImgGemmArgs(C.Structure):
     _fields_ = [("a_img", C.c_void_p), ("a_chunks", C.c_int32), ("b_blocks", C.c_void_p), ("N", C.c_int32),
                 ("bias", C.c_void_p), ("epi", C.c_int32), ("out_img", C.c_void_p), ("mask_img", C.c_void_p),
@@ -151,6 +165,9 @@ PROTOTYPES = {
     "nsff_composite_backward": (C.c_int, [C.POINTER(CompositeArgs), C.POINTER(CompositeGrads), C.c_void_p]),
     "nsff_interpolate_scratch_floats": (C.c_size_t, [C.c_int64, C.c_int]),
     "nsff_interpolate": (C.c_int, [C.POINTER(InterpolateArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsff_loss_stats_floats": (C.c_int, []),
+    "nsff_nerfw_loss_forward": (C.c_int, [C.POINTER(LossArgs), C.c_void_p]),
+    "nsff_nerfw_loss_backward": (C.c_int, [C.POINTER(LossArgs), C.c_void_p]),
     "nsff_frame_rays": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p]),
     "nsff_ndc_rays": (C.c_int, [C.POINTER(C.c_float), C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int64,

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("NSFF_LIB_OUT") or os.path.join(HERE, "libnsff_b200.so")      # NSFF_LIB_OUT: side build (tools/timeline.py)
 STAMP = LIB + ".stamp"
-SOURCES = ["nsff_points.cu", "nsff_composite.cu", "nsff_composite_bwd.cu", "nsff_resample.cu", "nsff_interpolate.cu", "nsff_field_fp32.cu", "nsff_field_tc.cu", "nsff_field_bwd_tc.cu"]
+SOURCES = ["nsff_points.cu", "nsff_composite.cu", "nsff_composite_bwd.cu", "nsff_resample.cu", "nsff_interpolate.cu", "nsff_loss.cu", "nsff_field_fp32.cu", "nsff_field_tc.cu", "nsff_field_bwd_tc.cu"]
 EXTRA = os.environ.get("NSFF_NVCC_EXTRA", "").split()      # e.g. -DNSFF_TIMELINE for tools/timeline.py
 NVCC_FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -24,7 +24,7 @@ def declared_symbols():
 
 def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
-    assert len(syms) == 37, syms
+    assert len(syms) == 40, syms
     for must in ("nsff_field_forward", "nsff_composite", "nsff_sample_points", "nsff_sample_pdf", "nsff_field_pack",
                  "nsff_field_backward_fp32", "nsff_composite_backward"):
         assert must in syms
@@ -72,6 +72,8 @@ def test_struct_layouts_match_the_c_header(libpath, tmp_path):
         "nsff_composite_grads": ["static_sigmas", "xyzs_fw_bw", "depth", "xyz_bw_ray", "rgb_bw", "d_raw", "d_raw_bw"],
         "nsff_field_grads": ["static_w", "static_dir_b", "trans_w", "trans_bw_b"],
         "nsff_interpolate_args": ["R", "S", "h", "dt", "cy", "P", "xyzs", "static_alpha", "ld_t", "rgb_tp1", "ld_tp1"],
+        "nsff_loss_args": ["R", "S", "n_reg", "max_t", "lambda_geo_d", "cross_entropy_w", "rgb_fine", "tw", "disoccs_bw",
+                           "xyzs_bw", "rgbs", "cam_ids", "Ps", "medians", "terms", "g_terms", "d_rgb_fine", "d_xyzs_bw"],
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "nsff_b200.h"', "int main(void){"]
     for st, fs in fields.items():
@@ -86,7 +88,7 @@ def test_struct_layouts_match_the_c_header(libpath, tmp_path):
     mirror = {"nsff_field_desc": _cabi.FieldDesc, "nsff_field_params": _cabi.FieldParams,
               "nsff_points": _cabi.Points, "nsff_composite_args": _cabi.CompositeArgs,
               "nsff_composite_grads": _cabi.CompositeGrads, "nsff_field_grads": _cabi.FieldGrads,
-              "nsff_interpolate_args": _cabi.InterpolateArgs}
+              "nsff_interpolate_args": _cabi.InterpolateArgs, "nsff_loss_args": _cabi.LossArgs}
     for st, cls in mirror.items():
         assert int(got[st]) == C.sizeof(cls), st
         for f in fields[st]:
