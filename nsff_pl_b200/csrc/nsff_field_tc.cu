@@ -25,7 +25,9 @@
 //                     (48), PE(dir) (27 -> 32) [+ appearance code (48)]  (128 rows x 64 bf16, 128B-swizzled, K-major)
 //   smem  B operand : 10-stage ring of weight pieces ((N/2) x 64 bf16 per CTA) streamed from the L2-resident field pack
 //                     with cp.async.bulk + mbarrier complete_tx
-//   warps 0-15      : prologue (encoding) + epilogue (4 TMEM lane quadrants x 4 column parts)
+//   warps 0-15      : epilogue (4 TMEM lane quadrants x 4 column parts)
+//   warps 18-19     : prologue: encode the NEXT tile's inputs into the extra chunks as soon as the issuer's commit says
+//                     the current tile's last MMA that reads them has completed - concurrently with the epilogues
 //   warp  16        : weight + bias producer (one elected lane)
 //   warp  17        : leader CTA: tcgen05.mma issuer (one elected lane walks a flat, host-built list of K-chunk ops);
 //                     peer CTA: relays "my weight half has landed" to the leader's barriers
@@ -228,7 +230,8 @@ __global__ void __launch_bounds__(256) merge_linear_kernel(const __grid_constant
 // ---------------------------------------------------------------------------------------------
 constexpr int kTileM = 128;
 constexpr int kEpiWarps = 16;        // 4 TMEM lane quadrants x 4 column parts
-constexpr int kThreads = (kEpiWarps + 2) * 32;
+constexpr int kPrologueWarps = 2;       // dedicated input-encoding warps (18 -> 20 warps: same 96-register allocation granule)
+constexpr int kThreads = (kEpiWarps + 2 + kPrologueWarps) * 32;
 constexpr uint32_t kChunkBytes = 128 * 128;          // 128 rows x 64 bf16
 constexpr uint32_t kSmemBias = 21 * 1024;            // the module's whole fp32 bias table (<= 5200 floats), resident
 constexpr uint32_t kSmemBar = 512;
@@ -254,7 +257,7 @@ struct Cfg {
   static constexpr uint32_t kSmemTotal = kSmemA + kSmemB + kSmemBias + kSmemBar + kSmemDbg + 1024;   // + alignment slack
 };
 
-enum : uint8_t { OP_TS = 1, OP_FIRST = 2, OP_LAST = 4, OP_ADV_HID = 8, OP_TWO = 16 };
+enum : uint8_t { OP_TS = 1, OP_FIRST = 2, OP_LAST = 4, OP_ADV_HID = 8, OP_TWO = 16, OP_EXTRA_DONE = 32 };
 
 // One or two K-chunks (4 tcgen05.mma of K = 16 each) of one sub-step: what the issuer issues (first 16 bytes, one
 // constant load) and what the producer copies (second 16 bytes).
@@ -350,8 +353,9 @@ enum {
   BAR_W_FULL = 0,                           // [kMaxStages] weight stage landed (tx + partner relay)
   BAR_W_EMPTY = BAR_W_FULL + kMaxStages,    // [kMaxStages] MMAs that read the stage completed (commit)
   BAR_HID_FULL = BAR_W_EMPTY + kMaxStages,  // [2]  bf16 image of hidden channels 0-127 / 128-255 written to TMEM (both CTAs)
-  BAR_EXTRA_FULL = BAR_HID_FULL + 2,        // [1]  prologue chunks written
-  BAR_ACC_FULL = BAR_EXTRA_FULL + 1,        // [kAccIds] accumulator complete (commit)
+  BAR_EXTRA_FULL = BAR_HID_FULL + 2,        // [1]  prologue chunks written (prologue warps of both CTAs)
+  BAR_EXTRA_EMPTY = BAR_EXTRA_FULL + 1,     // [1]  every MMA that reads the prologue chunks of this tile has completed (commit)
+  BAR_ACC_FULL = BAR_EXTRA_EMPTY + 1,       // [kAccIds] accumulator complete (commit)
   BAR_ACC_EMPTY = BAR_ACC_FULL + kAccIds,   // [kAccIds] accumulator drained
   BAR_COUNT = BAR_ACC_EMPTY + kAccIds
 };
@@ -379,132 +383,106 @@ __device__ __forceinline__ void store_unit_at(uint32_t row_base, int rsw, int un
                  pack_bf16x2(f[6], f[7]));
 }
 
-// column c (0..63) of the xyz encoding row [x, sin(2^0 x), cos(2^0 x), ...] (nerf.py:17-30); col 63 = pad
-// PE(xyz) columns [16*kPart, 16*kPart+16) of one row (nerf.py:17-30): col 0-2 = x, then per octave f: sin(2^f x) (3),
-// cos(2^f x) (3); col 63 is the zero pad.  One accurate sincosf at octave 0, doubling up to the octaves this part needs.
-template <int kPart>
-__device__ __forceinline__ void encode_pe_part(uint32_t chPE, int row, const float (&base)[3]) {
-  constexpr int lo = 16 * kPart, hi = lo + 16;
-  constexpr int f_last = kPart == 0 ? 2 : kPart == 1 ? 4 : kPart == 2 ? 7 : 9;
-  float sn[3], cs[3], v[16];
+// One row of the octave encoding [x, sin(2^0 x), cos(2^0 x), ..., sin(2^(F-1) x), cos(2^(F-1) x)] (nerf.py:17-30) into the
+// first 3+6F columns of a swizzled 64-column chunk (remaining columns of the last touched unit zero): one accurate
+// sincosf at octave 0, then the doubling recurrence (pe_next_octave, nsff_common.cuh).
+template <int kFreqs, int kUnits>
+__device__ __forceinline__ void encode_octaves(uint32_t chunk, int row, const float (&x)[3]) {
+  float sn[3], cs[3], v[kUnits * 8];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) sincosf(base[c], &sn[c], &cs[c]);
+  for (int i = 0; i < kUnits * 8; ++i) v[i] = i < 3 ? x[i % 3] : 0.f;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = (lo + i < 3) ? base[(lo + i) % 3] : 0.f;
+  for (int c = 0; c < 3; ++c) sincosf(x[c], &sn[c], &cs[c]);
 #pragma unroll
-  for (int f = 0; f <= f_last; ++f) {
+  for (int f = 0; f < kFreqs; ++f) {
 #pragma unroll
-    for (int r = 0; r < 6; ++r) {
-      const int col = 3 + 6 * f + r;
-      if (col >= lo && col < hi) v[col - lo] = r < 3 ? sn[r % 3] : cs[r % 3];
-    }
-    if (f < f_last) pe_next_octave(sn, cs);
+    for (int r = 0; r < 6; ++r) v[3 + 6 * f + r] = r < 3 ? sn[r % 3] : cs[r % 3];
+    if (f + 1 < kFreqs) pe_next_octave(sn, cs);
   }
 #pragma unroll
-  for (int u = 0; u < 2; ++u) {
+  for (int u = 0; u < kUnits; ++u) {
     const float w[8] = {v[8 * u], v[8 * u + 1], v[8 * u + 2], v[8 * u + 3], v[8 * u + 4], v[8 * u + 5], v[8 * u + 6], v[8 * u + 7]};
-    store_unit(chPE, row, kPart * 2 + u, w);
+    store_unit(chunk, row, u, w);
   }
 }
 
-// Prologue of one tile: encode the inputs of `row` into the PE / time-code / PE(dir) chunks (bf16, swizzled).
-// Four threads (part 0..3) share a row: each writes 2 of the 8 PE units; parts 0-2 also write 2 of the 6
-// time-code units, part 3 the 4 PE(dir) units.
-__device__ __forceinline__ void encode_tile_row(const FwdParams& P, uint32_t sA, int row, int part, int64_t p,
-                                                bool valid) {
-  const uint32_t chPE = sA + 0 * kChunkBytes, chT = sA + 1 * kChunkBytes, chD = sA + 2 * kChunkBytes;
+// 48 code floats (time / appearance) of one row -> units 0..5 of a chunk
+__device__ __forceinline__ void encode_code48(uint32_t chunk, int row, const float* src) {
+  const float4* tp = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int u = 0; u < 6; ++u) {
+    const float4 a = __ldg(tp + 2 * u), b = __ldg(tp + 2 * u + 1);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    store_unit(chunk, row, u, v);
+  }
+}
+
+// the position of point p (+ the flow offset of the legacy warp-pass interface): loaded separately so that the prologue
+// warps can have the loads of all their rows in flight before they start encoding
+__device__ __forceinline__ void load_point(const FwdParams& P, int64_t p, float (&base)[3]) {
+  if (P.x_emb != nullptr) return;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = P.pts.xyz[p * 3 + c];
+    if (P.pts.offset) v = __fadd_rn(v, P.pts.offset[p * P.pts.offset_ld + c]);
+    base[c] = v;
+  }
+}
+
+// Prologue of one tile row: encode the inputs of point p into the PE / time-code / PE(dir) [/ appearance] chunks.
+__device__ __forceinline__ void encode_tile_row(const FwdParams& P, uint32_t sA, int row, int64_t p, bool valid,
+                                                const float (&base)[3]) {
+  const uint32_t chPE = sA + 0 * kChunkBytes, chT = sA + 1 * kChunkBytes, chD = sA + 2 * kChunkBytes,
+                 chA = sA + 3 * kChunkBytes;
   if (P.x_emb == nullptr) {
     const int64_t ray = p / P.pts.S;
-    float base[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float v = P.pts.xyz[p * 3 + c];
-      if (P.pts.offset) v = __fadd_rn(v, P.pts.offset[p * P.pts.offset_ld + c]);
-      base[c] = v;
-    }
-    if (part == 0 && valid && P.pts.xyz_out) {
+    if (valid && P.pts.xyz_out) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) P.pts.xyz_out[p * 3 + c] = base[c];
     }
-    if (part == 0) encode_pe_part<0>(chPE, row, base);
-    else if (part == 1) encode_pe_part<1>(chPE, row, base);
-    else if (part == 2) encode_pe_part<2>(chPE, row, base);
-    else encode_pe_part<3>(chPE, row, base);
-    if (P.need_t && part < 3) {
+    encode_octaves<10, 8>(chPE, row, base);                  // 63 columns + the zero pad
+    if (P.need_t) {
       int64_t trow = ray;
       if (P.pts.t_index) {
         trow = P.pts.t_index[ray] + P.pts.t_shift;
         trow = trow < 0 ? 0 : (trow > P.pts.max_t ? P.pts.max_t : trow);
       }
-      const float4* tp = reinterpret_cast<const float4*>(P.pts.t_table + trow * 48) + part * 4;
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        float4 a = __ldg(tp + 2 * u), b = __ldg(tp + 2 * u + 1);
-        float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        store_unit(chT, row, part * 2 + u, v);
-      }
+      encode_code48(chT, row, P.pts.t_table + trow * 48);
     }
-    if (P.need_a && part < 3) {
-      const int64_t arow = P.pts.a_index ? P.pts.a_index[ray] : ray;
-      const float4* ap = reinterpret_cast<const float4*>(P.pts.a_table + arow * 48) + part * 4;
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        float4 a = __ldg(ap + 2 * u), b = __ldg(ap + 2 * u + 1);
-        float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        store_unit(sA + 3 * kChunkBytes, row, part * 2 + u, v);
-      }
-    }
-    if (P.need_dir && part == 3) {
-      float d[3] = {P.pts.dirs[ray * 3 + 0], P.pts.dirs[ray * 3 + 1], P.pts.dirs[ray * 3 + 2]};
-      float sn[3], cs[3], pe[32];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) sincosf(d[c], &sn[c], &cs[c]);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) pe[i] = i < 3 ? d[i % 3] : 0.f;
-#pragma unroll
-      for (int f = 0; f < 4; ++f) {
-#pragma unroll
-        for (int r = 0; r < 6; ++r) pe[3 + 6 * f + r] = r < 3 ? sn[r % 3] : cs[r % 3];
-        if (f < 3) pe_next_octave(sn, cs);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float v[8] = {pe[8 * u], pe[8 * u + 1], pe[8 * u + 2], pe[8 * u + 3], pe[8 * u + 4], pe[8 * u + 5], pe[8 * u + 6], pe[8 * u + 7]};
-        store_unit(chD, row, u, v);
-      }
+    if (P.need_a) encode_code48(chA, row, P.pts.a_table + (P.pts.a_index ? P.pts.a_index[ray] : ray) * 48);
+    if (P.need_dir) {
+      const float d[3] = {P.pts.dirs[ray * 3 + 0], P.pts.dirs[ray * 3 + 1], P.pts.dirs[ray * 3 + 2]};
+      encode_octaves<4, 4>(chD, row, d);                     // 27 columns, 5 zeros
     }
   } else {
     // embedded mode: x row = [xyz63 | dir27 | a | t48] already encoded by the caller
     const float* xr = P.x_emb + p * P.x_ld;
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < 8; ++u) {
       float v[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        int c = (part * 2 + u) * 8 + i;
-        v[i] = c < 63 ? xr[c] : 0.f;
-      }
-      store_unit(chPE, row, part * 2 + u, v);
+      for (int i = 0; i < 8; ++i) v[i] = u * 8 + i < 63 ? xr[u * 8 + i] : 0.f;
+      store_unit(chPE, row, u, v);
     }
-    if (P.need_t && part < 3) {
+    if (P.need_t) {
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < 6; ++u) {
         float v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = xr[P.c_t + (part * 2 + u) * 8 + i];
-        store_unit(chT, row, part * 2 + u, v);
+        for (int i = 0; i < 8; ++i) v[i] = xr[P.c_t + u * 8 + i];
+        store_unit(chT, row, u, v);
       }
     }
-    if (P.need_a && part < 3) {
+    if (P.need_a) {
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < 6; ++u) {
         float v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = xr[P.c_a + (part * 2 + u) * 8 + i];
-        store_unit(sA + 3 * kChunkBytes, row, part * 2 + u, v);
+        for (int i = 0; i < 8; ++i) v[i] = xr[P.c_a + u * 8 + i];
+        store_unit(chA, row, u, v);
       }
     }
-    if (P.need_dir && part == 3) {
+    if (P.need_dir) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         float v[8];
@@ -515,7 +493,6 @@ __device__ __forceinline__ void encode_tile_row(const FwdParams& P, uint32_t sA,
     }
   }
 }
-
 
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
@@ -595,7 +572,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
       mbar_init(bar(BAR_W_EMPTY + i), 1);
     }
     for (int i = 0; i < 2; ++i) mbar_init(bar(BAR_HID_FULL + i), kEpiWarps * 2);
-    mbar_init(bar(BAR_EXTRA_FULL), kEpiWarps * 2);
+    mbar_init(bar(BAR_EXTRA_FULL), kPrologueWarps * 2);
+    mbar_init(bar(BAR_EXTRA_EMPTY), 1);
     for (int i = 0; i < kAccIds; ++i) {
       mbar_init(bar(BAR_ACC_FULL + i), 1);
       mbar_init(bar(BAR_ACC_EMPTY + i), kEpiWarps * 2);
@@ -728,6 +706,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
               }
             }
             pending_empty = empty_bar;
+            if (flags & OP_EXTRA_DONE) mma_commit_pair_mc(bar(BAR_EXTRA_EMPTY), 3);   // prologue chunks are dead: next tile's may be written
             if (flags & OP_LAST) {
               mma_commit_pair_mc(bar(BAR_ACC_FULL + acc), 3);  // (the epilogue is waiting for this one: not deferred)
               fill_par ^= 1u << acc;
@@ -752,8 +731,34 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
         }
       }
     }
+  } else if (warp >= kEpiWarps + 2) {
+    // ===================== prologue warps =====================
+    // Encode a tile's inputs into the extra chunks (bf16, swizzled): 128 rows over 64 threads, one whole row at a time.
+    // The first tile is encoded at once; tile i+1 as soon as the issuer's commit on EXTRA_EMPTY reports that the last
+    // MMA of tile i that reads these chunks has completed - while the epilogue warps carry on with the remaining layers.
+    const int t64 = (warp - (kEpiWarps + 2)) * 32 + lane;
+    uint32_t it = 0;
+    for (int unit = group; unit < n_units; unit += n_groups, ++it) {
+      if (it > 0) mbar_wait_sleep(bar(BAR_EXTRA_EMPTY), (it - 1u) & 1u);
+      constexpr int kRows = kTileM / (kPrologueWarps * 32);             // 2 rows per thread
+      float base[kRows][3];
+#pragma unroll
+      for (int j = 0; j < kRows; ++j) {                                 // all position loads in flight first
+        const int64_t pr = (int64_t)(unit * 2 + (int)cta_rank) * kTileM + j * (kPrologueWarps * 32) + t64;
+        load_point(P, pr < P.pts.B ? pr : P.pts.B - 1, base[j]);
+      }
+      for (int j = 0; j < kRows; ++j) {
+        const int row = j * (kPrologueWarps * 32) + t64;
+        const int64_t pr = (int64_t)(unit * 2 + (int)cta_rank) * kTileM + row;
+        const bool ok = pr < P.pts.B;
+        encode_tile_row(P, sA, row, ok ? pr : P.pts.B - 1, ok, base[j]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) arrive_leader(BAR_EXTRA_FULL);
+    }
   } else {
-    // ===================== prologue + epilogue warps =====================
+    // ===================== epilogue warps =====================
     const int q = warp & 3, part = warp >> 2;      // TMEM lane quadrant, 16-column part of every 64-column slice
     const int row = q * 32 + lane;
     const uint32_t lane_field = (uint32_t)(q * 32) << 16;
@@ -767,18 +772,6 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
     int tl_n = 0;
     const bool tl_on = P.dbg && blockIdx.x == 0 && warp == 0;
 #endif
-    // Prologue: encode a tile's inputs into the extra chunks.  Only the first tile pays for it up front; for every
-    // later tile it is run during the previous tile, right after the last sub-step that reads those chunks
-    // (P.last_extra_sub), i.e. hidden behind the remaining layers instead of idling the tensor pipe.
-    auto prologue = [&](int unit_) {
-      const int64_t pr = (int64_t)(unit_ * 2 + (int)cta_rank) * kTileM + row;
-      const bool ok = pr < P.pts.B;
-      encode_tile_row(P, sA, row, part, ok ? pr : P.pts.B - 1, ok);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) arrive_leader(BAR_EXTRA_FULL);
-    };
-    if (group < n_units) prologue(group);
     for (int unit = group; unit < n_units; unit += n_groups) {
       NSFF_TL((gsub << 8) | 13);                             // epi: tile start
       const int tile = unit * 2 + (int)cta_rank;
@@ -904,8 +897,6 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
             }
           }
         }
-        // this sub-step's accumulator was complete => every MMA up to and including it has finished reading smem
-        if (s == P.last_extra_sub && unit + n_groups < n_units) prologue(unit + n_groups);
       }
     }
     NSFF_TL_DUMP();
@@ -1288,6 +1279,13 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
     uint32_t waited_accs = 0;
     for (int i = 0; i < n_ops; ++i) waited_accs |= P.ops[i].wait_empty;
     for (int i = 0; i < n_subs; ++i) P.subs[i].arrive_empty = (waited_accs >> P.subs[i].acc_id) & 1u;
+  }
+  {
+    int last_extra_op = -1;
+    for (int i = 0; i < n_ops; ++i)
+      if (!(P.ops[i].flags & OP_TS)) last_extra_op = i;
+    if (last_extra_op < 0) return NSFF_EUNSUPPORTED;     // every program starts from the encoded inputs
+    P.ops[last_extra_op].flags |= OP_EXTRA_DONE;
   }
   P.n_subs = n_subs;
   P.n_ops = n_ops;
