@@ -230,7 +230,9 @@ def train_record(args, rank, local_rank, world, steps, warmup, loss_impl="fused"
         m.recompute_in_backward = args.bwd_recompute
     emb["t"].weight.requires_grad_(True)
     params = [p for m in models.values() for p in m.parameters()] + [emb["t"].weight]
-    opt = torch.optim.Adam(params, lr=5e-4)
+    # the torch.optim.Adam the reference builds (utils/__init__.py), fused CUDA implementation; capturable: the step may be
+    # replayed from a CUDA graph
+    opt = torch.optim.Adam(params, lr=5e-4, fused=True, capturable=True)
     phase = {}
     rays, ts = synthetic_rays(R, n_frames=N_FRAMES, seed=100 + rank)
     rays, ts = rays.to(dev), ts.to(dev)
@@ -296,25 +298,65 @@ def train_record(args, rank, local_rank, world, steps, warmup, loss_impl="fused"
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    n0 = _cabi.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-    e0.record()
-    for i in range(steps):
-        loss = step()
-        marks[i].record()
-    e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ms = _max_over_ranks(e0.elapsed_time(e1), dev, world)
-    per_step = sorted(([e0] + marks)[i].elapsed_time(marks[i]) for i in range(steps))
-    launches = int(_cabi.launch_count() - n0)
+
+    def timed(run):
+        n0 = _cabi.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        e0.record()
+        for i in range(steps):
+            run()
+            marks[i].record()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = _max_over_ranks(e0.elapsed_time(e1), dev, world)
+        per = sorted(([e0] + marks)[i].elapsed_time(marks[i]) for i in range(steps))
+        return ms, per, int(_cabi.launch_count() - n0)
+
+    box = {}
+
+    def eager():
+        box["loss"] = step()
+
+    ms, per_step, launches = timed(eager)
+    loss = box["loss"]
     phase["on"] = True                       # one more instrumented step for the phase split (outside the timed region)
     step()
     torch.cuda.synchronize()
-    evs = phase["ev"]
+    evs = phase.pop("ev")
+    phase.pop("on")
     split = {evs[i][0]: round(evs[i - 1][1].elapsed_time(evs[i][1]), 3) for i in range(1, len(evs))}
+    # The same step replayed from a CUDA graph (one rank only; the ~220 launches of a 4 ms step leave the GPU waiting for
+    # the host otherwise).  Everything inside is stream-ordered device work: the forward, the loss, the hand-written
+    # backward, the re-pack of the bf16 weight images and the (capturable) Adam update.  New rays would be copied into
+    # the static `rays` / `ts` tensors between replays.
+    graph_info = {"used": False}
+    if world == 1 and not getattr(args, "no_train_graph", False):
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            opt.zero_grad(set_to_none=True)
+            n_before = _cabi.launch_count()
+            with torch.cuda.graph(g):
+                static_loss = step()
+            per_graph = int(_cabi.launch_count() - n_before)
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize()
+            ms_g, per_g, _ = timed(g.replay)
+            graph_info = {"used": True, "ms_per_step_eager": ms / steps, "launches_per_replay": per_graph}
+            ms, per_step, launches, loss = ms_g, per_g, per_graph * steps, static_loss
+        except Exception as e:  # capture is an optimisation of the caller loop: report and keep the eager number
+            graph_info = {"used": False, "error": f"{type(e).__name__}: {str(e)[:200]}"}
+            torch.cuda.synchronize()
     tc = args.grad_precision == "bf16"
     return {"metric": "ray-samples/sec (training step fwd+bwd+Adam)", "value": R * S * world * steps / (ms * 1e-3),
             "unit": "ray-samples/s", "n_gpus": world, "steps": steps, "warmup": max(3, warmup), "ms_per_step": ms / steps,
@@ -325,7 +367,7 @@ def train_record(args, rank, local_rank, world, steps, warmup, loss_impl="fused"
                        "backward": (("bf16 tcgen05 GEMMs over tile images (dgrad + wgrad per layer; activations "
                                      + ("recomputed" if args.bwd_recompute else "saved by the forward kernel") + ")")
                                     if tc else "fp32 CUDA-core kernels (verification path)")},
-            "phase_ms": split,
+            "phase_ms": split, "cuda_graph": graph_info,
             "step_ms": {"min": round(per_step[0], 3), "median": round(per_step[len(per_step) // 2], 3),
                         "max": round(per_step[-1], 3)},
             "algorithmic_tflop_per_step": round(R * S * 14.28e6 / 1e12, 3),
@@ -534,6 +576,7 @@ def main():
                     help="render workload: skip the train / sequence / strong sub-records of the JSON line")
     ap.add_argument("--grad-precision", default="bf16", choices=["bf16", "fp32"],
                     help="train workload: tensor-core backward (default) or the fp32 verification backward")
+    ap.add_argument("--no-train-graph", action="store_true", help="time the training step eagerly only (no CUDA graph replay)")
     ap.add_argument("--loss", default="fused", choices=["fused", "reference"],
                     help="train workload: nsff_pl_b200.losses.NeRFWLoss (default) or the unmodified reference class")
     ap.add_argument("--bwd-recompute", action="store_true",

@@ -555,6 +555,8 @@ struct WgradParams {
   uint32_t b_stride[4];
   int32_t nb, n_tiles, l2_hint;
   float* acc_t;                   // [(64*nb) x 256]
+  float* colsum;                  // optional: colsum[m] += sum over the points of A[:, m] (bias gradient of the layer whose
+                                  // dZ image is A), computed by the otherwise idle epilogue warps from the staged tiles
 };
 constexpr int kWgEpiWarps = 8;
 constexpr int kWgThreads = (kWgEpiWarps + 2) * 32;
@@ -589,10 +591,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) img_wgrad_kernel(const __grid_c
   const int t1 = (int)((int64_t)P.n_tiles * (blockIdx.x + 1) / gridDim.x);
   const int n_half = (t1 - t0) * 2;
 
+#ifdef NSFF_WATCHDOG
+  if (threadIdx.x == 0 && blockIdx.x == 0) printf("NSFF_WATCHDOG wgrad: barriers @%u (FULL[3] EMPTY[3] ACC), colsum %d\n", sBar, P.colsum != nullptr);
+#endif
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWgStages; ++i) {
       mbar_init(bar(WB_FULL + i), 1);
-      mbar_init(bar(WB_EMPTY + i), 1);
+      mbar_init(bar(WB_EMPTY + i), P.colsum ? 1 + kWgEpiWarps : 1);    // MMA commit (+ the column-sum warps)
     }
     mbar_init(bar(WB_ACC), 1);
     fence_mbar_init();
@@ -654,6 +659,27 @@ __global__ void __launch_bounds__(kWgThreads, 1) img_wgrad_kernel(const __grid_c
       }
     } else {
       const int q = warp & 3, mh = warp >> 2;
+      if (P.colsum) {
+        // column sums of the A image (256 channels, one per thread) from the staged half tiles: 64 points x 2 bytes per
+        // thread and stage; the 32 lanes of a warp read 64 contiguous (swizzled) bytes of each row
+        const int ch = threadIdx.x, c = ch >> 6, col = ch & 63;
+        float sum = 0.f;
+        uint32_t stage = 0, par = 0;
+        for (int h = 0; h < n_half; ++h) {
+          mbar_wait(bar(WB_FULL + stage), par);
+          const uint32_t a0 = base + stage * kWgStageBytes + (uint32_t)c * kHalfChunk + (uint32_t)(col & 7) * 2u;
+#pragma unroll 8
+          for (int r = 0; r < 64; ++r) {
+            uint16_t v;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a0 + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((col >> 3) ^ r) & 7) << 4))));
+            sum += __uint_as_float((uint32_t)v << 16);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(WB_EMPTY + stage));
+          if (++stage == kWgStages) stage = 0, par ^= 1u;
+        }
+        atomicAdd(P.colsum + ch, sum);
+      }
       mbar_wait(bar(WB_ACC), 0);
       tc_fence_after_sync();
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)mh * 256u;
@@ -774,6 +800,7 @@ static int launch_wgrad(WgradParams& P, cudaStream_t st) {
 }
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+constexpr int kTinCol0 = 64;     // column of the first time-code gradient in the (B,128) trunk-input gradient rows
 
 // ---- weight pack of the backward ----------------------------------------------------------------------------------
 // All blocks are N x 64 bf16 (N = 256, or 128 for the "trunk input" extras), zero where no weight maps.
@@ -904,9 +931,13 @@ static void build_pack(const nsff_field_desc* d, const nsff_field_params* p, Bwd
     pb.job(L.t_headT, 0, p ? p->trans_bw_w : nullptr, W, true, 0, 0, 256, 3, 7);
     L.t_in1T = pb.alloc(4, 128);
     L.t_in5T = pb.alloc(4, 128);
+    // rows 0..62: PE(xyz) columns, rows 64..111: time-code columns (kTinCol0) - the two 64-row halves are separate
+    // N = 64 blocks of the backward chain, so a pass that only needs the time-code gradient issues one of them
     for (int j = 0; j < 4; ++j) {
-      pb.job(L.t_in1T, j, p ? p->trans_w[0] : nullptr, nx + nt, true, 0, 64 * j, nx + nt, 64);
-      pb.job(L.t_in5T, j, p ? p->trans_w[sk] : nullptr, nx + nt + W, true, 0, 64 * j, nx + nt, 64);
+      pb.job(L.t_in1T, j, p ? p->trans_w[0] : nullptr, nx + nt, true, 0, 64 * j, nx, 64);
+      pb.job(L.t_in1T, j, p ? p->trans_w[0] : nullptr, nx + nt, true, nx, 64 * j, nt, 64, 0, kTinCol0);
+      pb.job(L.t_in5T, j, p ? p->trans_w[sk] : nullptr, nx + nt + W, true, 0, 64 * j, nx, 64);
+      pb.job(L.t_in5T, j, p ? p->trans_w[sk] : nullptr, nx + nt + W, true, nx, 64 * j, nt, 64, 0, kTinCol0);
     }
   }
   L.bytes = pb.off;
@@ -915,6 +946,8 @@ static void build_pack(const nsff_field_desc* d, const nsff_field_params* p, Bwd
 // ---- scratch --------------------------------------------------------------------------------------------------------
 struct Scratch {
   uint8_t *PE, *T, *DIR, *A, *SH[8], *SFEAT, *SDIRO, *TH[8], *TFEAT, *G0, *G1, *DP;
+  // backward chain: dZ image of every layer (the weight-gradient GEMMs run after the chain), second head-gradient chunk
+  uint8_t *GS[8], *GS_FIN, *GS_DIR, *GT[8], *GT_FIN, *DP2, *base;
   uint32_t *SHB[8], *SDIROB, *THB[8];       // ReLU bit planes of the activations above
   float *DIN, *ACC;
   size_t acc_bytes, total;
@@ -943,6 +976,15 @@ static Scratch carve(const nsff_field_desc* d, int64_t B, uint8_t* base, bool wi
   }
   s.TFEAT = take(t4);
   s.G0 = take(four); s.G1 = take(four); s.DP = take(one);
+  s.base = base;
+  {
+    const size_t c4 = with_acts ? 0 : four, ct4 = d->has_transient ? c4 : 0;     // chain: only with a save buffer
+    for (int i = 0; i < 8; ++i) s.GS[i] = take(c4);
+    s.GS_FIN = take(c4); s.GS_DIR = take(d->use_viewdir ? c4 : 0);
+    for (int i = 0; i < 8; ++i) s.GT[i] = take(ct4);
+    s.GT_FIN = take(ct4);
+    s.DP2 = take(with_acts ? 0 : one);
+  }
   s.DIN = reinterpret_cast<float*>(take((size_t)B * 128 * sizeof(float)));
   s.acc_bytes = kAccSlots * 64 * 256 * sizeof(float);
   s.ACC = reinterpret_cast<float*>(take(s.acc_bytes));
@@ -1022,7 +1064,7 @@ static std::vector<Src> four(const uint8_t* img) {
   return {chunk_of(img, 4, 0), chunk_of(img, 4, 1), chunk_of(img, 4, 2), chunk_of(img, 4, 3)};
 }
 // acc_t rows = channels of the B chunks, columns = the 256 channels of `a_img`
-static int wgrad_img(Ctx& c, const uint8_t* a_img, const std::vector<Src>& b, float** acc_out) {
+static int wgrad_img(Ctx& c, const uint8_t* a_img, const std::vector<Src>& b, float** acc_out, float* colsum = nullptr) {
   const size_t need = b.size() * 64 * 256;
   if (b.empty() || b.size() > 4 || c.acc_used + need > c.acc_cap) return NSFF_EINVAL;
   WgradParams P;
@@ -1031,6 +1073,7 @@ static int wgrad_img(Ctx& c, const uint8_t* a_img, const std::vector<Src>& b, fl
   for (size_t j = 0; j < b.size(); ++j) P.b_base[j] = b[j].p, P.b_stride[j] = b[j].stride;
   P.nb = (int)b.size(); P.n_tiles = c.n_tiles;
   P.acc_t = c.acc + c.acc_used;
+  P.colsum = colsum;
   c.acc_used += need;
   *acc_out = P.acc_t;
   return launch_wgrad(P, c.st);
@@ -1105,7 +1148,7 @@ static int trunk_backward(Ctx& c, const nsff_field_desc* d, const Trunk& t, uint
       TRY(wgrad_img(c, g_cur, t.in, &acc));
       if (t.trans) TRY(finish_cols(c, acc, t.gw[i], in_k, {0, d->in_xyz}, {d->in_xyz, d->in_t}));
       else TRY(finish_cols(c, acc, t.gw[i], in_k, {0}, {d->in_xyz}));
-      if (d_in) TRY(gemm_rows(c, four(g_cur), first ? *in1T : *in5T, d_in, 128, t.n_in, first ? 1 : 0));
+      if (d_in) TRY(gemm_rows(c, four(g_cur), first ? *in1T : *in5T, d_in, 128, kTinCol0 + d->in_t, first ? 1 : 0));
     }
     if (!first) {
       if (!t.gb[i - 1]) return NSFF_EINVAL;
@@ -1117,6 +1160,181 @@ static int trunk_backward(Ctx& c, const nsff_field_desc* d, const Trunk& t, uint
     }
   }
   return NSFF_OK;
+}
+
+// ---- chained backward ------------------------------------------------------------------------------------------------
+// The dgrad GEMMs of all layers as ONE launch of the forward's tile machinery (nsff_field_tc.cu, kBwd): per tile, dZ of a
+// layer stays in tensor memory as the A operand of the next (earlier) layer; the launch writes the dZ image of every
+// layer and the fp32 trunk-input gradient rows.  The weight-gradient GEMMs then run over the saved images - their idle
+// epilogue warps also sum the columns of dZ (bias gradients).  Needs the forward's save buffer; appearance codes use the
+// layer-wise path.
+static int chain_enabled() {
+  const char* e = getenv("NSFF_BWD_CHAIN");
+  return e ? atoi(e) != 0 : 1;
+}
+
+static int backward_chain(Ctx& c, const nsff_field_desc* d, const BwdPack& L, Scratch& s, const SaveLayout& SL,
+                          const uint8_t* saved, const nsff_points* pts, bool want_s, bool want_t, bool want_fw, bool want_bw,
+                          const float* out, const float* d_out, int32_t out_ld, const nsff_field_grads* g, float* d_pos,
+                          float* d_t) {
+  using namespace nsff::tc;
+  const int W = 256;
+  const int64_t B = c.B, R = B / pts->S;
+  cudaStream_t st = c.st;
+  const Src pe = chunk_of(s.PE, 1, 0, 4), tcode = chunk_of(s.T, 1, 0, 3), dirc = chunk_of(s.DIR, 1, 0, 2);
+  const Src dps = chunk_of(s.DP, 1, 0, 1), dpt = chunk_of(s.DP2, 1, 0, 1);
+  auto heads = [&](const HeadSpec& H, uint8_t* img) {
+    const int blocks = c.n_tiles < 4 * sm_count() ? c.n_tiles : 4 * sm_count();
+    heads_dpre_kernel<<<(unsigned)blocks, 128, 0, st>>>(d_out, out, out_ld, H, pts->zs, d->flow_scale, B, img, kChunkBytes,
+                                                        c.n_tiles);
+    return after_launch();
+  };
+  auto off_of = [&](const uint8_t* p) { return (uint64_t)(p - s.base); };
+  std::vector<ChainLayer> chain;
+  auto hidden = [&](const Blk& blk, std::initializer_list<uint8_t> chunks, std::initializer_list<uint8_t> blks, bool mask,
+                    uint64_t bits_off, uint8_t* save) {
+    ChainLayer l;
+    memset(&l, 0, sizeof(l));
+    l.w_off = blk.off; l.block_rows = 256; l.row0 = 0; l.n = 256;
+    l.nchunks = (int)chunks.size();
+    int k = 0;
+    for (uint8_t ch : chunks) l.chunk[k++] = ch;
+    k = 0;
+    for (uint8_t b : blks) l.blk[k++] = b;
+    l.epi = mask ? CHAIN_MASK : CHAIN_LIN;
+    l.bits_off = bits_off;
+    l.save_off = off_of(save);
+    chain.push_back(l);
+  };
+  auto rows = [&](const Blk& blk, int half, int beta) {
+    ChainLayer l;
+    memset(&l, 0, sizeof(l));
+    l.w_off = blk.off; l.block_rows = 128; l.row0 = 64 * half; l.n = 64; l.nchunks = 4;
+    for (int k = 0; k < 4; ++k) l.chunk[k] = (uint8_t)(CC_H3 - k), l.blk[k] = (uint8_t)(3 - k);    // last chunk first (drain proof)
+    l.epi = CHAIN_ROWS;
+    l.save_off = l.bits_off = ~0ull;
+    l.out_col0 = 64 * half;
+    l.beta = beta;
+    chain.push_back(l);
+  };
+  const std::initializer_list<uint8_t> H4 = {CC_H0, CC_H1, CC_H2, CC_H3}, B4 = {0, 1, 2, 3};
+
+  int col = 0;
+  HeadSpec Hs, Ht;
+  float* t_rows[16] = {nullptr};
+  if (want_s) {
+    memset(&Hs, 0, sizeof(Hs));
+    for (int i = 0; i < 16; ++i) Hs.src[i] = -1;
+    for (int i = 0; i < 3; ++i) Hs.src[i] = (int8_t)(col + i), Hs.act[i] = 1, Hs.db[i] = g->static_rgb_b ? g->static_rgb_b + i : nullptr;
+    Hs.src[3] = (int8_t)(col + 3), Hs.act[3] = 0, Hs.db[3] = g->static_sigma_b;
+    TRY(heads(Hs, s.DP));
+    if (!g->static_rgb_w || !g->static_sigma_w || !g->static_final_b || !g->static_final_w) return NSFF_EINVAL;
+    if (d->use_viewdir) {
+      if (!g->static_dir_w || !g->static_dir_b) return NSFF_EINVAL;
+      hidden(L.s_rgbT, {CC_DP_STATIC}, {0}, true, SL.s_dirb, s.GS_DIR);                               // dZ_dir
+      hidden(L.s_dirT, H4, B4, false, ~0ull, s.GS_FIN);                                                // dFEAT
+    } else {
+      hidden(L.s_rgbT, {CC_DP_STATIC}, {0}, false, ~0ull, s.GS_FIN);
+    }
+    hidden(L.s_finT, {CC_DP_STATIC, CC_H0, CC_H1, CC_H2, CC_H3}, {4, 0, 1, 2, 3}, true, SL.s_hb[7], s.GS[7]);   // dZ_8 (+ sigma head)
+    for (int i = 7; i >= 1; --i) hidden(L.s_hidT[i], H4, B4, true, SL.s_hb[i - 1], s.GS[i - 1]);
+    col += 4;
+  }
+  if (want_t) {
+    memset(&Ht, 0, sizeof(Ht));
+    for (int i = 0; i < 16; ++i) Ht.src[i] = -1;
+    for (int i = 0; i < 3; ++i) Ht.src[i] = (int8_t)(col + i), Ht.act[i] = 1, Ht.db[i] = g->trans_rgb_b ? g->trans_rgb_b + i : nullptr;
+    Ht.src[3] = (int8_t)(col + 3), Ht.act[3] = 0, Ht.db[3] = g->trans_sigma_b;
+    if (!g->trans_rgb_w || !g->trans_sigma_w || !g->trans_final_b || !g->trans_final_w) return NSFF_EINVAL;
+    t_rows[0] = g->trans_rgb_w, t_rows[1] = g->trans_rgb_w + W, t_rows[2] = g->trans_rgb_w + 2 * W, t_rows[3] = g->trans_sigma_w;
+    int cc = col + 4;
+    if (want_fw) {
+      if (!g->trans_fw_w) return NSFF_EINVAL;
+      for (int i = 0; i < 3; ++i) {
+        Ht.src[4 + i] = (int8_t)(cc + i), Ht.act[4 + i] = 2, Ht.db[4 + i] = g->trans_fw_b ? g->trans_fw_b + i : nullptr;
+        t_rows[4 + i] = g->trans_fw_w + i * W;
+      }
+      cc += 3;
+    }
+    if (want_bw) {
+      if (!g->trans_bw_w) return NSFF_EINVAL;
+      for (int i = 0; i < 3; ++i) {
+        Ht.src[7 + i] = (int8_t)(cc + i), Ht.act[7 + i] = 2, Ht.db[7 + i] = g->trans_bw_b ? g->trans_bw_b + i : nullptr;
+        t_rows[7 + i] = g->trans_bw_w + i * W;
+      }
+      cc += 3;
+    }
+    TRY(heads(Ht, s.DP2));
+    hidden(L.t_headT, {CC_DP_TRANS}, {0}, false, ~0ull, s.GT_FIN);                                     // dTFEAT
+    hidden(L.t_finT, H4, B4, true, SL.t_hb[7], s.GT[7]);                                               // dZ_8
+    const bool rows_pe = d_pos != nullptr, rows_t = d_t != nullptr && d->in_t > 0;
+    for (int i = 7; i >= 1; --i) {
+      if (i == d->skip) {                          // chain state = dZ of the skip layer: its trunk-input columns
+        if (rows_pe) rows(L.t_in5T, 0, 0);
+        if (rows_t) rows(L.t_in5T, 1, 0);
+      }
+      hidden(L.t_hidT[i], H4, B4, true, SL.t_hb[i - 1], s.GT[i - 1]);
+    }
+    if (rows_pe) rows(L.t_in1T, 0, 1);
+    if (rows_t) rows(L.t_in1T, 1, 1);
+  }
+  TRY(launch_backward_chain(chain.data(), (int)chain.size(), c.pack, want_s ? s.DP : nullptr, want_t ? s.DP2 : nullptr, B,
+                            saved, s.base, s.DIN, 128, st));
+
+  // ---- weight gradients over the saved images (any order) ----
+  float* acc;
+  auto trunk_wgrads = [&](bool trans, uint8_t* const* G, uint8_t* const* H, float* const* gw, float* const* gb) -> int {
+    const int n_in = trans ? d->in_xyz + d->in_t : d->in_xyz;
+    for (int i = 7; i >= 0; --i) {
+      const bool first = i == 0, skip = i == d->skip;
+      const int in_k = first ? n_in : (skip ? n_in + W : W);
+      if (!gw[i] || !gb[i]) return NSFF_EINVAL;
+      if (!first) {
+        TRY(wgrad_img(c, G[i], four(H[i - 1]), &acc, gb[i]));
+        const int h0 = skip ? n_in : 0;
+        TRY(finish_cols(c, acc, gw[i], in_k, {h0, h0 + 64, h0 + 128, h0 + 192}, {64, 64, 64, 64}));
+      }
+      if (first || skip) {
+        if (trans) {
+          TRY(wgrad_img(c, G[i], {pe, tcode}, &acc, first ? gb[i] : nullptr));
+          TRY(finish_cols(c, acc, gw[i], in_k, {0, d->in_xyz}, {d->in_xyz, d->in_t}));
+        } else {
+          TRY(wgrad_img(c, G[i], {pe}, &acc, first ? gb[i] : nullptr));
+          TRY(finish_cols(c, acc, gw[i], in_k, {0}, {d->in_xyz}));
+        }
+      }
+    }
+    return NSFF_OK;
+  };
+  if (want_s) {
+    const uint8_t* rgb_in = d->use_viewdir ? s.SDIRO : s.SFEAT;
+    float* rows1[16] = {g->static_rgb_w, g->static_rgb_w + W, g->static_rgb_w + 2 * W};
+    TRY(wgrad_img(c, rgb_in, {dps}, &acc));
+    TRY(finish_rows(c, acc, rows1));
+    float* rows2[16] = {nullptr, nullptr, nullptr, g->static_sigma_w};
+    TRY(wgrad_img(c, s.SH[7], {dps}, &acc));
+    TRY(finish_rows(c, acc, rows2));
+    if (d->use_viewdir) {
+      const int kd = W + d->in_dir;
+      TRY(wgrad_img(c, s.GS_DIR, four(s.SFEAT), &acc, g->static_dir_b));
+      TRY(finish_cols(c, acc, g->static_dir_w, kd, {0, 64, 128, 192}, {64, 64, 64, 64}));
+      TRY(wgrad_img(c, s.GS_DIR, {dirc}, &acc));
+      TRY(finish_cols(c, acc, g->static_dir_w, kd, {W}, {d->in_dir}));
+    }
+    TRY(wgrad_img(c, s.GS_FIN, four(s.SH[7]), &acc, g->static_final_b));
+    TRY(finish_cols(c, acc, g->static_final_w, W, {0, 64, 128, 192}, {64, 64, 64, 64}));
+    TRY(trunk_wgrads(false, s.GS, s.SH, g->static_w, g->static_b));
+  }
+  if (want_t) {
+    TRY(wgrad_img(c, s.TFEAT, {dpt}, &acc));
+    TRY(finish_rows(c, acc, t_rows));
+    TRY(wgrad_img(c, s.GT_FIN, four(s.TH[7]), &acc, g->trans_final_b));
+    TRY(finish_cols(c, acc, g->trans_final_w, W, {0, 64, 128, 192}, {64, 64, 64, 64}));
+    TRY(trunk_wgrads(true, s.GT, s.TH, g->trans_w, g->trans_b));
+    if (d_t && d->in_t > 0) TRY(launch_ray_reduce(s.DIN, 128, kTinCol0, d->in_t, pts->S, R, d_t, st));
+    if (d_pos) TRY(launch_pe_bwd(s.DIN, 128, pts->xyz, (d->in_xyz - 3) / 6, d_pos, B, st));
+  }
+  return flush_finish(c);
 }
 
 }  // namespace bwd
@@ -1212,6 +1430,9 @@ int nsff_field_backward_tc(const nsff_field_desc* d, const nsff_field_params* p,
     embed_img_kernel<<<(unsigned)cdiv64((int64_t)c.n_tiles * 128 * 4, 128), 128, 0, st>>>(E);
     TRY(after_launch());
   }
+  if (saved && d->in_a == 0 && chain_enabled())
+    return backward_chain(c, d, L, s, save_layout(d, B, out_mask), reinterpret_cast<const uint8_t*>(saved), pts, want_s,
+                          want_t, want_fw, want_bw, out, d_out, out_ld, g, d_pos, d_t);
   const Src pe = chunk_of(s.PE, 1, 0, 4), tc = chunk_of(s.T, 1, 0, 3), dirc = chunk_of(s.DIR, 1, 0, 2),
             ac = chunk_of(s.A, 1, 0, 3), dp = chunk_of(s.DP, 1, 0, 1);
   int col = 0;
@@ -1363,7 +1584,7 @@ int nsff_field_backward_tc(const nsff_field_desc* d, const nsff_field_params* p,
     }
     float* d_in = (d_pos || d_t) ? s.DIN : nullptr;
     TRY(trunk_backward(c, d, t, s.G1, s.G0, &L.t_in1T, &L.t_in5T, d_in));
-    if (d_t && d->in_t > 0) TRY(launch_ray_reduce(d_in, 128, d->in_xyz, d->in_t, pts->S, R, d_t, st));
+    if (d_t && d->in_t > 0) TRY(launch_ray_reduce(d_in, 128, kTinCol0, d->in_t, pts->S, R, d_t, st));
     if (d_pos) TRY(launch_pe_bwd(d_in, 128, pts->xyz, (d->in_xyz - 3) / 6, d_pos, B, st));
   }
   return flush_finish(c);

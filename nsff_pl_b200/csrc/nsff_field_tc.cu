@@ -45,6 +45,7 @@
 #include <initializer_list>
 
 #include "nsff_common.cuh"
+#include "nsff_field_host.cuh"
 #include "nsff_field_save.cuh"
 #include "nsff_sm100.cuh"
 
@@ -63,7 +64,9 @@ enum LayerId {
   // inference-only blocks with the activation-free 256x256 "final" layer folded in (see build_layout)
   L_SDIRM, L_SRGBM, L_THEADM, L_COUNT
 };
-enum Epi : uint8_t { EPI_RELU_HID = 0, EPI_LIN_HID = 1, EPI_HEAD = 2 };
+// EPI_MASK_HID / EPI_ROWS: backward chain (field_forward_kernel<.., kBwd = true>): hidden = dZ of a layer, zeroed where
+// the forward's ReLU was inactive (bit plane written by the saving forward); rows = 64 fp32 columns per point to global
+enum Epi : uint8_t { EPI_RELU_HID = 0, EPI_LIN_HID = 1, EPI_HEAD = 2, EPI_MASK_HID = 3, EPI_ROWS = 4 };
 enum HeadAct : uint8_t { HA_NONE = 0, HA_SIGMOID = 1, HA_FLOW = 2 };
 
 constexpr int kMaxChunks = 6;
@@ -72,9 +75,14 @@ struct PackLayer {
   bool present;
   uint32_t w_off;      // byte offset of the first weight block
   uint32_t bias_off;   // float index into the bias table
-  int n;               // 256 or 16
+  int n;               // 256 or 16 (backward chain: 64)
   int nchunks;
   uint8_t chunk[kMaxChunks];
+  // generalisations used by the backward chain (0 = the forward's defaults)
+  uint8_t blk[kMaxChunks];   // block index of K-chunk kc (default: kc)
+  bool blk_explicit;
+  int block_rows;            // rows of one packed block (default: n)
+  int row0;                  // first row of the block this layer uses
 };
 
 struct PackLayout {
@@ -173,8 +181,8 @@ __device__ __forceinline__ uint32_t swz_off(int row, int col /*bf16 column 0..63
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((col >> 3) ^ (row & 7)) & 7) << 4) + (col & 7) * 2);
 }
 
-__global__ void pack_kernel(const PackJobs* __restrict__ jobs_dev, uint8_t* __restrict__ pack, uint32_t bias_base) {
-  const PackJob j = jobs_dev->job[blockIdx.x];
+__global__ void pack_kernel(const __grid_constant__ PackJobs jobs, uint8_t* __restrict__ pack, uint32_t bias_base) {
+  const PackJob& j = jobs.job[blockIdx.x];
   if (j.is_bias) {
     float* b = reinterpret_cast<float*>(pack + bias_base) + j.dst_off;
     for (int i = threadIdx.x; i < j.rows; i += blockDim.x) b[i] = j.src ? j.src[i] : 0.f;
@@ -238,7 +246,7 @@ constexpr uint32_t kSmemBar = 512;
 constexpr int kMaxStages = 18;
 constexpr int kMaxSubs = 44;                         // sub-steps per tile (main pass, split: 19 x 2 + 3 heads = 41)
 constexpr int kMaxOps = 176;                         // ops per tile (main pass, one K-chunk per op: 164 with the appearance chunk)
-constexpr int kAccIds = 5;                           // accumulators with their own full/empty barriers: X.h0 X.h1 Y.h0 Y.h1 head
+constexpr int kAccIds = 6;                           // accumulators with their own full/empty barriers: X.h0 X.h1 Y.h0 Y.h1, narrow 0 / 1
 constexpr int kHeadAcc = 4;
 
 #ifdef NSFF_TIMELINE
@@ -313,6 +321,10 @@ struct FwdParams {
   int32_t n_stages;
   float flow_scale;
   uint8_t* save_base;       // training mode (kSave kernels): activation save buffer, see nsff_field_save.cuh
+  // backward chain (kBwd kernels): head pre-activation gradients as bf16 chunk images ([tile][128 rows x 128 B], columns
+  // 0..15 used) for the static / transient branch, and the base of the forward's save buffer (ReLU bit planes)
+  const uint8_t* dp_img[2];
+  const uint8_t* mask_base;
   unsigned long long* dbg;  // NSFF_TIMELINE builds only: (tag, clock64) event log of CTA 0
   SubStep subs[kMaxSubs];
   ChunkOp ops[kMaxOps];
@@ -530,13 +542,30 @@ __device__ __forceinline__ void bias_act_pack(const uint32_t (&v)[16], const flo
   }
 }
 
+// backward chain: 16 accumulator columns of one row -> bf16 pairs, zeroed where the forward's ReLU bit is clear
+// (bit pair b1 b0 -> x = (b1 b0) * 0x4080 puts b0 into the sign bit of byte 0 and b1 into the sign bit of byte 1; prmt
+// with sign replication expands them to 0x0000FFFF / 0xFFFF0000 halves: 4 integer instructions per bf16 pair)
+__device__ __forceinline__ void mask_pack(const uint32_t (&v)[16], uint32_t bits, uint32_t (&w)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t p = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+    uint32_t y, m;
+    asm("bfe.u32 %0, %1, %2, 2;" : "=r"(y) : "r"(bits), "r"(2 * i));
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m) : "r"(y * 0x4080u), "r"(0u), "r"(0x9988u));
+    w[i] = p & m;
+  }
+}
+
 // tanh through one exp: |error| ~ 1e-7 (tanhf's branchy multi-range code costs ~3x the instructions)
 __device__ __forceinline__ float tanh_f(float x) {
   const float e = __expf(-2.f * fabsf(x));
   return copysignf(__fdividef(1.f - e, 1.f + e), x);
 }
 
-template <bool kAppear, bool kSave>
+// kBwd: the same machinery runs the BACKWARD chain of a tile (build_chain_program): the "hidden activation" kept in
+// tensor memory is dZ of the current layer, the streamed blocks are W^T, the prologue warps copy the head gradients
+// instead of encoding inputs, and the epilogue masks with the forward's ReLU bits instead of adding a bias.
+template <bool kAppear, bool kSave, bool kBwd = false>
 __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid_constant__ FwdParams P) {
   using C = Cfg<kAppear>;
   extern __shared__ uint8_t smem_raw[];
@@ -565,6 +594,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
   const int n_stages = P.n_stages;
   const uint32_t stage_bytes = P.stage_bytes;
 
+#ifdef NSFF_WATCHDOG
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    printf("NSFF_WATCHDOG field kernel (bwd %d): barriers @%u (8 B each: W_FULL[%d] W_EMPTY[%d] HID[2] XF XE ACC_FULL[%d] ACC_EMPTY[%d]), %d subs %d ops\n",
+           (int)kBwd, sBar, kMaxStages, kMaxStages, kAccIds, kAccIds, P.n_subs, P.n_ops);
+#endif
   if (threadIdx.x == 0) {
     for (int i = 0; i < n_stages; ++i) {
       // leader: own pieces (producer arrive + tx) AND the partner's relay arrive complete a stage
@@ -587,8 +621,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
     for (uint32_t o = threadIdx.x * 16u; o < C::kSmemA; o += kEpiWarps * 32u * 16u)
       asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sA + o), "r"(0u) : "memory");
     // the module's bias table stays in shared memory for the whole kernel (no per-layer copies, no barriers)
-    for (int i = threadIdx.x; i < P.n_bias; i += kEpiWarps * 32)
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(sBias + 4u * (uint32_t)i), "f"(__ldg(P.bias + i)) : "memory");
+    if constexpr (!kBwd)
+      for (int i = threadIdx.x; i < P.n_bias; i += kEpiWarps * 32)
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sBias + 4u * (uint32_t)i), "f"(__ldg(P.bias + i)) : "memory");
   }
   tc_fence_before_sync();
   cluster_sync_all();              // also: the peer's barriers are initialised before any remote arrive
@@ -740,18 +775,43 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
     uint32_t it = 0;
     for (int unit = group; unit < n_units; unit += n_groups, ++it) {
       if (it > 0) mbar_wait_sleep(bar(BAR_EXTRA_EMPTY), (it - 1u) & 1u);
-      constexpr int kRows = kTileM / (kPrologueWarps * 32);             // 2 rows per thread
-      float base[kRows][3];
+      if constexpr (kBwd) {
+        // head gradients of this tile: K-step 0 (two 16-byte units per row) of the static / transient chunk images;
+        // the other units of the chunks stay zero (zero-filled above, never written)
+        const int tile = unit * 2 + (int)cta_rank;
+        if (tile < P.n_tiles) {
 #pragma unroll
-      for (int j = 0; j < kRows; ++j) {                                 // all position loads in flight first
-        const int64_t pr = (int64_t)(unit * 2 + (int)cta_rank) * kTileM + j * (kPrologueWarps * 32) + t64;
-        load_point(P, pr < P.pts.B ? pr : P.pts.B - 1, base[j]);
-      }
-      for (int j = 0; j < kRows; ++j) {
-        const int row = j * (kPrologueWarps * 32) + t64;
-        const int64_t pr = (int64_t)(unit * 2 + (int)cta_rank) * kTileM + row;
-        const bool ok = pr < P.pts.B;
-        encode_tile_row(P, sA, row, ok ? pr : P.pts.B - 1, ok, base[j]);
+          for (int b = 0; b < 2; ++b) {
+            if (!P.dp_img[b]) continue;
+            const uint8_t* src = P.dp_img[b] + (size_t)tile * kChunkBytes;
+            uint4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int idx = j * 64 + t64, row = idx >> 1, u = idx & 1;
+              v[j] = __ldg(reinterpret_cast<const uint4*>(src + (row >> 3) * 1024 + (row & 7) * 128 + (((u ^ row) & 7) << 4)));
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int idx = j * 64 + t64, row = idx >> 1, u = idx & 1;
+              st_shared_v4(sA + (uint32_t)b * kChunkBytes + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (((u ^ row) & 7) << 4)),
+                           v[j].x, v[j].y, v[j].z, v[j].w);
+            }
+          }
+        }
+      } else {
+        constexpr int kRows = kTileM / (kPrologueWarps * 32);             // 2 rows per thread
+        float base[kRows][3];
+#pragma unroll
+        for (int j = 0; j < kRows; ++j) {                                 // all position loads in flight first
+          const int64_t pr = (int64_t)(unit * 2 + (int)cta_rank) * kTileM + j * (kPrologueWarps * 32) + t64;
+          load_point(P, pr < P.pts.B ? pr : P.pts.B - 1, base[j]);
+        }
+        for (int j = 0; j < kRows; ++j) {
+          const int row = j * (kPrologueWarps * 32) + t64;
+          const int64_t pr = (int64_t)(unit * 2 + (int)cta_rank) * kTileM + row;
+          const bool ok = pr < P.pts.B;
+          encode_tile_row(P, sA, row, ok ? pr : P.pts.B - 1, ok, base[j]);
+        }
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -794,13 +854,23 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
         const uint32_t t_acc = tmem_base + lane_field + d_col;
         const uint32_t acc_full = bar(BAR_ACC_FULL + acc), acc_par = (drain_par >> acc) & 1u;
         drain_par ^= 1u << acc;
-        if (epi != EPI_HEAD) {
+        if (epi != EPI_HEAD && epi != EPI_ROWS) {
           // One N = 128 half of a 256-wide layer: two 64-column slices; this warp owns 16 columns of each.
           const bool relu = epi == EPI_RELU_HID;
           // bias of the first slice is fetched before the accumulator is awaited: it is off the critical path
           float4 b[4];
+          uint32_t mb0 = 0xFFFFu, mb1 = 0xFFFFu;               // kBwd: ReLU bits of this warp's 16 columns of either slice
+          if constexpr (kBwd) {
+            if (epi == EPI_MASK_HID && tile < P.n_tiles) {
+              const uint8_t* bp = P.mask_base + ss.bits_off + (size_t)tile * kSaveBitsPerTile + (size_t)row * 4 + (part & 1) * 2;
+              const size_t w0i = (size_t)(2 * (2 * half) + (part >> 1)) * 512;      // word plane of chunk 2*half (128 rows x 4 B)
+              mb0 = __ldg(reinterpret_cast<const uint16_t*>(bp + w0i));
+              mb1 = __ldg(reinterpret_cast<const uint16_t*>(bp + w0i + 1024));      // chunk 2*half + 1: two word planes on
+            }
+          } else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) lds_v4(s_bias + (uint32_t)((part * 16 + i * 4) * 4), b[i]);
+            for (int i = 0; i < 4; ++i) lds_v4(s_bias + (uint32_t)((part * 16 + i * 4) * 4), b[i]);
+          }
           NSFF_TL((gsub << 8) | 5);                            // epi: waiting for the accumulator
           mbar_wait(acc_full, acc_par);
           NSFF_TL((gsub << 8) | 6);                            // epi: accumulator complete
@@ -818,12 +888,17 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
           }
           uint32_t w0[8], w1[8];
           float4 b1[4];                                        // bias of the second slice: in flight during the first
+          if constexpr (kBwd) {
+            mask_pack(v0, mb0, w0);
+          } else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) lds_v4(s_bias + (uint32_t)((64 + part * 16 + i * 4) * 4), b1[i]);
-          bias_act_pack(v0, b, relu, w0);
+            for (int i = 0; i < 4; ++i) lds_v4(s_bias + (uint32_t)((64 + part * 16 + i * 4) * 4), b1[i]);
+            bias_act_pack(v0, b, relu, w0);
+          }
           // K-step `part` of hidden chunk slice0: 16 bf16 = 8 columns, in place (columns this warp has drained)
           tmem_st8(t_acc + (uint32_t)(part * 16), w0[0], w0[1], w0[2], w0[3], w0[4], w0[5], w0[6], w0[7]);
-          bias_act_pack(v1, b1, relu, w1);
+          if constexpr (kBwd) mask_pack(v1, mb1, w1);
+          else bias_act_pack(v1, b1, relu, w1);
           tmem_st8(t_acc + (uint32_t)(8 + part * 16), w1[0], w1[1], w1[2], w1[3], w1[4], w1[5], w1[6], w1[7]);
           // both chunks of this 128-channel half are written: publish it to the MMA issuer
           tmem_st_wait();
@@ -855,6 +930,33 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
                       (uint16_t)pos16;
                 }
               }
+            }
+          }
+        } else if (kBwd && epi == EPI_ROWS) {
+          // 64 fp32 columns per point to global rows (gradient w.r.t. the trunk input columns): 16 columns per warp
+          const uint32_t col0 = hot.y & 0xFFFFu;
+          const bool beta = ss.head_tbl[0] == 1;
+          float* orow = P.out + p * P.out_ld + col0 + part * 16;
+          float4 old[4];
+          if (beta && valid) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) old[i] = *reinterpret_cast<const float4*>(orow + 4 * i);
+          }
+          mbar_wait(acc_full, acc_par);
+          tc_fence_after_sync();
+          uint32_t v[16];
+          tmem_ld16(t_acc + (uint32_t)(part * 16), v);
+          tmem_ld_wait();
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) arrive_leader(BAR_ACC_EMPTY + acc);
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float4 x = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                     __uint_as_float(v[4 * i + 3]));
+              if (beta) x.x += old[i].x, x.y += old[i].y, x.z += old[i].z, x.w += old[i].w;
+              *reinterpret_cast<float4*>(orow + 4 * i) = x;
             }
           }
         } else {
@@ -1055,38 +1157,42 @@ extern "C" int nsff_field_pack(const nsff_field_desc* desc, const nsff_field_par
   merge_linear_kernel<<<dim3(256, nm), 256, 0, st>>>(mj);
   if (int lrc = after_launch()) return lrc;
   NSFF_CUDA_TRY(cudaMemsetAsync(p8, 0, jobs_off, st));   // zero padding rows/cols and unused bias slots
-  NSFF_CUDA_TRY(cudaMemcpyAsync(p8 + jobs_off, &jobs, sizeof(PackJob) * nj, cudaMemcpyHostToDevice, st));
-  // (pageable-source cudaMemcpyAsync returns once `jobs` has been staged, so the host copy may be reused)
-  pack_kernel<<<nj, 256, 0, st>>>(reinterpret_cast<const PackJobs*>(p8 + jobs_off), p8, L.bias_base);
+  // the job table travels as a kernel parameter (no host -> device copy: the whole re-pack can be captured in a CUDA graph)
+  pack_kernel<<<nj, 256, 0, st>>>(jobs, p8, L.bias_base);
   return after_launch();
 }
 
 // Builds the per-tile program: the sub-step table the epilogue warps walk and the flat K-chunk op list the producer
-// and the MMA issuer walk.  `split`: every 256-wide layer becomes two N = 128 sub-steps (see the file header).
-static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_mask, bool split, bool fine, bool fuse,
-                         FwdParams& P,
-                         int* n_out_cols, const SaveLayout* SL) {
-  const bool sigma_only = out_mask & NSFF_OUT_SIGMA_ONLY;
-  const bool want_s = out_mask & NSFF_OUT_STATIC, want_t = out_mask & NSFF_OUT_TRANSIENT;
-  const bool want_fw = out_mask & NSFF_OUT_FLOW_FW, want_bw = out_mask & NSFF_OUT_FLOW_BW;
-  if (!want_s && !want_t) return NSFF_EINVAL;
-  if (want_t && !d.has_transient) return NSFF_EINVAL;
-  if ((want_fw || want_bw) && (!want_t || !d.has_flow || sigma_only)) return NSFF_EINVAL;
-  int n_subs = 0, n_ops = 0, col = 0;
+// and the MMA issuer walk.  Every 256-wide layer becomes two N = 128 sub-steps (see the file header).  Shared by the
+// forward (build_program) and the backward chain (build_chain_program).
+struct ProgramBuilder {
+  FwdParams& P;
+  const bool split, fine;
+  int n_subs = 0, n_ops = 0;
   int cur = -1;                        // region (0 = X, 1 = Y) that holds the current hidden activation; -1: none yet
   bool overflow = false;
-  P.last_extra_sub = 0;
-  const int half_cols = split ? 128 : 64;            // TMEM columns between the bf16 images of channels 0-127 / 128-255
-  auto a_of = [&](int ch) -> uint16_t {              // A-operand address of K-step 0 of chunk `ch`
-    if (ch < CH_PE) return (uint16_t)(cur * 256 + (ch >> 1) * half_cols + (ch & 1) * 8);     // TMEM column
-    return (uint16_t)((ch - CH_PE) * (int)(kChunkBytes >> 4));                                 // smem, 16-byte units
-  };
-  // host-only bookkeeping for the drain analysis below
+  // Has any op waited for "half h of the current hidden layer published"?  Every publish must be waited for by the
+  // issuer before the NEXT publish of the same barrier can complete, or a later parity wait would be satisfied by the
+  // stale phase (the issuer may only ever be one phase behind).  The forward reads every hidden layer; in the backward
+  // chain dZ of a branch's first layer has no reader, so the layer after it (extras only) takes the waits.
+  bool hid_read[2] = {true, true};
+  // host-only bookkeeping for the drain analysis in finish()
   struct OpMeta { int acc; bool first, head; int waits_half; bool needs_hi; };
   OpMeta meta[kMaxOps];
-  auto push = [&](int lid, uint8_t epi) -> SubStep* {
-    const PackLayer& pl = L.layer[lid];
-    const bool head = epi == EPI_HEAD;
+
+  ProgramBuilder(FwdParams& p, bool split_, bool fine_) : P(p), split(split_), fine(fine_) { P.last_extra_sub = 0; }
+
+  uint16_t a_of(int ch) const {                      // A-operand address of K-step 0 of chunk `ch`
+    const int half_cols = split ? 128 : 64;          // TMEM columns between the bf16 images of channels 0-127 / 128-255
+    if (ch < CH_PE) return (uint16_t)(cur * 256 + (ch >> 1) * half_cols + (ch & 1) * 8);     // TMEM column
+    return (uint16_t)((ch - CH_PE) * (int)(kChunkBytes >> 4));                                 // smem, 16-byte units
+  }
+
+  // `narrow`: an N <= 64 block (head, fp32 rows) whose accumulator lives in the free upper columns of the region that
+  // holds its input - slot 0: above the bf16 image of channels 0-127 (accumulator id kHeadAcc), slot 1: above the image
+  // of channels 128-255 (id kHeadAcc + 1)
+  SubStep* push(const PackLayer& pl, uint8_t epi, uint64_t save_off = kNoSave, uint64_t bits_off = kNoSave, int slot = 0) {
+    const bool head = epi == EPI_HEAD || epi == EPI_ROWS;
     const int parts = (!head && split) ? 2 : 1;
     const int region = head ? cur : (cur < 0 ? 0 : 1 - cur);
     if (head && cur < 0) { overflow = true; return nullptr; }
@@ -1104,9 +1210,9 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
       s.n = (uint16_t)n;
       s.epi = epi;
       if (head) {
-        // free columns of the region that holds the input: above the in-place bf16 image of channels 0-127
-        s.d_col = (uint16_t)(region * 256 + (split ? 64 : 128));
-        s.acc_id = kHeadAcc;
+        // free columns of the region that holds the input: above the in-place bf16 image of channels 0-127 / 128-255
+        s.d_col = (uint16_t)(region * 256 + (split ? 64 : 128) + (slot ? 128 : 0));
+        s.acc_id = (uint8_t)(kHeadAcc + (slot ? 1 : 0));
         s.slice0 = 0;
       } else {
         s.d_col = (uint16_t)(region * 256 + h * 128);
@@ -1115,15 +1221,10 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
       }
       memset(s.head_tbl, 0xFF, sizeof(s.head_tbl));
       memset(s.pad, 0, sizeof(s.pad));
-      s.save_off = s.bits_off = kNoSave;
-      if (SL) {
-        if (lid >= L_S1 && lid <= L_S8) s.save_off = SL->s_h[lid - L_S1], s.bits_off = SL->s_hb[lid - L_S1];
-        else if (lid == L_SFIN) s.save_off = SL->s_feat;
-        else if (lid == L_SDIR) s.save_off = SL->s_dir, s.bits_off = SL->s_dirb;
-        else if (lid >= L_T1 && lid <= L_T8) s.save_off = SL->t_h[lid - L_T1], s.bits_off = SL->t_hb[lid - L_T1];
-        else if (lid == L_TFIN) s.save_off = SL->t_feat;
-      }
-      const uint32_t block_bytes = (uint32_t)pl.n * 128u;                // whole N x 64 block of one K-chunk
+      s.save_off = save_off;
+      s.bits_off = bits_off;
+      const int block_rows = pl.block_rows ? pl.block_rows : pl.n;
+      const uint32_t block_bytes = (uint32_t)block_rows * 128u;          // whole packed block of one K-chunk
       const uint32_t piece = (uint32_t)n * 128u / 2u;                    // this CTA's N/2 rows of it
       int k = 0;
       for (int kc = 0; kc < pl.nchunks; ++k) {
@@ -1136,18 +1237,22 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
         // two consecutive K-chunks of the same kind share an op: (H0,H1) (H2,H3) / (H3,H2) (H1,H0) / (PE,T) / (DIR,A)
         const bool two = !(fine && !head) && kc + 1 < pl.nchunks && ((pl.chunk[kc + 1] < CH_PE) == hidden) &&
                          (hidden ? (pl.chunk[kc + 1] >> 1) == (ch >> 1) : pl.chunk[kc + 1] == ch + 1);
+        auto src_of = [&](int c) {
+          const uint32_t b = pl.blk_explicit ? pl.blk[c] : (uint32_t)c;
+          return pl.w_off + b * block_bytes + (uint32_t)(pl.row0 + h * n) * 128u;
+        };
         o.idesc = make_idesc_bf16(2 * kTileM, (uint32_t)n);
         o.a = a_of(ch);
         o.d_col = s.d_col;
         o.acc_id = s.acc_id;
         o.bytes = piece;
-        o.w_src0 = pl.w_off + (uint32_t)kc * block_bytes + (uint32_t)h * (uint32_t)n * 128u;
+        o.w_src0 = src_of(kc);
         o.flags = hidden ? OP_TS : 0;
         if (two) {
           o.flags |= OP_TWO;
           o.a2 = a_of(pl.chunk[kc + 1]);
           o.b2 = (uint16_t)(piece >> 4);
-          o.w_src1 = o.w_src0 + block_bytes;
+          o.w_src1 = src_of(kc + 1);
         }
         m.acc = s.acc_id, m.first = kc == 0, m.head = head, m.waits_half = -1;
         m.needs_hi = hidden && (ch >> 1) == 1;
@@ -1163,6 +1268,17 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
       }
       n_half = k;
     }
+    if (!head && parts == 2 && cur >= 0) {
+      for (int h = 0; h < 2; ++h)
+        if (!hid_read[h] && !seen_half[h]) {
+          // nobody read half h of the previous hidden layer: this layer's half-h ops wait for its publish all the same
+          half_ops[h][0].wait_hid = (uint8_t)(1 + h);
+          half_meta[h][0].waits_half = h;
+          seen_half[h] = true;
+        }
+    }
+    for (int h = 0; h < 2; ++h)
+      if (seen_half[h]) hid_read[h] = true;
     // Issue order inside a layer.  The ops that read channels 0-127 of the previous layer run before anything needs
     // channels 128-255, which the epilogue of the previous layer's second half is still producing; and half 0 of THIS
     // layer finishes while three ops of half 1 are still to come, so that its epilogue (whose result the next layer's
@@ -1193,8 +1309,95 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
     if (overflow) return nullptr;
     if (!head) P.ops[n_ops - 1].flags |= OP_ADV_HID;
     n_subs += parts;
-    if (!head) cur = region;
+    if (!head) cur = region, hid_read[0] = hid_read[1] = false;
     return first;
+  }
+
+  int finish() {
+    if (overflow) return NSFF_EUNSUPPORTED;
+    // the last hidden layer of the tile, if nobody read it: the first layer of the NEXT tile waits for its publish
+    // (first tile: parity of a fresh barrier, passes at once)
+    for (int h = 0; h < 2; ++h)
+      if (!hid_read[h]) {
+        int at = -1;
+        for (int i = 0; i < n_ops && at < 0; ++i)
+          if (meta[i].first && !meta[i].head && (meta[i].acc & 1) == h) at = i;
+        if (at < 0 || P.ops[at].wait_hid != 0) return NSFF_EUNSUPPORTED;
+        P.ops[at].wait_hid = (uint8_t)(1 + h);
+        meta[at].waits_half = h;
+      }
+    // Which accumulators must the issuer explicitly wait to be drained before overwriting them?  The drain of a hidden
+    // accumulator (region r, half h) is implied once any op has waited for "hidden half h of the layer stored there
+    // published" (the epilogue reads the accumulator before it publishes), which the next layer always does; what is
+    // left are the narrow accumulators (inside a half of a region) and whatever the walk below finds uncovered.
+    // The table is the same for every tile, so the walk covers two consecutive tiles and keeps the union.
+    {
+      int stored[kAccIds], waited[2] = {-1, -1}, layer = 0, cur_layer = -1;
+      for (int i = 0; i < kAccIds; ++i) stored[i] = -1;
+      bool narrow_pending[2] = {false, false};
+      int narrow_region[2] = {-1, -1};
+      for (int pass = 0; pass < 2; ++pass)
+        for (int i = 0; i < n_ops; ++i) {
+          ChunkOp& o = P.ops[i];
+          const OpMeta& m = meta[i];
+          if (m.waits_half >= 0) waited[m.waits_half] = cur_layer;
+          if (m.first) {
+            uint8_t mask = 0;
+            if (m.head) {
+              const int k = m.acc - kHeadAcc;
+              if (narrow_pending[k]) mask |= 1u << m.acc;            // previous narrow accumulator (same barrier pair)
+              narrow_pending[k] = true;
+              narrow_region[k] = (o.d_col >> 8) & 1;
+            } else {
+              const int h = m.acc & 1, r = m.acc >> 1;
+              if (stored[m.acc] >= 0 && waited[h] < stored[m.acc]) mask |= 1u << m.acc;
+              if (narrow_pending[h] && r == narrow_region[h]) mask |= 1u << (kHeadAcc + h), narrow_pending[h] = false;
+              stored[m.acc] = layer;
+            }
+            o.wait_empty |= mask;
+          }
+          if (o.flags & OP_ADV_HID) cur_layer = layer++;
+        }
+    }
+    {
+      uint32_t waited_accs = 0;
+      for (int i = 0; i < n_ops; ++i) waited_accs |= P.ops[i].wait_empty;
+      for (int i = 0; i < n_subs; ++i) P.subs[i].arrive_empty = (waited_accs >> P.subs[i].acc_id) & 1u;
+    }
+    {
+      int last_extra_op = -1;
+      for (int i = 0; i < n_ops; ++i)
+        if (!(P.ops[i].flags & OP_TS)) last_extra_op = i;
+      if (last_extra_op < 0) return NSFF_EUNSUPPORTED;     // every program starts from chunks the prologue warps write
+      P.ops[last_extra_op].flags |= OP_EXTRA_DONE;
+    }
+    P.n_subs = n_subs;
+    P.n_ops = n_ops;
+    return NSFF_OK;
+  }
+};
+
+static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_mask, bool split, bool fine, bool fuse,
+                         FwdParams& P,
+                         int* n_out_cols, const SaveLayout* SL) {
+  const bool sigma_only = out_mask & NSFF_OUT_SIGMA_ONLY;
+  const bool want_s = out_mask & NSFF_OUT_STATIC, want_t = out_mask & NSFF_OUT_TRANSIENT;
+  const bool want_fw = out_mask & NSFF_OUT_FLOW_FW, want_bw = out_mask & NSFF_OUT_FLOW_BW;
+  if (!want_s && !want_t) return NSFF_EINVAL;
+  if (want_t && !d.has_transient) return NSFF_EINVAL;
+  if ((want_fw || want_bw) && (!want_t || !d.has_flow || sigma_only)) return NSFF_EINVAL;
+  int col = 0;
+  ProgramBuilder pb(P, split, fine);
+  auto push = [&](int lid, uint8_t epi) -> SubStep* {
+    uint64_t save_off = kNoSave, bits_off = kNoSave;
+    if (SL) {
+      if (lid >= L_S1 && lid <= L_S8) save_off = SL->s_h[lid - L_S1], bits_off = SL->s_hb[lid - L_S1];
+      else if (lid == L_SFIN) save_off = SL->s_feat;
+      else if (lid == L_SDIR) save_off = SL->s_dir, bits_off = SL->s_dirb;
+      else if (lid >= L_T1 && lid <= L_T8) save_off = SL->t_h[lid - L_T1], bits_off = SL->t_hb[lid - L_T1];
+      else if (lid == L_TFIN) save_off = SL->t_feat;
+    }
+    return pb.push(L.layer[lid], epi, save_off, bits_off);
   };
   P.need_dir = 0;
   P.need_t = 0;
@@ -1242,55 +1445,8 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
       }
     }
   }
-  if (overflow) return NSFF_EUNSUPPORTED;
-  // Which accumulators must the issuer explicitly wait to be drained before overwriting them?  The drain of a hidden
-  // accumulator (region r, half h) is implied once any op has waited for "hidden half h of the layer stored there
-  // published" (the epilogue reads the accumulator before it publishes), which the next layer always does; what is
-  // left are the head accumulators (inside the first half of a region) and whatever the walk below finds uncovered.
-  // The table is the same for every tile, so the walk covers two consecutive tiles and keeps the union.
-  {
-    int stored[kAccIds], waited[2] = {-1, -1}, layer = 0, cur_layer = -1;
-    for (int i = 0; i < kAccIds; ++i) stored[i] = -1;
-    bool head_pending = false;
-    int head_region = -1;
-    for (int pass = 0; pass < 2; ++pass)
-      for (int i = 0; i < n_ops; ++i) {
-        ChunkOp& o = P.ops[i];
-        const OpMeta& m = meta[i];
-        if (m.waits_half >= 0) waited[m.waits_half] = cur_layer;
-        if (m.first) {
-          uint8_t mask = 0;
-          if (m.head) {
-            if (head_pending) mask |= 1u << kHeadAcc;            // previous head accumulator (same barrier pair)
-            head_pending = true;
-            head_region = (o.d_col >> 8) & 1;
-          } else {
-            const int h = m.acc & 1, r = m.acc >> 1;
-            if (stored[m.acc] >= 0 && waited[h] < stored[m.acc]) mask |= 1u << m.acc;
-            if (head_pending && h == 0 && r == head_region) mask |= 1u << kHeadAcc, head_pending = false;
-            stored[m.acc] = layer;
-          }
-          o.wait_empty |= mask;
-        }
-        if (o.flags & OP_ADV_HID) cur_layer = layer++;
-      }
-  }
-  {
-    uint32_t waited_accs = 0;
-    for (int i = 0; i < n_ops; ++i) waited_accs |= P.ops[i].wait_empty;
-    for (int i = 0; i < n_subs; ++i) P.subs[i].arrive_empty = (waited_accs >> P.subs[i].acc_id) & 1u;
-  }
-  {
-    int last_extra_op = -1;
-    for (int i = 0; i < n_ops; ++i)
-      if (!(P.ops[i].flags & OP_TS)) last_extra_op = i;
-    if (last_extra_op < 0) return NSFF_EUNSUPPORTED;     // every program starts from the encoded inputs
-    P.ops[last_extra_op].flags |= OP_EXTRA_DONE;
-  }
-  P.n_subs = n_subs;
-  P.n_ops = n_ops;
   *n_out_cols = col;
-  return NSFF_OK;
+  return pb.finish();
 }
 
 static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdParams& P, int out_mask, int64_t B,
@@ -1400,6 +1556,90 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
 #endif
   return after_launch();
 }
+
+// ---- backward chain launcher (declared in nsff_field_host.cuh; called by nsff_field_backward_tc) ------------------------
+namespace nsff {
+namespace tc {
+int launch_backward_chain(const ChainLayer* layers, int n_layers, const void* pack, const uint8_t* dp_static,
+                          const uint8_t* dp_trans, int64_t B, const uint8_t* mask, uint8_t* save, float* out_rows,
+                          int32_t out_ld, cudaStream_t st) {
+  if (!layers || n_layers < 1 || !pack || B <= 0 || !save) return NSFF_EINVAL;
+  static thread_local FwdParams P;          // 8 KB: keep it off the stack of the calling thread
+  memset(&P, 0, sizeof(P));
+  ProgramBuilder pb(P, /*split=*/true, /*fine=*/false);
+  for (int i = 0; i < n_layers; ++i) {
+    const ChainLayer& c = layers[i];
+    if (c.nchunks < 1 || c.nchunks > kMaxChunks) return NSFF_EINVAL;
+    PackLayer pl;
+    memset(&pl, 0, sizeof(pl));
+    pl.present = true;
+    pl.w_off = c.w_off;
+    pl.n = c.n;
+    pl.nchunks = c.nchunks;
+    pl.blk_explicit = true;
+    pl.block_rows = c.block_rows;
+    pl.row0 = c.row0;
+    for (int k = 0; k < c.nchunks; ++k) {
+      pl.chunk[k] = c.chunk[k] < 4 ? c.chunk[k] : (uint8_t)(CH_PE + (c.chunk[k] - CC_DP_STATIC));   // DP chunks: extra slots 0 / 1
+      pl.blk[k] = c.blk[k];
+      if (c.chunk[k] == CC_DP_STATIC && !dp_static) return NSFF_EINVAL;
+      if (c.chunk[k] == CC_DP_TRANS && !dp_trans) return NSFF_EINVAL;
+    }
+    if (c.epi == CHAIN_ROWS) {
+      if (c.n != 64 || !out_rows || (out_ld & 3) || ((uintptr_t)out_rows & 15u) || (c.out_col0 & 3)) return NSFF_EINVAL;
+      pl.bias_off = (uint32_t)c.out_col0;            // the sub-step's bias_off field carries the destination column
+      SubStep* s = pb.push(pl, EPI_ROWS, kNoSave, kNoSave, c.out_col0 >= 64 ? 1 : 0);
+      if (s) s->head_tbl[0] = c.beta ? 1 : 0;
+    } else {
+      if (c.n != 256) return NSFF_EINVAL;
+      if (c.epi == CHAIN_MASK && (!mask || c.bits_off == kNoSave)) return NSFF_EINVAL;
+      SubStep* s = pb.push(pl, c.epi == CHAIN_MASK ? EPI_MASK_HID : EPI_LIN_HID, c.save_off, c.bits_off);
+      if (s) s[0].bias_off = s[1].bias_off = 0;
+    }
+  }
+  int rc = pb.finish();
+  if (rc != NSFF_OK) return rc;
+  int dev = 0, major = 0, sms = 0;
+  NSFF_CUDA_TRY(cudaGetDevice(&dev));
+  NSFF_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) return NSFF_EARCH;
+  NSFF_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  P.pack = static_cast<const uint8_t*>(pack);
+  P.pts.B = B;
+  P.pts.S = 1;
+  P.out = out_rows;
+  P.out_ld = out_ld;
+  P.n_tiles = (int)cdiv64(B, kTileM);
+  P.stage_bytes = 16384u;
+  P.n_stages = (int)(Cfg<false>::kSmemB / P.stage_bytes);
+  P.save_base = save;
+  P.mask_base = mask;
+  P.dp_img[0] = dp_static;
+  P.dp_img[1] = dp_trans;
+  auto kern = field_forward_kernel<false, true, true>;
+  const uint32_t smem = Cfg<false>::kSmemTotal;
+  NSFF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int n_pairs = (P.n_tiles + 1) / 2;
+  int clusters = sms / 2;
+  if (clusters < 1) clusters = 1;
+  if (n_pairs < clusters) clusters = n_pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NSFF_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, P));
+  return after_launch();
+}
+}  // namespace tc
+}  // namespace nsff
 
 extern "C" int nsff_field_forward(const nsff_field_desc* desc, const void* pack, const nsff_points* pts,
                                   int out_mask, float* out, int32_t out_ld, void* stream) {

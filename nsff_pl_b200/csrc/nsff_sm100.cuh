@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace nsff {
 namespace sm100 {
@@ -47,9 +48,30 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Debug builds (-DNSFF_WATCHDOG, tools/watchdog.sh): a wait that lasts longer than ~1 s reports who waits for which
+// barrier and traps, so that a protocol error shows up as a launch failure with a message instead of a hung GPU.
+#ifdef NSFF_WATCHDOG
+#define NSFF_WD_DECL const long long wd_t0 = clock64(); bool wd_said = false
+#define NSFF_WD_CHECK(bar, parity)                                                                              \
+  do {                                                                                                          \
+    const long long wd_dt = clock64() - wd_t0;                                                                  \
+    if (wd_dt > 2000000000ll && !wd_said) {                                                                     \
+      wd_said = true;                                                                                           \
+      printf("NSFF_WATCHDOG block %d warp %d lane %d waits for barrier @%u (slot %d) parity %u\n", (int)blockIdx.x, \
+             (int)(threadIdx.x >> 5), (int)(threadIdx.x & 31), (unsigned)(bar), (int)(((bar) & 0xFFFFFFu) >> 3), (unsigned)(parity)); \
+    }                                                                                                           \
+    if (wd_dt > 6000000000ll) __trap();                                                                         \
+  } while (0)
+#else
+#define NSFF_WD_DECL do {} while (0)
+#define NSFF_WD_CHECK(bar, parity) do {} while (0)
+#endif
+
 // Waits until the phase with the given parity has completed (fresh barrier: parity 1 passes at once).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  NSFF_WD_DECL;
   while (!mbar_try_wait(bar, parity)) {
+    NSFF_WD_CHECK(bar, parity);
   }
 }
 
@@ -57,6 +79,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // hint so the warp sleeps in hardware until the phase flips, and backs off between polls instead of spinning.
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+  NSFF_WD_DECL;
   for (;;) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -66,6 +89,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity), "r"(20000u)
         : "memory");
     if (ok) return;
+    NSFF_WD_CHECK(bar, parity);
     __nanosleep(64);
   }
 }
@@ -73,6 +97,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
 // Same, with cluster-scope acquire: for barriers that receive arrives from the partner CTA.
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+  NSFF_WD_DECL;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -81,6 +106,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         : "=r"(ok)
         : "r"(bar), "r"(parity)
         : "memory");
+    NSFF_WD_CHECK(bar, parity);
   } while (!ok);
 }
 

@@ -494,3 +494,34 @@ def test_empty_ray_batch_returns_empty_results_with_the_same_keys():
         for k in one:
             assert none[k].shape == (0,) + tuple(one[k].shape[1:]), k
             assert none[k].dtype == one[k].dtype
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# composite: the staged kernel (bulk copies into per-warp shared-memory stages) and the direct kernel share one
+# per-sample body, so their results must be IDENTICAL bit for bit - on every mode and on ragged chunk counts.
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_samples", [128, 40, 24, 4])
+@pytest.mark.parametrize("mode", ["static", "transient", "flow_test", "warp_train", "warp_noise"])
+def test_staged_composite_is_bit_identical_to_the_direct_kernel(monkeypatch, mode, n_samples):
+    from nsff_pl_b200.models.rendering import render_rays
+    transient = mode != "static"
+    models, emb, _, _ = build_fields(W=256, transient=transient, seed=41, precision="bf16", n_frames=8)
+    rays, ts = synthetic_rays(333, n_frames=8, seed=42)
+    kw = dict(N_samples=n_samples, perturb=0, noise_std=0, test_time=True)
+    if mode == "transient":
+        kw.update(output_transient=True, output_transient_flow=[])
+    elif mode == "flow_test":                      # test_time: flows composited, no warp passes
+        kw.update(output_transient_flow=["fw", "bw"])
+    elif mode == "warp_train":
+        kw.update(output_transient_flow=["fw", "bw", "disocc"], test_time=False)
+    elif mode == "warp_noise":
+        kw.update(output_transient_flow=["fw", "bw", "disocc"], test_time=False, perturb=1.0, noise_std=1.0)
+    outs = []
+    for direct in ("0", "1"):
+        monkeypatch.setenv("NSFF_COMP_DIRECT", direct)
+        torch.manual_seed(7)
+        with torch.no_grad():
+            outs.append(render_rays(models, emb, rays.cuda(), ts.cuda() if transient else None, 7, **kw))
+    assert list(outs[0]) == list(outs[1])
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k

@@ -123,7 +123,8 @@ def test_pack_unpack_pixels_roundtrip():
 
 def test_backward_buffer_sizes_are_host_side_pure_functions():
     """Size queries of the tensor-core backward need no GPU: tile-image bytes, the activation save buffer written by
-    nsff_field_forward_save, the W / W^T block pack and the scratch (smaller when the forward saved the activations)."""
+    nsff_field_forward_save, the W / W^T block pack and the scratch (recompute mode: the activation images; saved mode: the
+    dZ image of every layer, which the chained backward keeps for the weight-gradient GEMMs)."""
     import ctypes as C
     from nsff_pl_b200 import _cabi
     from nsff_pl_b200.models.nerf import NeRF
@@ -143,7 +144,7 @@ def test_backward_buffer_sizes_are_host_side_pure_functions():
     assert pack > 0 and pack % (64 * 128) == 0                 # whole 64-row x 64-column bf16 blocks
     full = L.nsff_field_bwd_tc_scratch_bytes(C.byref(desc), B, 0)
     lean = L.nsff_field_bwd_tc_scratch_bytes(C.byref(desc), B, 1)
-    assert 0 < lean < full and full - lean >= (10 + 9) * img
+    assert full >= (10 + 9) * img and lean >= (10 + 9) * img and abs(full - lean) < 4 * img
     small = NeRF("fine", W=64, encode_transient=True, in_channels_t=48, output_flow=True)
     assert L.nsff_field_bwd_tc_pack_bytes(C.byref(small.field_desc())) == 0      # tcgen05 path: 8 x 256 only
 
