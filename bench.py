@@ -293,6 +293,13 @@ def train_record(args, rank, local_rank, world, steps, warmup, loss_impl="fused"
         mark("allreduce+adam")
         return loss
 
+    # every step - eager or captured - runs on ONE side stream: the parameters' AccumulateGrad nodes then live on the stream the
+    # capture uses (a node left over from a default-stream step would drag the legacy stream into the capture and invalidate it)
+    import contextlib
+    stack = contextlib.ExitStack()
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    stack.enter_context(torch.cuda.stream(side))
     for _ in range(max(3, warmup)):
         step()
     if world > 1:
@@ -318,7 +325,7 @@ def train_record(args, rank, local_rank, world, steps, warmup, loss_impl="fused"
     box = {}
 
     def eager():
-        box["loss"] = step()
+        box["loss"] = step().detach()        # (no reference to the autograd graph outlives the step: see the capture below)
 
     ms, per_step, launches = timed(eager)
     loss = box["loss"]
@@ -335,18 +342,12 @@ def train_record(args, rank, local_rank, world, steps, warmup, loss_impl="fused"
     graph_info = {"used": False}
     if world == 1 and not getattr(args, "no_train_graph", False):
         try:
-            side = torch.cuda.Stream(dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                for _ in range(3):
-                    step()
-            torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             opt.zero_grad(set_to_none=True)
             n_before = _cabi.launch_count()
-            with torch.cuda.graph(g):
-                static_loss = step()
+            with torch.cuda.graph(g, stream=side):
+                static_loss = step().detach()
             per_graph = int(_cabi.launch_count() - n_before)
             for _ in range(3):
                 g.replay()
@@ -357,6 +358,8 @@ def train_record(args, rank, local_rank, world, steps, warmup, loss_impl="fused"
         except Exception as e:  # capture is an optimisation of the caller loop: report and keep the eager number
             graph_info = {"used": False, "error": f"{type(e).__name__}: {str(e)[:200]}"}
             torch.cuda.synchronize()
+    stack.close()
+    torch.cuda.current_stream(dev).wait_stream(side)
     tc = args.grad_precision == "bf16"
     return {"metric": "ray-samples/sec (training step fwd+bwd+Adam)", "value": R * S * world * steps / (ms * 1e-3),
             "unit": "ray-samples/s", "n_gpus": world, "steps": steps, "warmup": max(3, warmup), "ms_per_step": ms / steps,

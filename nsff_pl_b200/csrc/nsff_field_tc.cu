@@ -239,7 +239,9 @@ __global__ void __launch_bounds__(256) merge_linear_kernel(const __grid_constant
 constexpr int kTileM = 128;
 constexpr int kEpiWarps = 16;        // 4 TMEM lane quadrants x 4 column parts
 constexpr int kPrologueWarps = 2;       // dedicated input-encoding warps (18 -> 20 warps: same 96-register allocation granule)
-constexpr int kThreads = (kEpiWarps + 2 + kPrologueWarps) * 32;
+constexpr int kSaverWarp = kEpiWarps + 2 + kPrologueWarps;   // training kernels: issues the bulk stores of the saved images
+constexpr int kThreads = kSaverWarp * 32;               // inference: 20 warps = 5 per scheduler, 96 registers each
+constexpr int kThreadsSave = (kSaverWarp + 1) * 32;     // training kernels: + the saver warp (6 warps on one scheduler: 80 registers)
 constexpr uint32_t kChunkBytes = 128 * 128;          // 128 rows x 64 bf16
 constexpr uint32_t kSmemBias = 21 * 1024;            // the module's whole fp32 bias table (<= 5200 floats), resident
 constexpr uint32_t kSmemBar = 512;
@@ -258,11 +260,17 @@ constexpr uint32_t kSmemDbg = 0;
 // kAppear: one more prologue chunk (the 48-wide NeRF-W appearance code feeding the dir layer), paid for with ring space.
 // The ring is cut into stages of TWO weight pieces (the two K-chunks of one op): 2 x 16 KB per CTA for N = 256 ops
 // 2 x 8 KB per CTA for the N = 128 sub-steps (9 stages; 8 with the appearance chunk).
-template <bool kAppear>
+// kSave (training forward, backward chain): every hidden sub-step also leaves the SM as a 2 x 16 KB tile image.  The
+// epilogue warps write their rows into one of two shared-memory staging buffers and a dedicated warp ships each buffer
+// with two cp.async.bulk stores (whole 128-byte lines, no LSU work); per-lane 32-byte global stores cost the epilogue
+// warps 1600-2100 cycles per sub-step (in-kernel timeline) - more than the drain itself.  The buffers are paid for with
+// four ring stages.
+template <bool kAppear, bool kSave = false>
 struct Cfg {
   static constexpr uint32_t kSmemA = (kAppear ? 4 : 3) * kChunkBytes;   // PE + T + DIR (+ A)
-  static constexpr uint32_t kSmemB = (kAppear ? 8 : 9) * 16384;
-  static constexpr uint32_t kSmemTotal = kSmemA + kSmemB + kSmemBias + kSmemBar + kSmemDbg + 1024;   // + alignment slack
+  static constexpr uint32_t kSmemB = ((kAppear ? 8 : 9) - (kSave ? 4 : 0)) * 16384;
+  static constexpr uint32_t kSmemSave = kSave ? 2 * 2 * kChunkBytes : 0;
+  static constexpr uint32_t kSmemTotal = kSmemA + kSmemB + kSmemSave + kSmemBias + kSmemBar + kSmemDbg + 1024;   // + alignment slack
 };
 
 enum : uint8_t { OP_TS = 1, OP_FIRST = 2, OP_LAST = 4, OP_ADV_HID = 8, OP_TWO = 16, OP_EXTRA_DONE = 32 };
@@ -369,7 +377,9 @@ enum {
   BAR_EXTRA_EMPTY = BAR_EXTRA_FULL + 1,     // [1]  every MMA that reads the prologue chunks of this tile has completed (commit)
   BAR_ACC_FULL = BAR_EXTRA_EMPTY + 1,       // [kAccIds] accumulator complete (commit)
   BAR_ACC_EMPTY = BAR_ACC_FULL + kAccIds,   // [kAccIds] accumulator drained
-  BAR_COUNT = BAR_ACC_EMPTY + kAccIds
+  BAR_SAVE_FULL = BAR_ACC_EMPTY + kAccIds,  // [2]  kSave: every epilogue warp of this CTA has written its rows into the staging buffer
+  BAR_SAVE_EMPTY = BAR_SAVE_FULL + 2,       // [2]  kSave: the bulk stores have read the staging buffer
+  BAR_COUNT = BAR_SAVE_EMPTY + 2
 };
 static_assert(BAR_COUNT * 8 + 8 <= kSmemBar, "barrier region too small");
 
@@ -566,13 +576,14 @@ __device__ __forceinline__ float tanh_f(float x) {
 // tensor memory is dZ of the current layer, the streamed blocks are W^T, the prologue warps copy the head gradients
 // instead of encoding inputs, and the epilogue masks with the forward's ReLU bits instead of adding a bias.
 template <bool kAppear, bool kSave, bool kBwd = false>
-__global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid_constant__ FwdParams P) {
-  using C = Cfg<kAppear>;
+__global__ void __launch_bounds__(kSave ? kThreadsSave : kThreads, 1) field_forward_kernel(const __grid_constant__ FwdParams P) {
+  using C = Cfg<kAppear, kSave>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;                       // extra chunks
   const uint32_t sB = smem_base + C::kSmemA;           // weight ring
-  const uint32_t sBias = sB + C::kSmemB;
+  const uint32_t sSave = sB + C::kSmemB;               // kSave: two staging buffers of two chunks
+  const uint32_t sBias = sSave + C::kSmemSave;
   const uint32_t sBar = sBias + kSmemBias;
   const uint32_t sTmemPtr = sBar + BAR_COUNT * 8;
 #ifdef NSFF_TIMELINE
@@ -611,6 +622,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
     for (int i = 0; i < kAccIds; ++i) {
       mbar_init(bar(BAR_ACC_FULL + i), 1);
       mbar_init(bar(BAR_ACC_EMPTY + i), kEpiWarps * 2);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(BAR_SAVE_FULL + i), kEpiWarps);
+      mbar_init(bar(BAR_SAVE_EMPTY + i), 1);
     }
     fence_mbar_init();
   }
@@ -766,6 +781,35 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
         }
       }
     }
+  } else if (warp == kSaverWarp) {
+    // ===================== saved-image store issuer (training kernels) =====================
+    if constexpr (kSave) {
+      if (elect_one()) {
+        uint32_t cnt = 0;
+        for (int unit = group; unit < n_units; unit += n_groups) {
+          const int tile = unit * 2 + (int)cta_rank;
+          for (int s = 0; s < n_subs; ++s) {
+            const SubStep& ss = P.subs[s];
+            if (ss.epi == EPI_HEAD || ss.epi == EPI_ROWS || ss.save_off == kNoSave) continue;
+            const uint32_t buf = cnt & 1u;
+            mbar_wait_sleep(bar(BAR_SAVE_FULL + buf), (cnt >> 1) & 1u);
+            if (tile < P.n_tiles) {
+              uint8_t* g = P.save_base + ss.save_off + (size_t)tile * kSaveImgPerTile + (size_t)ss.slice0 * kChunkBytes;
+              bulk_s2g(g, sSave + buf * 2u * kChunkBytes, 2u * kChunkBytes);      // chunks slice0, slice0 + 1 are adjacent
+            }
+            bulk_commit_group();
+            // the previous group has been read out of its buffer once at most this one is still reading
+            bulk_wait_group_read<1>();
+            if (cnt > 0) mbar_arrive(bar(BAR_SAVE_EMPTY + (buf ^ 1u)));
+            ++cnt;
+          }
+        }
+        bulk_wait_group_read<0>();
+        if (cnt > 0) mbar_arrive(bar(BAR_SAVE_EMPTY + ((cnt - 1u) & 1u)));
+        bulk_wait_group<0>();              // the stores have been performed: the CTA may exit
+      }
+      __syncwarp();
+    }
   } else if (warp >= kEpiWarps + 2) {
     // ===================== prologue warps =====================
     // Encode a tile's inputs into the extra chunks (bf16, swizzled): 128 rows over 64 threads, one whole row at a time.
@@ -826,6 +870,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
     const int rsw = row & 7;
     uint32_t gsub = 0;
     uint32_t drain_par = 0;                        // bit a: (number of drains of accumulator a so far) & 1
+    uint32_t save_cnt = 0;                         // kSave: hidden sub-steps staged so far (buffer = count & 1)
 #ifdef NSFF_TIMELINE
     const uint32_t tl_base = sDbg + 2 * kDbgPerRole * 8;
     const int tl_role = 2;
@@ -842,6 +887,19 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
       float zrow = 0.f;
       if (P.pts.zs && P.x_emb == nullptr) zrow = P.pts.zs[p];
 
+      // kBwd: the ReLU bits of this warp's 2 x 16 columns of a masked sub-step (low / high half word), fetched one
+      // sub-step ahead - their global-memory latency (~700 cycles) would otherwise sit on the epilogue's critical path
+      // 38 times per tile
+      // (kept as the two raw 16-bit loads: combining them here would wait for the loads right after issuing them)
+      uint32_t mask_lo = 0xFFFFu, mask_hi = 0xFFFFu;
+      bool mask_pref_ok = false;
+      auto load_mask = [&](int si, uint32_t& lo, uint32_t& hi) {
+        const SubStep& ms = P.subs[si];
+        const uint8_t* bp = P.mask_base + ms.bits_off + (size_t)tile * kSaveBitsPerTile + (size_t)row * 4 + (part & 1) * 2 +
+                            (size_t)(2 * (int)ms.slice0 + (part >> 1)) * 512;      // word plane of chunk slice0 (128 rows x 4 B)
+        lo = __ldg(reinterpret_cast<const uint16_t*>(bp));
+        hi = __ldg(reinterpret_cast<const uint16_t*>(bp + 1024));                  // chunk slice0 + 1: two word planes on
+      };
       // ---------------- epilogues, one per sub-step ----------------
       for (int s = 0; s < n_subs; ++s, ++gsub) {
         const SubStep& ss = P.subs[s];
@@ -861,11 +919,16 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
           float4 b[4];
           uint32_t mb0 = 0xFFFFu, mb1 = 0xFFFFu;               // kBwd: ReLU bits of this warp's 16 columns of either slice
           if constexpr (kBwd) {
-            if (epi == EPI_MASK_HID && tile < P.n_tiles) {
-              const uint8_t* bp = P.mask_base + ss.bits_off + (size_t)tile * kSaveBitsPerTile + (size_t)row * 4 + (part & 1) * 2;
-              const size_t w0i = (size_t)(2 * (2 * half) + (part >> 1)) * 512;      // word plane of chunk 2*half (128 rows x 4 B)
-              mb0 = __ldg(reinterpret_cast<const uint16_t*>(bp + w0i));
-              mb1 = __ldg(reinterpret_cast<const uint16_t*>(bp + w0i + 1024));      // chunk 2*half + 1: two word planes on
+            if (tile < P.n_tiles) {
+              if (epi == EPI_MASK_HID) {
+                if (!mask_pref_ok) load_mask(s, mask_lo, mask_hi);
+                mb0 = mask_lo, mb1 = mask_hi;
+              }
+              mask_pref_ok = false;
+              // prefetch for the next hidden sub-step (rows sub-steps in between do not touch the prefetched words)
+              int sn = s + 1;
+              while (sn < n_subs && P.subs[sn].epi == EPI_ROWS) ++sn;
+              if (sn < n_subs && P.subs[sn].epi == EPI_MASK_HID) load_mask(sn, mask_lo, mask_hi), mask_pref_ok = true;
             }
           } else {
 #pragma unroll
@@ -908,23 +971,45 @@ __global__ void __launch_bounds__(kThreads, 1) field_forward_kernel(const __grid
           NSFF_TL((gsub << 8) | 7);                            // epi: hidden half published
           if constexpr (kSave) {
             // training mode: the bf16 rows just written are also the backward's tile image (128B-swizzled chunk
-            // [tile][chunk][128 rows x 128 B]); this warp owns one aligned 32-byte sector of its row per chunk, and
-            // 16 ReLU bits per chunk (recomputed from the packed bf16 values: positive <=> non-zero after ReLU)
-            if (ss.save_off != kNoSave && tile < P.n_tiles) {
+            // [tile][chunk][128 rows x 128 B]).  This warp owns one aligned 32-byte sector of its row per chunk: it goes
+            // into the staging buffer (same layout), from where the store issuer ships whole chunks; and 16 ReLU bits
+            // per chunk (recomputed from the packed bf16 values: positive <=> non-zero after ReLU) go straight to global.
+            if (ss.save_off != kNoSave) {
+              const uint32_t buf = save_cnt & 1u;
+              mbar_wait(bar(BAR_SAVE_EMPTY + buf), ((save_cnt >> 1) & 1u) ^ 1u);
+              NSFF_TL((gsub << 8) | 8);                        // epi: staging buffer free
+              ++save_cnt;
 #pragma unroll
               for (int c = 0; c < 2; ++c) {
                 const uint32_t* w = c ? w1 : w0;
-                const int cg = (int)(2 * half) + c;
-                uint8_t* g = P.save_base + ss.save_off + (size_t)tile * kSaveImgPerTile + (size_t)cg * kChunkBytes +
-                             (row_off);
                 const bool swap = rsw & 1;
-                const uint4 lo = make_uint4(w[0], w[1], w[2], w[3]), hi = make_uint4(w[4], w[5], w[6], w[7]);
-                st_global_v8(g + ((((part * 2) ^ rsw) & 6) << 4), swap ? hi : lo, swap ? lo : hi);
-                if (relu) {
-                  uint32_t pos16 = 0;
+                const uint32_t a = sSave + (buf * 2u + (uint32_t)c) * kChunkBytes + row_off + (uint32_t)((((part * 2) ^ rsw) & 6) << 4);
+                if (swap) {
+                  st_shared_v4(a, w[4], w[5], w[6], w[7]);
+                  st_shared_v4(a + 16, w[0], w[1], w[2], w[3]);
+                } else {
+                  st_shared_v4(a, w[0], w[1], w[2], w[3]);
+                  st_shared_v4(a + 16, w[4], w[5], w[6], w[7]);
+                }
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar(BAR_SAVE_FULL + buf));
+              NSFF_TL((gsub << 8) | 9);                        // epi: rows staged
+              if (relu && tile < P.n_tiles) {
 #pragma unroll
-                  for (int i = 0; i < 8; ++i)
-                    pos16 |= ((w[i] & 0x7FFFu) ? 1u : 0u) << (2 * i) | ((w[i] & 0x7FFF0000u) ? 1u : 0u) << (2 * i + 1);
+                for (int c = 0; c < 2; ++c) {
+                  const uint32_t* w = c ? w1 : w0;
+                  const int cg = (int)(2 * half) + c;
+                  // bit 2i / 2i+1 = low / high bf16 of word i is non-zero: per word one SIMD compare, collect the low-half
+                  // flags in bits 0-7 and the high-half flags in bits 16-23, then interleave the two bytes
+                  uint32_t acc2 = 0;
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) acc2 |= (__vcmpne2(w[i] & 0x7FFF7FFFu, 0u) & 0x00010001u) << i;
+                  acc2 = (acc2 | (acc2 << 4)) & 0x0F0F0F0Fu;
+                  acc2 = (acc2 | (acc2 << 2)) & 0x33333333u;
+                  acc2 = (acc2 | (acc2 << 1)) & 0x55555555u;
+                  const uint32_t pos16 = (acc2 & 0xFFFFu) | (acc2 >> 15);
                   *reinterpret_cast<uint16_t*>(P.save_base + ss.bits_off + (size_t)tile * kSaveBitsPerTile +
                                                ((size_t)(2 * cg + (part >> 1)) * 128 + row) * 4 + (part & 1) * 2) =
                       (uint16_t)pos16;
@@ -1449,6 +1534,37 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
   return pb.finish();
 }
 
+#ifdef NSFF_TIMELINE
+// NSFF_TIMELINE builds: every launch with NSFF_TIMELINE_OUT=<prefix> set dumps CTA 0's event log to <prefix>.<n>.bin
+static cudaError_t timeline_begin(FwdParams& P, cudaStream_t st, unsigned long long** dev) {
+  *dev = nullptr;
+  if (!getenv("NSFF_TIMELINE_OUT")) return cudaSuccess;
+  const size_t bytes = (size_t)3 * kDbgPerRole * sizeof(unsigned long long);
+  cudaError_t e = cudaMalloc(dev, bytes);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(*dev, 0, bytes, st);
+  P.dbg = *dev;
+  return e;
+}
+static cudaError_t timeline_end(cudaStream_t st, unsigned long long* dev) {
+  if (!dev) return cudaSuccess;
+  static int tl_seq = 0;
+  const size_t bytes = (size_t)3 * kDbgPerRole * sizeof(unsigned long long);
+  unsigned long long* host = (unsigned long long*)malloc(bytes);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaMemcpy(host, dev, bytes, cudaMemcpyDeviceToHost);
+  char name[512];
+  snprintf(name, sizeof(name), "%s.%d.bin", getenv("NSFF_TIMELINE_OUT"), tl_seq++);
+  if (FILE* f = fopen(name, "wb")) {
+    fwrite(host, 1, bytes, f);
+    fclose(f);
+  }
+  free(host);
+  cudaFree(dev);
+  return e;
+}
+#endif
+
 static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdParams& P, int out_mask, int64_t B,
                           float* out, int32_t out_ld, void* stream, void* save = nullptr) {
   if (!desc || !pack || !out) return NSFF_EINVAL;
@@ -1497,17 +1613,12 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
   }
   cudaStream_t st = (cudaStream_t)stream;
 #ifdef NSFF_TIMELINE
-  const char* tl_path = getenv("NSFF_TIMELINE_OUT");
   unsigned long long* tl_dev = nullptr;
-  const size_t tl_bytes = (size_t)3 * kDbgPerRole * sizeof(unsigned long long);
-  if (tl_path) {
-    NSFF_CUDA_TRY(cudaMalloc(&tl_dev, tl_bytes));
-    NSFF_CUDA_TRY(cudaMemsetAsync(tl_dev, 0, tl_bytes, st));
-    P.dbg = tl_dev;
-  }
+  NSFF_CUDA_TRY(timeline_begin(P, st, &tl_dev));
 #endif
   const bool appear = P.need_a != 0;
-  P.n_stages = (int)((appear ? Cfg<true>::kSmemB : Cfg<false>::kSmemB) / P.stage_bytes);
+  P.n_stages = (int)((save ? (appear ? Cfg<true, true>::kSmemB : Cfg<false, true>::kSmemB)
+                           : (appear ? Cfg<true>::kSmemB : Cfg<false>::kSmemB)) / P.stage_bytes);
   auto launch_pair = [&](auto kern, uint32_t smem) -> int {
     NSFF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int n_pairs = (P.n_tiles + 1) / 2;
@@ -1516,7 +1627,7 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
     if (n_pairs < clusters) clusters = n_pairs;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(save ? kThreadsSave : kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -1531,28 +1642,15 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
   };
   int lrc;
   if (save) {
-    lrc = appear ? launch_pair(field_forward_kernel<true, true>, Cfg<true>::kSmemTotal)
-                 : launch_pair(field_forward_kernel<false, true>, Cfg<false>::kSmemTotal);
+    lrc = appear ? launch_pair(field_forward_kernel<true, true>, Cfg<true, true>::kSmemTotal)
+                 : launch_pair(field_forward_kernel<false, true>, Cfg<false, true>::kSmemTotal);
   } else {
     lrc = appear ? launch_pair(field_forward_kernel<true, false>, Cfg<true>::kSmemTotal)
                  : launch_pair(field_forward_kernel<false, false>, Cfg<false>::kSmemTotal);
   }
   if (lrc != NSFF_OK) return lrc;
 #ifdef NSFF_TIMELINE
-  if (tl_dev) {
-    static int tl_seq = 0;
-    unsigned long long* host = (unsigned long long*)malloc(tl_bytes);
-    NSFF_CUDA_TRY(cudaStreamSynchronize(st));
-    NSFF_CUDA_TRY(cudaMemcpy(host, tl_dev, tl_bytes, cudaMemcpyDeviceToHost));
-    char name[512];
-    snprintf(name, sizeof(name), "%s.%d.bin", tl_path, tl_seq++);
-    if (FILE* f = fopen(name, "wb")) {
-      fwrite(host, 1, tl_bytes, f);
-      fclose(f);
-    }
-    free(host);
-    cudaFree(tl_dev);
-  }
+  NSFF_CUDA_TRY(timeline_end(st, tl_dev));
 #endif
   return after_launch();
 }
@@ -1611,13 +1709,13 @@ int launch_backward_chain(const ChainLayer* layers, int n_layers, const void* pa
   P.out_ld = out_ld;
   P.n_tiles = (int)cdiv64(B, kTileM);
   P.stage_bytes = 16384u;
-  P.n_stages = (int)(Cfg<false>::kSmemB / P.stage_bytes);
+  P.n_stages = (int)(Cfg<false, true>::kSmemB / P.stage_bytes);
   P.save_base = save;
   P.mask_base = mask;
   P.dp_img[0] = dp_static;
   P.dp_img[1] = dp_trans;
   auto kern = field_forward_kernel<false, true, true>;
-  const uint32_t smem = Cfg<false>::kSmemTotal;
+  const uint32_t smem = Cfg<false, true>::kSmemTotal;
   NSFF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int n_pairs = (P.n_tiles + 1) / 2;
   int clusters = sms / 2;
@@ -1625,7 +1723,7 @@ int launch_backward_chain(const ChainLayer* layers, int n_layers, const void* pa
   if (n_pairs < clusters) clusters = n_pairs;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * clusters);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(kThreadsSave);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1635,7 +1733,14 @@ int launch_backward_chain(const ChainLayer* layers, int n_layers, const void* pa
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+#ifdef NSFF_TIMELINE
+  unsigned long long* tl_dev = nullptr;
+  NSFF_CUDA_TRY(timeline_begin(P, st, &tl_dev));
+#endif
   NSFF_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, P));
+#ifdef NSFF_TIMELINE
+  NSFF_CUDA_TRY(timeline_end(st, tl_dev));
+#endif
   return after_launch();
 }
 }  // namespace tc

@@ -18,7 +18,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 PER = 512
 EV = {1: "prod: stage free, copy issued", 3: "mma: A ready", 4: "mma: weights ready, issue", 11: "mma: sub-step committed",
       5: "epi: wait acc", 6: "epi: acc complete", 7: "epi: hidden half published", 13: "epi: tile start",
-      14: "mma: accumulators free", 15: "mma: prologue ready"}
+      14: "mma: accumulators free", 15: "mma: prologue ready", 8: "epi: staging buffer free", 9: "epi: rows staged"}
 
 
 def run(prefix):
@@ -31,6 +31,27 @@ def run(prefix):
     with torch.no_grad():
         render_rays(models, emb, rays.cuda(), ts.cuda(), 29, N_samples=128, test_time=False,
                     output_transient_flow=["fw", "bw", "disocc"])
+    torch.cuda.synchronize()
+    print("wrote", prefix + ".*.bin")
+
+
+def run_train(prefix):
+    """one training forward + backward (1024 rays x 128): launches 0-2 = saving forwards (main, fw, bw), 3-5 = backward chains
+    (bw, fw, main)"""
+    import torch
+    os.environ["NSFF_TIMELINE_OUT"] = prefix
+    from parity_util import build_fields, synthetic_rays
+    from nsff_pl_b200.models.rendering import render_rays
+    models, emb, _, _ = build_fields(W=256, seed=0, n_frames=30)
+    for m in models.values():
+        m.requires_grad_(True)
+    emb["t"].weight.requires_grad_(True)
+    rays, ts = synthetic_rays(1024, n_frames=30, seed=1)
+    res = render_rays(models, emb, rays.cuda(), ts.cuda(), 29, N_samples=128, test_time=False,
+                      output_transient_flow=["fw", "bw", "disocc"])
+    loss = sum(res[k].square().mean() for k in ("rgb_fine", "rgb_fw", "rgb_bw", "transient_flow_fw", "transient_flow_bw",
+                                                 "xyzs_fw_bw", "xyzs_bw_fw"))
+    loss.backward()
     torch.cuda.synchronize()
     print("wrote", prefix + ".*.bin")
 
@@ -69,5 +90,7 @@ def show(path, s0=0, s1=10**9):
 if __name__ == "__main__":
     if sys.argv[1] == "run":
         run(sys.argv[2])
+    elif sys.argv[1] == "run_train":
+        run_train(sys.argv[2])
     else:
         show(sys.argv[2], *(int(x) for x in sys.argv[3:5]))
