@@ -353,7 +353,8 @@ def train_record(args, rank, local_rank, world, steps, warmup, loss_impl="fused"
                 g.replay()
             torch.cuda.synchronize()
             ms_g, per_g, _ = timed(g.replay)
-            graph_info = {"used": True, "ms_per_step_eager": ms / steps, "launches_per_replay": per_graph}
+            graph_info = {"used": True, "ms_per_step_eager": ms / steps, "median_step_ms_eager": round(per_step[len(per_step) // 2], 3),
+                          "launches_per_replay": per_graph}
             ms, per_step, launches, loss = ms_g, per_g, per_graph * steps, static_loss
         except Exception as e:  # capture is an optimisation of the caller loop: report and keep the eager number
             graph_info = {"used": False, "error": f"{type(e).__name__}: {str(e)[:200]}"}
@@ -727,7 +728,7 @@ def main():
         comp_ms = [a.elapsed_time(b) for a, b, _ in composite_events]
         comp_bytes = [n for _, _, n in composite_events]
         comp_gbs = (sum(comp_bytes) / (sum(comp_ms) * 1e-3)) / 1e9 if comp_ms else None
-        roofline_composite = {"bound": "hbm", "kernel": "nsff::composite_kernel<1,1,1>", "achieved": comp_gbs,
+        roofline_composite = {"bound": "hbm", "kernel": "nsff::composite_staged_kernel<1,1,1>", "achieved": comp_gbs,
                               "peak": peaks["hbm"], "unit": "GB/s", "frac": None if comp_gbs is None else comp_gbs / peaks["hbm"],
                               "traffic": _traffic("composite_traffic.json"), "peak_source": f"{peaks['source']} hbm_gbs",
                               "launches_timed": len(comp_ms), "avg_launch_ms": sum(comp_ms) / max(1, len(comp_ms)),

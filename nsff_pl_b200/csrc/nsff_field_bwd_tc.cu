@@ -548,15 +548,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) img_gemm_kernel(const __grid_
 // ------------------------------------------------------------------------------------------------------------------
 // img_wgrad_kernel: both operands MN-major (K = points), split over the point range, fp32 RED into acc_t
 // ------------------------------------------------------------------------------------------------------------------
-struct WgradParams {
+// One launch runs up to kWgMaxJobs independent weight-gradient GEMMs side by side (the chained backward has all dZ images
+// before the first one starts): each job owns a contiguous range of CTAs sized by its bytes per tile, so a CTA walks
+// 4-8 times more tiles per launch ramp and per accumulator flush than with one job per launch.
+struct WgradJob {
   const uint8_t* a_base;          // 4 chunks (M = 256 channels)
   uint32_t a_stride;
+  int32_t nb;
   const uint8_t* b_base[4];       // nb chunks (N = 64*nb channels)
   uint32_t b_stride[4];
-  int32_t nb, n_tiles, l2_hint;
   float* acc_t;                   // [(64*nb) x 256]
   float* colsum;                  // optional: colsum[m] += sum over the points of A[:, m] (bias gradient of the layer whose
                                   // dZ image is A), computed by the otherwise idle epilogue warps from the staged tiles
+};
+constexpr int kWgMaxJobs = 8;
+struct WgradParams {
+  WgradJob job[kWgMaxJobs];
+  int32_t cta0[kWgMaxJobs + 1];   // job j runs on CTAs [cta0[j], cta0[j+1])
+  int32_t n_jobs, n_tiles, l2_hint;
 };
 constexpr int kWgEpiWarps = 8;
 constexpr int kWgThreads = (kWgEpiWarps + 2) * 32;
@@ -586,18 +595,22 @@ __global__ void __launch_bounds__(kWgThreads, 1) img_wgrad_kernel(const __grid_c
   const uint32_t sTmemPtr = sBar + WB_COUNT * 8;
   auto bar = [&](int i) { return sBar + (uint32_t)i * 8u; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // contiguous tile range of this CTA
-  const int t0 = (int)((int64_t)P.n_tiles * blockIdx.x / gridDim.x);
-  const int t1 = (int)((int64_t)P.n_tiles * (blockIdx.x + 1) / gridDim.x);
+  int ji = 0;
+  while (ji + 1 < P.n_jobs && (int)blockIdx.x >= P.cta0[ji + 1]) ++ji;
+  const WgradJob& J = P.job[ji];
+  const int bi = (int)blockIdx.x - P.cta0[ji], nbi = P.cta0[ji + 1] - P.cta0[ji];
+  // contiguous tile range of this CTA inside its job
+  const int t0 = (int)((int64_t)P.n_tiles * bi / nbi);
+  const int t1 = (int)((int64_t)P.n_tiles * (bi + 1) / nbi);
   const int n_half = (t1 - t0) * 2;
 
 #ifdef NSFF_WATCHDOG
-  if (threadIdx.x == 0 && blockIdx.x == 0) printf("NSFF_WATCHDOG wgrad: barriers @%u (FULL[3] EMPTY[3] ACC), colsum %d\n", sBar, P.colsum != nullptr);
+  if (threadIdx.x == 0 && blockIdx.x == 0) printf("NSFF_WATCHDOG wgrad: barriers @%u (FULL[3] EMPTY[3] ACC), colsum %d\n", sBar, J.colsum != nullptr);
 #endif
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWgStages; ++i) {
       mbar_init(bar(WB_FULL + i), 1);
-      mbar_init(bar(WB_EMPTY + i), P.colsum ? 1 + kWgEpiWarps : 1);    // MMA commit (+ the column-sum warps)
+      mbar_init(bar(WB_EMPTY + i), J.colsum ? 1 + kWgEpiWarps : 1);    // MMA commit (+ the column-sum warps)
     }
     mbar_init(bar(WB_ACC), 1);
     fence_mbar_init();
@@ -609,7 +622,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) img_wgrad_kernel(const __grid_c
   tc_fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sTmemPtr));
-  const uint32_t N = (uint32_t)P.nb * 64u;
+  const uint32_t N = (uint32_t)J.nb * 64u;
   if (warp != kWgEpiWarps + 1) griddep_wait();       // operand tiles and the RED target belong to earlier kernels
 
   if (n_half > 0) {
@@ -617,16 +630,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) img_wgrad_kernel(const __grid_c
       if (elect_one()) {
         uint32_t stage = 0, par = 1;
         const uint64_t pol = policy_evict_first();
-        const uint32_t bytes = (4u + (uint32_t)P.nb) * kHalfChunk;
+        const uint32_t bytes = (4u + (uint32_t)J.nb) * kHalfChunk;
         for (int h = 0; h < n_half; ++h) {
           const size_t tile = (size_t)(t0 + (h >> 1));
           const size_t hoff = (size_t)(h & 1) * kHalfChunk;
           mbar_wait(bar(WB_EMPTY + stage), par);
           mbar_arrive_expect_tx(bar(WB_FULL + stage), bytes);
           const uint32_t s0 = base + stage * kWgStageBytes;
-          for (int c = 0; c < 4 + P.nb; ++c) {
-            const uint8_t* src = c < 4 ? P.a_base + tile * P.a_stride + (size_t)c * kChunkBytes + hoff
-                                       : P.b_base[c - 4] + tile * P.b_stride[c - 4] + hoff;
+          for (int c = 0; c < 4 + J.nb; ++c) {
+            const uint8_t* src = c < 4 ? J.a_base + tile * J.a_stride + (size_t)c * kChunkBytes + hoff
+                                       : J.b_base[c - 4] + tile * J.b_stride[c - 4] + hoff;
             if (P.l2_hint) bulk_g2s_hint(s0 + (uint32_t)c * kHalfChunk, src, kHalfChunk, bar(WB_FULL + stage), pol);
             else bulk_g2s(s0 + (uint32_t)c * kHalfChunk, src, kHalfChunk, bar(WB_FULL + stage));
           }
@@ -659,7 +672,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) img_wgrad_kernel(const __grid_c
       }
     } else {
       const int q = warp & 3, mh = warp >> 2;
-      if (P.colsum) {
+      if (J.colsum) {
         // column sums of the A image (256 channels, one per thread) from the staged half tiles: 64 points x 2 bytes per
         // thread and stage; the 32 lanes of a warp read 64 contiguous (swizzled) bytes of each row
         const int ch = threadIdx.x, c = ch >> 6, col = ch & 63;
@@ -678,15 +691,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) img_wgrad_kernel(const __grid_c
           if (lane == 0) mbar_arrive(bar(WB_EMPTY + stage));
           if (++stage == kWgStages) stage = 0, par ^= 1u;
         }
-        atomicAdd(P.colsum + ch, sum);
+        atomicAdd(J.colsum + ch, sum);
       }
       mbar_wait(bar(WB_ACC), 0);
       tc_fence_after_sync();
       const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)mh * 256u;
-      float* dst = P.acc_t + mh * 128 + q * 32 + lane;
+      float* dst = J.acc_t + mh * 128 + q * 32 + lane;
       // every CTA adds into the same 64*nb x 256 words: start each CTA at a different column so that the L2 atomic
       // units see different addresses at any one time
-      const uint32_t rot = ((uint32_t)blockIdx.x * 32u) % N;
+      const uint32_t rot = ((uint32_t)bi * 32u) % N;
       for (uint32_t c0 = 0; c0 < N; c0 += 32) {
         const uint32_t cb = (c0 + rot) % N;
         uint32_t v[32];
@@ -790,13 +803,26 @@ static int launch_gemm(GemmParams& P, cudaStream_t st) {
 }
 
 static int launch_wgrad(WgradParams& P, cudaStream_t st) {
-  if (P.n_tiles <= 0) return NSFF_OK;
-  if (P.nb < 1 || P.nb > 4) return NSFF_EINVAL;
+  if (P.n_tiles <= 0 || P.n_jobs <= 0) return NSFF_OK;
+  if (P.n_jobs > kWgMaxJobs) return NSFF_EINVAL;
+  int weight = 0;
+  for (int j = 0; j < P.n_jobs; ++j) {
+    if (P.job[j].nb < 1 || P.job[j].nb > 4) return NSFF_EINVAL;
+    weight += 4 + P.job[j].nb;                      // bytes per tile: 4 A chunks + nb B chunks
+  }
   NSFF_CUDA_TRY(cudaFuncSetAttribute(img_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem));
   P.l2_hint = l2_hint_enabled();
-  int grid = sm_count();
-  if (grid > P.n_tiles) grid = P.n_tiles;
-  return launch_pdl(img_wgrad_kernel, grid, kWgThreads, kWgSmem, st, P);
+  const int sms = sm_count();
+  int at = 0;
+  for (int j = 0; j < P.n_jobs; ++j) {
+    int n = (int)((int64_t)sms * (4 + P.job[j].nb) / weight);
+    if (n < 1) n = 1;
+    if (n > P.n_tiles) n = P.n_tiles;
+    P.cta0[j] = at;
+    at += n;
+  }
+  P.cta0[P.n_jobs] = at;
+  return launch_pdl(img_wgrad_kernel, at, kWgThreads, kWgSmem, st, P);
 }
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -1009,9 +1035,25 @@ struct Ctx {
   float* acc;
   size_t acc_used, acc_cap;   // in floats
   std::vector<FinishJob> finish;   // scatter jobs of the wgrad results, launched in batches (each owns its acc slot)
+  bool batch_wgrads = false;       // chained backward: every dZ image exists up front, so the weight-gradient GEMMs are
+  std::vector<WgradJob> pending;   // collected and launched kWgMaxJobs at a time
 };
 
+static int flush_wgrads(Ctx& c) {
+  for (size_t i = 0; i < c.pending.size(); i += kWgMaxJobs) {
+    WgradParams P;
+    memset(&P, 0, sizeof(P));
+    P.n_jobs = (int)std::min<size_t>(kWgMaxJobs, c.pending.size() - i);
+    for (int j = 0; j < P.n_jobs; ++j) P.job[j] = c.pending[i + j];
+    P.n_tiles = c.n_tiles;
+    TRY(launch_wgrad(P, c.st));
+  }
+  c.pending.clear();
+  return NSFF_OK;
+}
+
 static int flush_finish(Ctx& c) {
+  TRY(flush_wgrads(c));
   for (size_t i = 0; i < c.finish.size(); i += kFinishBatch) {
     FinishJobs JJ;
     memset(&JJ, 0, sizeof(JJ));
@@ -1067,16 +1109,18 @@ static std::vector<Src> four(const uint8_t* img) {
 static int wgrad_img(Ctx& c, const uint8_t* a_img, const std::vector<Src>& b, float** acc_out, float* colsum = nullptr) {
   const size_t need = b.size() * 64 * 256;
   if (b.empty() || b.size() > 4 || c.acc_used + need > c.acc_cap) return NSFF_EINVAL;
-  WgradParams P;
-  memset(&P, 0, sizeof(P));
-  P.a_base = a_img; P.a_stride = 4 * kChunkBytes;
-  for (size_t j = 0; j < b.size(); ++j) P.b_base[j] = b[j].p, P.b_stride[j] = b[j].stride;
-  P.nb = (int)b.size(); P.n_tiles = c.n_tiles;
-  P.acc_t = c.acc + c.acc_used;
-  P.colsum = colsum;
+  WgradJob J;
+  memset(&J, 0, sizeof(J));
+  J.a_base = a_img; J.a_stride = 4 * kChunkBytes;
+  for (size_t j = 0; j < b.size(); ++j) J.b_base[j] = b[j].p, J.b_stride[j] = b[j].stride;
+  J.nb = (int)b.size();
+  J.acc_t = c.acc + c.acc_used;
+  J.colsum = colsum;
   c.acc_used += need;
-  *acc_out = P.acc_t;
-  return launch_wgrad(P, c.st);
+  *acc_out = J.acc_t;
+  c.pending.push_back(J);
+  if (c.batch_wgrads) return NSFF_OK;               // launched by flush_wgrads (at the latest from flush_finish)
+  return flush_wgrads(c);
 }
 static int finish_cols(Ctx& c, const float* acc, float* dW, int ldw, std::initializer_list<int> dcol0,
                        std::initializer_list<int> ncols) {
@@ -1281,7 +1325,8 @@ static int backward_chain(Ctx& c, const nsff_field_desc* d, const BwdPack& L, Sc
   TRY(launch_backward_chain(chain.data(), (int)chain.size(), c.pack, want_s ? s.DP : nullptr, want_t ? s.DP2 : nullptr, B,
                             saved, s.base, s.DIN, 128, st));
 
-  // ---- weight gradients over the saved images (any order) ----
+  // ---- weight gradients over the saved images (any order: collected and launched kWgMaxJobs at a time) ----
+  c.batch_wgrads = true;
   float* acc;
   auto trunk_wgrads = [&](bool trans, uint8_t* const* G, uint8_t* const* H, float* const* gw, float* const* gb) -> int {
     const int n_in = trans ? d->in_xyz + d->in_t : d->in_xyz;
@@ -1660,12 +1705,14 @@ int nsff_img_wgrad(const nsff_img_wgrad_args* a, void* stream) {
   TRY(check_arch());
   WgradParams P;
   memset(&P, 0, sizeof(P));
-  P.a_base = reinterpret_cast<const uint8_t*>(a->a_img); P.a_stride = 4 * kChunkBytes;
+  WgradJob& J = P.job[0];
+  J.a_base = reinterpret_cast<const uint8_t*>(a->a_img); J.a_stride = 4 * kChunkBytes;
   for (int j = 0; j < a->b_chunks; ++j) {
-    P.b_base[j] = reinterpret_cast<const uint8_t*>(a->b_img) + (size_t)j * kChunkBytes;
-    P.b_stride[j] = (uint32_t)a->b_chunks * kChunkBytes;
+    J.b_base[j] = reinterpret_cast<const uint8_t*>(a->b_img) + (size_t)j * kChunkBytes;
+    J.b_stride[j] = (uint32_t)a->b_chunks * kChunkBytes;
   }
-  P.nb = a->b_chunks; P.n_tiles = (int)cdiv64(a->n_rows, 128); P.acc_t = a->acc_t;
+  J.nb = a->b_chunks; J.acc_t = a->acc_t;
+  P.n_jobs = 1; P.n_tiles = (int)cdiv64(a->n_rows, 128);
   return launch_wgrad(P, (cudaStream_t)stream);
 }
 }
