@@ -308,8 +308,11 @@ struct alignas(16) SubStep {
   uint64_t bits_off;       // ... and of its ReLU bit plane
   uint16_t n;              // 128 (hidden) or 16 (head)
   uint8_t pad[6];
+  // backward chain: byte offsets (from the per-thread base pointer into the forward's bit planes) of this sub-step's
+  // ReLU bits and of the bits to prefetch now for the next masked sub-step (kNoSave: none)
+  uint64_t mask_off, next_mask_off;
 };
-static_assert(sizeof(SubStep) == 48, "SubStep layout");
+static_assert(sizeof(SubStep) == 64, "SubStep layout");
 
 struct FwdParams {
   const uint8_t* pack;
@@ -887,19 +890,15 @@ __global__ void __launch_bounds__(kSave ? kThreadsSave : kThreads, 1) field_forw
       float zrow = 0.f;
       if (P.pts.zs && P.x_emb == nullptr) zrow = P.pts.zs[p];
 
-      // kBwd: the ReLU bits of this warp's 2 x 16 columns of a masked sub-step (low / high half word), fetched one
-      // sub-step ahead - their global-memory latency (~700 cycles) would otherwise sit on the epilogue's critical path
-      // 38 times per tile
-      // (kept as the two raw 16-bit loads: combining them here would wait for the loads right after issuing them)
+      // kBwd: the ReLU bits of this warp's 2 x 16 columns of a masked sub-step are fetched one sub-step ahead - their
+      // global-memory latency (~700 cycles) would otherwise sit on the epilogue's critical path 38 times per tile.  The
+      // plane offsets come precomputed with the sub-step table; the two raw 16-bit loads are kept apart (combining them
+      // here would wait for the loads right after issuing them).
       uint32_t mask_lo = 0xFFFFu, mask_hi = 0xFFFFu;
       bool mask_pref_ok = false;
-      auto load_mask = [&](int si, uint32_t& lo, uint32_t& hi) {
-        const SubStep& ms = P.subs[si];
-        const uint8_t* bp = P.mask_base + ms.bits_off + (size_t)tile * kSaveBitsPerTile + (size_t)row * 4 + (part & 1) * 2 +
-                            (size_t)(2 * (int)ms.slice0 + (part >> 1)) * 512;      // word plane of chunk slice0 (128 rows x 4 B)
-        lo = __ldg(reinterpret_cast<const uint16_t*>(bp));
-        hi = __ldg(reinterpret_cast<const uint16_t*>(bp + 1024));                  // chunk slice0 + 1: two word planes on
-      };
+      const uint8_t* mask_tb = nullptr;
+      if constexpr (kBwd)
+        mask_tb = P.mask_base + (size_t)tile * kSaveBitsPerTile + (size_t)row * 4 + (part & 1) * 2 + (part >> 1) * 512;
       // ---------------- epilogues, one per sub-step ----------------
       for (int s = 0; s < n_subs; ++s, ++gsub) {
         const SubStep& ss = P.subs[s];
@@ -921,14 +920,18 @@ __global__ void __launch_bounds__(kSave ? kThreadsSave : kThreads, 1) field_forw
           if constexpr (kBwd) {
             if (tile < P.n_tiles) {
               if (epi == EPI_MASK_HID) {
-                if (!mask_pref_ok) load_mask(s, mask_lo, mask_hi);
+                if (!mask_pref_ok) {                 // (first masked sub-step of a tile only)
+                  mask_lo = __ldg(reinterpret_cast<const uint16_t*>(mask_tb + ss.mask_off));
+                  mask_hi = __ldg(reinterpret_cast<const uint16_t*>(mask_tb + ss.mask_off + 1024));
+                }
                 mb0 = mask_lo, mb1 = mask_hi;
               }
-              mask_pref_ok = false;
-              // prefetch for the next hidden sub-step (rows sub-steps in between do not touch the prefetched words)
-              int sn = s + 1;
-              while (sn < n_subs && P.subs[sn].epi == EPI_ROWS) ++sn;
-              if (sn < n_subs && P.subs[sn].epi == EPI_MASK_HID) load_mask(sn, mask_lo, mask_hi), mask_pref_ok = true;
+              const uint64_t nmo = ss.next_mask_off;
+              mask_pref_ok = nmo != kNoSave;
+              if (mask_pref_ok) {
+                mask_lo = __ldg(reinterpret_cast<const uint16_t*>(mask_tb + nmo));
+                mask_hi = __ldg(reinterpret_cast<const uint16_t*>(mask_tb + nmo + 1024));    // chunk slice0 + 1: two word planes on
+              }
             }
           } else {
 #pragma unroll
@@ -1308,6 +1311,7 @@ struct ProgramBuilder {
       memset(s.pad, 0, sizeof(s.pad));
       s.save_off = save_off;
       s.bits_off = bits_off;
+      s.mask_off = s.next_mask_off = kNoSave;
       const int block_rows = pl.block_rows ? pl.block_rows : pl.n;
       const uint32_t block_bytes = (uint32_t)block_rows * 128u;          // whole packed block of one K-chunk
       const uint32_t piece = (uint32_t)n * 128u / 2u;                    // this CTA's N/2 rows of it
@@ -1697,6 +1701,17 @@ int launch_backward_chain(const ChainLayer* layers, int n_layers, const void* pa
   }
   int rc = pb.finish();
   if (rc != NSFF_OK) return rc;
+  {
+    // ReLU bit planes: [tile][8 word planes][128 rows] uint32; chunk c = planes 2c, 2c+1 (nsff_field_save.cuh)
+    uint64_t next = kNoSave;
+    for (int i = P.n_subs - 1; i >= 0; --i) {
+      SubStep& s = P.subs[i];
+      if (s.epi == EPI_ROWS) continue;
+      s.next_mask_off = next;
+      if (s.epi == EPI_MASK_HID) s.mask_off = s.bits_off + (uint64_t)s.slice0 * 1024u, next = s.mask_off;
+      else next = kNoSave;
+    }
+  }
   int dev = 0, major = 0, sms = 0;
   NSFF_CUDA_TRY(cudaGetDevice(&dev));
   NSFF_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
