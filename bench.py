@@ -270,7 +270,7 @@ def train_record(args, rank, local_rank, world, steps, warmup, loss_impl="fused"
             ev.record()
             phase.setdefault("ev", []).append((name, ev))
 
-    def step():
+    def compute():
         mark("start")
         opt.zero_grad(set_to_none=True)
         res = render_rays(models, emb, rays, ts, N_FRAMES - 1, **kw)
@@ -287,10 +287,17 @@ def train_record(args, rank, local_rank, world, steps, warmup, loss_impl="fused"
         mark("loss")
         loss.backward()
         mark("backward")
+        return loss
+
+    def update():
         if world > 1:
             parallel.all_reduce_gradients(params)
         opt.step()
         mark("allreduce+adam")
+
+    def step():
+        loss = compute()
+        update()
         return loss
 
     # every step - eager or captured - runs on ONE side stream: the parameters' AccumulateGrad nodes then live on the stream the
@@ -339,21 +346,31 @@ def train_record(args, rank, local_rank, world, steps, warmup, loss_impl="fused"
     # the host otherwise).  Everything inside is stream-ordered device work: the forward, the loss, the hand-written
     # backward, the re-pack of the bf16 weight images and the (capturable) Adam update.  New rays would be copied into
     # the static `rays` / `ts` tensors between replays.
+    # With several ranks only the rank-local part (forward, loss, backward) is captured; the gradient all-reduce (NCCL) and
+    # the Adam update stay eager launches after each replay - every rank issues the same collectives in either mode.
     graph_info = {"used": False}
-    if world == 1 and not getattr(args, "no_train_graph", False):
+    if not getattr(args, "no_train_graph", False):
         try:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             opt.zero_grad(set_to_none=True)
             n_before = _cabi.launch_count()
+            whole = world == 1
             with torch.cuda.graph(g, stream=side):
-                static_loss = step().detach()
+                static_loss = (step() if whole else compute()).detach()
             per_graph = int(_cabi.launch_count() - n_before)
-            for _ in range(3):
+
+            def replay():
                 g.replay()
+                if not whole:
+                    update()
+
+            for _ in range(3):
+                replay()
             torch.cuda.synchronize()
-            ms_g, per_g, _ = timed(g.replay)
-            graph_info = {"used": True, "ms_per_step_eager": ms / steps, "median_step_ms_eager": round(per_step[len(per_step) // 2], 3),
+            ms_g, per_g, _ = timed(replay)
+            graph_info = {"used": True, "captured": "whole step" if whole else "forward + loss + backward (all-reduce + Adam eager)",
+                          "ms_per_step_eager": ms / steps, "median_step_ms_eager": round(per_step[len(per_step) // 2], 3),
                           "launches_per_replay": per_graph}
             ms, per_step, launches, loss = ms_g, per_g, per_graph * steps, static_loss
         except Exception as e:  # capture is an optimisation of the caller loop: report and keep the eager number

@@ -134,13 +134,40 @@ def render_frame_sharded(render_fn, rays: torch.Tensor, ts, keys: Sequence[str] 
 
 def all_reduce_gradients(params: Sequence[torch.Tensor], group=None) -> int:
     """Data-parallel training (the reference's DDP, train.py:294-301): average the gradients of
-    `params` over the ranks with ONE all-reduce of a flat fp32 bucket (2.4 M parameters = 9.8 MB for fine + coarse +
+    `params` over the ranks with ONE all-reduce per flat gradient buffer (the per-model buffer the backward kernels fill,
+    reduced in place) plus ONE flat fp32 bucket for whatever lives elsewhere (2.4 M parameters = 9.8 MB for fine + coarse +
     time codes).  Parameters without a gradient on this rank contribute zeros - every rank must pass the same list.
     Returns the number of elements reduced."""
     world = dist.get_world_size(group)
     params = [p for p in params if p.requires_grad]
     if world == 1 or not params:
         return 0
+    # Gradients that already tile one storage densely (the per-model gradient buffer of models/autograd.py) are reduced
+    # in place through one flat view of that range - no bucket copies; everything else goes through the flat bucket.
+    n_reduced = 0
+    rest = params
+    if all(p.grad is not None for p in params):
+        by_storage = {}
+        for p in params:
+            g = p.grad
+            if g.is_contiguous() and g.dtype == torch.float32:
+                by_storage.setdefault((g.untyped_storage().data_ptr(), g.device), []).append(p)
+        rest = []
+        taken = set()
+        for (_, dev), ps in by_storage.items():
+            lo = min(p.grad.storage_offset() for p in ps)
+            hi = max(p.grad.storage_offset() + p.grad.numel() for p in ps)
+            if len(ps) < 2 or sum(p.grad.numel() for p in ps) < 0.9 * (hi - lo):
+                continue
+            flat = torch.empty(0, dtype=torch.float32, device=dev).set_(ps[0].grad.untyped_storage(), lo, (hi - lo,))
+            dist.all_reduce(flat, group=group)
+            flat /= world
+            n_reduced += int(flat.numel())
+            taken.update(id(p) for p in ps)
+        rest = [p for p in params if id(p) not in taken]
+        if not rest:
+            return n_reduced
+    params = rest
     ref = next((p.grad for p in params if p.grad is not None), None)
     dev = ref.device if ref is not None else params[0].device
     flat = torch.zeros(sum(p.numel() for p in params), device=dev, dtype=torch.float32)
@@ -160,4 +187,4 @@ def all_reduce_gradients(params: Sequence[torch.Tensor], group=None) -> int:
         else:
             p.grad.copy_(flat[o:o + n].view_as(p.grad))
         o += n
-    return int(flat.numel())
+    return n_reduced + int(flat.numel())

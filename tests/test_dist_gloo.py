@@ -104,6 +104,47 @@ def test_gradient_all_reduce_averages_over_ranks():
         assert torch.allclose(got[3], sum(want3) / world)
 
 
+def _arena_grad_worker(rank, world, port, ret):
+    for p in (ROOT, HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from nsff_pl_b200 import parallel
+        params = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(6))]
+        g = torch.Generator().manual_seed(200 + rank)
+        flat = torch.randn(16 + 8, generator=g)                   # 16-byte slots like models/autograd.py: 15 -> 16, 7 -> 8
+        params[0].grad = flat[0:15].view(5, 3)
+        params[1].grad = flat[16:23]
+        params[2].grad = torch.randn(6, generator=g)              # a gradient that lives elsewhere (the time-code table)
+        n = parallel.all_reduce_gradients(params)
+        ret[rank] = (n, [p.grad.clone() for p in params], params[0].grad.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_all_reduce_reduces_a_shared_gradient_buffer_in_place():
+    """Gradients that tile one storage (the per-model buffer the backward kernels fill) are reduced through one flat view of
+    it, in place; the rest goes through the bucket."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_arena_grad_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    flats, others = [], []
+    for r in range(world):
+        g = torch.Generator().manual_seed(200 + r)
+        flats.append(torch.randn(24, generator=g))
+        others.append(torch.randn(6, generator=g))
+    want = sum(flats) / world
+    for r in range(world):
+        n, got, in_place = ret[r]
+        assert n == 23 + 6 and in_place
+        assert torch.allclose(got[0].reshape(-1), want[0:15]) and torch.allclose(got[1], want[16:23])
+        assert torch.allclose(got[2], sum(others) / world)
+
+
 def _gather_worker(rank, world, port, ret):
     for p in (ROOT, HERE):
         if p not in sys.path:
