@@ -938,7 +938,7 @@ __global__ void __launch_bounds__(kSave ? kThreadsSave : kThreads, 1) field_forw
             for (int i = 0; i < 4; ++i) lds_v4(s_bias + (uint32_t)((part * 16 + i * 4) * 4), b[i]);
           }
           NSFF_TL((gsub << 8) | 5);                            // epi: waiting for the accumulator
-          mbar_wait(acc_full, acc_par);
+          mbar_wait(acc_full, acc_par);          // (a non-suspending test_wait spin here was measured 6 % slower: 16 spinning warps take issue slots)
           NSFF_TL((gsub << 8) | 6);                            // epi: accumulator complete
           tc_fence_after_sync();
           uint32_t v0[16], v1[16];
@@ -1265,7 +1265,8 @@ struct ProgramBuilder {
   // chain dZ of a branch's first layer has no reader, so the layer after it (extras only) takes the waits.
   bool hid_read[2] = {true, true};
   // host-only bookkeeping for the drain analysis in finish()
-  struct OpMeta { int acc; bool first, head; int waits_half; bool needs_hi; };
+  struct OpMeta { int acc; bool first, head; int waits_half; bool needs_hi; int acc2; };   // acc2: second accumulator a merged op starts (-1: none)
+  bool merge_pre = true;               // issue the K-chunks both halves read first as N = 256 MMAs (see push)
   OpMeta meta[kMaxOps];
 
   ProgramBuilder(FwdParams& p, bool split_, bool fine_) : P(p), split(split_), fine(fine_) { P.last_extra_sub = 0; }
@@ -1343,7 +1344,7 @@ struct ProgramBuilder {
           o.b2 = (uint16_t)(piece >> 4);
           o.w_src1 = src_of(kc + 1);
         }
-        m.acc = s.acc_id, m.first = kc == 0, m.head = head, m.waits_half = -1;
+        m.acc = s.acc_id, m.acc2 = -1, m.first = kc == 0, m.head = head, m.waits_half = -1;
         m.needs_hi = hidden && (ch >> 1) == 1;
         if (hidden) {
           // only the first op of the layer that reads a hidden half waits for it (half 1's ops issue later)
@@ -1384,9 +1385,36 @@ struct ProgramBuilder {
       int n_pre = 0;
       while (n_pre < n_half && !half_meta[0][n_pre].needs_hi) ++n_pre;
       const int hold = (fine && n_pre < n_half && n_pre > 0) ? 1 : 0;     // ops of half 1 kept back to cover half 0's epilogue
-      for (int k = 0; k < n_pre; ++k) {
-        emit(0, k);
-        if (k < n_pre - hold) emit(1, k);
+      if (merge_pre && !fine && n_pre > 0 && n_pre < n_half) {
+        // The K-chunks that only need channels 0-127 of the previous layer (or the prologue chunks) feed BOTH halves:
+        // one N = 256 MMA per K-step into the two adjacent accumulators instead of two N = 128 MMAs (138 vs 2 x 74
+        // cycles, profiles/r02a_ubench_mma.txt).  One K-chunk per op: its weight piece (128 rows per CTA) fills a stage.
+        for (int k = 0; k < n_pre; ++k) {
+          const ChunkOp& a = half_ops[0][k];
+          const int pieces = (a.flags & OP_TWO) ? 2 : 1;
+          for (int c = 0; c < pieces; ++c) {
+            if (n_ops >= kMaxOps) { overflow = true; break; }
+            ChunkOp o = a;
+            OpMeta m = half_meta[0][k];
+            o.idesc = make_idesc_bf16(2 * kTileM, 256u);
+            o.flags = (uint8_t)(a.flags & ~(OP_TWO | OP_LAST | (c ? OP_FIRST : 0)));
+            o.a = c ? a.a2 : a.a;
+            o.a2 = 0, o.b2 = 0;
+            o.w_src0 = c ? a.w_src1 : a.w_src0;
+            o.w_src1 = 0;
+            o.bytes = 256u * 128u / 2u;
+            if (c) o.wait_hid = 0, m.waits_half = -1;
+            m.first = (o.flags & OP_FIRST) != 0;
+            m.acc2 = m.first ? half_meta[1][k].acc : -1;
+            meta[n_ops] = m;
+            P.ops[n_ops++] = o;
+          }
+        }
+      } else {
+        for (int k = 0; k < n_pre; ++k) {
+          emit(0, k);
+          if (k < n_pre - hold) emit(1, k);
+        }
       }
       if (fine) {
         for (int k = n_pre; k < n_half; ++k) emit(0, k);
@@ -1410,7 +1438,7 @@ struct ProgramBuilder {
       if (!hid_read[h]) {
         int at = -1;
         for (int i = 0; i < n_ops && at < 0; ++i)
-          if (meta[i].first && !meta[i].head && (meta[i].acc & 1) == h) at = i;
+          if (meta[i].first && !meta[i].head && ((meta[i].acc & 1) == h || (meta[i].acc2 >= 0 && (meta[i].acc2 & 1) == h))) at = i;
         if (at < 0 || P.ops[at].wait_hid != 0) return NSFF_EUNSUPPORTED;
         P.ops[at].wait_hid = (uint8_t)(1 + h);
         meta[at].waits_half = h;
@@ -1438,10 +1466,13 @@ struct ProgramBuilder {
               narrow_pending[k] = true;
               narrow_region[k] = (o.d_col >> 8) & 1;
             } else {
-              const int h = m.acc & 1, r = m.acc >> 1;
-              if (stored[m.acc] >= 0 && waited[h] < stored[m.acc]) mask |= 1u << m.acc;
-              if (narrow_pending[h] && r == narrow_region[h]) mask |= 1u << (kHeadAcc + h), narrow_pending[h] = false;
-              stored[m.acc] = layer;
+              for (int a : {m.acc, m.acc2}) {
+                if (a < 0) continue;
+                const int h = a & 1, r = a >> 1;
+                if (stored[a] >= 0 && waited[h] < stored[a]) mask |= 1u << a;
+                if (narrow_pending[h] && r == narrow_region[h]) mask |= 1u << (kHeadAcc + h), narrow_pending[h] = false;
+                stored[a] = layer;
+              }
             }
             o.wait_empty |= mask;
           }
@@ -1477,6 +1508,7 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
   if ((want_fw || want_bw) && (!want_t || !d.has_flow || sigma_only)) return NSFF_EINVAL;
   int col = 0;
   ProgramBuilder pb(P, split, fine);
+  if (const char* me = getenv("NSFF_TC_MERGE")) pb.merge_pre = atoi(me) != 0;      // A/B knob
   auto push = [&](int lid, uint8_t epi) -> SubStep* {
     uint64_t save_off = kNoSave, bits_off = kNoSave;
     if (SL) {
@@ -1669,6 +1701,7 @@ int launch_backward_chain(const ChainLayer* layers, int n_layers, const void* pa
   static thread_local FwdParams P;          // 8 KB: keep it off the stack of the calling thread
   memset(&P, 0, sizeof(P));
   ProgramBuilder pb(P, /*split=*/true, /*fine=*/false);
+  if (const char* me = getenv("NSFF_TC_MERGE")) pb.merge_pre = atoi(me) != 0;
   for (int i = 0; i < n_layers; ++i) {
     const ChainLayer& c = layers[i];
     if (c.nchunks < 1 || c.nchunks > kMaxChunks) return NSFF_EINVAL;
