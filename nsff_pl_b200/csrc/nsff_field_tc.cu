@@ -20,7 +20,9 @@
 //       last-chunk-first so that "chunk 3 published" proves the whole region has been drained.
 //   split mode (NSFF_TC_SPLIT=1): every 256-wide layer is issued as two N = 128 halves with their own accumulator
 //       columns and barriers, so the epilogue of half 0 runs under the MMAs of half 1 and the first two K-chunks of the
-//       next layer are ready when half 1 completes: no accumulator-drain bubble between layers.
+//       next layer are ready when half 1 completes: no accumulator-drain bubble between layers.  The K-chunks both halves
+//       read first (prologue chunks, channels 0-127 of the previous layer) are issued once, as N = 256 MMAs into the two
+//       adjacent accumulators.
 //   smem  A operand : only the "extra" chunks written once per tile by the prologue: PE(xyz) (63 -> 64 cols), time code
 //                     (48), PE(dir) (27 -> 32) [+ appearance code (48)]  (128 rows x 64 bf16, 128B-swizzled, K-major)
 //   smem  B operand : 10-stage ring of weight pieces ((N/2) x 64 bf16 per CTA) streamed from the L2-resident field pack
@@ -1373,7 +1375,7 @@ struct ProgramBuilder {
     // channels 128-255, which the epilogue of the previous layer's second half is still producing; and half 0 of THIS
     // layer finishes while three ops of half 1 are still to come, so that its epilogue (whose result the next layer's
     // first ops need) has cover too:      a0 b0 a1 | a2 a3 | b1 b2 b3        (a = half 0, b = half 1, one K-chunk each).
-    // With two-chunk ops (fine = false) this degenerates to a01 b01 a23 b23.
+    // With two-chunk ops (fine = false) this degenerates to a01 b01 a23 b23 - and a01 b01 become the merged ab0 ab1 below.
     auto emit = [&](int h, int k) {
       if (n_ops >= kMaxOps) { overflow = true; return; }
       meta[n_ops] = half_meta[h][k];
@@ -1617,7 +1619,8 @@ static int launch_forward(const nsff_field_desc* desc, const void* pack, FwdPara
     P.save_base = static_cast<uint8_t*>(save);
   }
   const bool split = true;       // every 256-wide layer = two N = 128 sub-steps (file header)
-  // default: two K-chunks (8 MMAs) per op, issue order a01 b01 a23 b23.  NSFF_TC_FINE=1: one K-chunk per op, order
+  // default: issue order ab0 ab1 a23 b23 (merged N = 256 ops for the chunks both halves read first, then two K-chunks =
+  // 8 MMAs per op; NSFF_TC_MERGE=0: a01 b01 a23 b23).  NSFF_TC_FINE=1: one K-chunk per op, order
   // a0 b0 a1 | a2 a3 | b1 b2 b3 (more cover for the first half's epilogue, but twice the per-op issue overhead: measured slower)
   const char* fe = getenv("NSFF_TC_FINE");
   const bool fine = fe ? atoi(fe) != 0 : false;
