@@ -525,3 +525,20 @@ def test_staged_composite_is_bit_identical_to_the_direct_kernel(monkeypatch, mod
     assert list(outs[0]) == list(outs[1])
     for k in outs[0]:
         assert torch.equal(outs[0][k], outs[1][k]), k
+
+
+def test_merged_n256_ops_equal_the_two_half_ops(monkeypatch):
+    """field kernel: the K-chunks both halves of a layer read first are issued as N = 256 MMAs into the two adjacent half
+    accumulators (NSFF_TC_MERGE=1, default) instead of two N = 128 MMAs: same products, same accumulation order per
+    accumulator element - the heads must agree to rounding noise (measured: bit-identical)."""
+    from nsff_pl_b200.models.rendering import render_rays
+    models, emb, _, _ = build_fields(W=256, seed=51, precision="bf16", n_frames=8)
+    rays, ts = synthetic_rays(300, n_frames=8, seed=52)
+    kw = dict(N_samples=64, perturb=0, noise_std=0, test_time=False, output_transient_flow=["fw", "bw", "disocc"])
+    outs = []
+    for merge in ("1", "0"):
+        monkeypatch.setenv("NSFF_TC_MERGE", merge)
+        with torch.no_grad():
+            outs.append(render_rays(models, emb, rays.cuda(), ts.cuda(), 7, **kw))
+    for k in outs[0]:
+        assert max_abs(outs[0][k], outs[1][k]) <= 1e-5 * max(1.0, float(outs[1][k].abs().max())), k
