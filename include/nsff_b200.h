@@ -376,7 +376,8 @@ NSFF_API int nsff_ndc_rays(const float* K4 /*host*/, float near, float shift_nea
  *     colour, shift/scale-invariant depth, entropy, static/dynamic cross-entropy, 2D-3D flow consistency, photometric
  *     warp, cycle consistency and the three scene-flow regularisers - every term of losses.py:72-161 - in three
  *     launches forward and one backward (the reference spends ~300 ATen kernels on it).  All tensors fp32 contiguous;
- *     `medians` = {median(depth_fine), median(-disps), median(depth_coarse)} (torch.median, device floats);
+ *     `medians` = {median(depth_fine), median(-disps), median(depth_coarse)} (lower medians as torch.median, device
+ *     floats): for R <= 2048 the forward computes and writes them itself, for larger R the caller supplies them;
  *     `terms` receives the NSFF_LOSS_TERMS means in nsff_loss_term order (flow terms: mean over the rays whose
  *     projected depth is positive and that have a neighbouring frame; 0 when there is none).  topk < 1 is not supported.
  */
@@ -405,7 +406,7 @@ typedef struct {
   const float *Ks;             /* (n_cams, 3, 3)                                                                     */
   const float *Ps;             /* (n_cams, n_frames, 3, 4)                                                           */
   const float *ray_weights;    /* kwargs['weights'] (R) or NULL                                                      */
-  const float *medians;        /* 3 device floats, see above                                                         */
+  float *medians;              /* 3 device floats, see above: WRITTEN by the forward when R <= 2048, else supplied   */
   float *stats;                /* nsff_loss_stats_floats() floats, written by the forward, read by the backward      */
   float *term_sums;            /* NSFF_LOSS_TERMS floats of scratch                                                  */
   float *terms;                /* NSFF_LOSS_TERMS floats: the loss dict                                              */

@@ -2,7 +2,8 @@
 //   loss_stats_kernel   one block: the global statistics the per-ray terms need - scale of the shift/scale-invariant depth
 //                       loss (losses.py:8-29: s = mean|d - median|, and the sums its gradient needs), the means of the
 //                       detached disocclusion weights (losses.py:131-145), the number of rays with a valid 2D-3D flow
-//                       target (losses.py:118-127).  The two medians come from the caller (torch.median, one op each).
+//                       target (losses.py:118-127).  For R <= kMedianMaxR it also finds the three medians (rank counting
+//                       in shared memory: exact lower medians, as torch.median); above that the caller supplies them.
 //   loss_kernel<false>  one warp per ray: every per-ray term, block-reduced, one atomicAdd per term and block.
 //   loss_kernel<true>   same traversal, writes d(sum_k g_k * term_k) / d(input) for every differentiable input.
 //   loss_finish_kernel  divides the sums by their denominators (R, or the valid-ray counts).
@@ -44,10 +45,42 @@ __device__ __forceinline__ void ndc2world_pullback(const float* p, Cam c, const 
   d[2] = (g[0] * (-p[0] * c.cxfx) + g[1] * (-p[1] * c.cyfy) + g[2]) * drz;
 }
 
+constexpr int kMedianMaxR = 2048;
+
+// lower median (sorted[(n - 1) / 2], torch.median's convention) of n <= kMedianMaxR values by rank counting: element i is
+// the answer iff #less <= k < #less + #equal.  One block; `vals` is shared memory.
+__device__ void block_median(const float* __restrict__ src, float sign, int n, float* vals, float* out) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) vals[i] = sign * src[i];
+  __syncthreads();
+  const int k = (n - 1) / 2;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = vals[i];
+    int less = 0, equal = 0;
+    for (int j = 0; j < n; ++j) {
+      const float w = vals[j];
+      less += w < v ? 1 : 0;
+      equal += w == v ? 1 : 0;
+    }
+    if (less <= k && k < less + equal) *out = v;      // (ties: every candidate writes the same value)
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(1024) loss_stats_kernel(const nsff_loss_args a) {
   __shared__ float sh[32];
   __shared__ float s_pred, s_gt, s_pred_c;
-  const float t_pred = a.medians[0], t_gt = a.medians[1], t_pred_c = a.depth_coarse ? a.medians[2] : 0.f;
+  __shared__ float med[3];
+  __shared__ float vals[kMedianMaxR];
+  if (a.R <= kMedianMaxR) {
+    block_median(a.depth_fine, 1.f, (int)a.R, vals, &med[0]);
+    block_median(a.disps, -1.f, (int)a.R, vals, &med[1]);
+    if (a.depth_coarse) block_median(a.depth_coarse, 1.f, (int)a.R, vals, &med[2]);
+    if (threadIdx.x < 3 && (threadIdx.x < 2 || a.depth_coarse)) a.medians[threadIdx.x] = med[threadIdx.x];
+  } else {
+    if (threadIdx.x < 3) med[threadIdx.x] = a.medians[threadIdx.x];
+    __syncthreads();
+  }
+  const float t_pred = med[0], t_gt = med[1], t_pred_c = a.depth_coarse ? med[2] : 0.f;
   const float invR = 1.f / (float)a.R;
   float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // |d-t|, |g-t|, |dc-t|, disocc_fw, disocc_bw, valid_fw, valid_bw, n_eq
   float neq_c = 0.f, csgn = 0.f, csgn_c = 0.f;
@@ -81,8 +114,22 @@ __global__ void __launch_bounds__(1024) loss_stats_kernel(const nsff_loss_args a
   for (int i = 0; i < 8; ++i) tot[i] = block_sum(v[i], sh);
   const float t_neq_c = block_sum(neq_c, sh), t_csgn = block_sum(csgn, sh), t_csgn_c = block_sum(csgn_c, sh);
   float dsf = 0.f, dsb = 0.f;
-  if (a.has_flow)
-    for (int64_t i = threadIdx.x; i < a.R * a.S; i += blockDim.x) dsf += a.disoccs_fw[i], dsb += a.disoccs_bw[i];
+  if (a.has_flow) {
+    const int64_t n = a.R * a.S;
+    if ((n & 3) == 0 && (((uintptr_t)a.disoccs_fw | (uintptr_t)a.disoccs_bw) & 15u) == 0) {
+      const float4* f4 = reinterpret_cast<const float4*>(a.disoccs_fw);
+      const float4* b4 = reinterpret_cast<const float4*>(a.disoccs_bw);
+      float f[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+      for (int64_t i = threadIdx.x; i < n / 4; i += blockDim.x) {
+        const float4 x = f4[i], y = b4[i];
+        f[0] += x.x, f[1] += x.y, f[2] += x.z, f[3] += x.w;
+        b[0] += y.x, b[1] += y.y, b[2] += y.z, b[3] += y.w;
+      }
+      dsf = (f[0] + f[1]) + (f[2] + f[3]), dsb = (b[0] + b[1]) + (b[2] + b[3]);
+    } else {
+      for (int64_t i = threadIdx.x; i < n; i += blockDim.x) dsf += a.disoccs_fw[i], dsb += a.disoccs_bw[i];
+    }
+  }
   const float t_dsf = block_sum(dsf, sh), t_dsb = block_sum(dsb, sh);
   if (threadIdx.x == 0) {
     s_pred = tot[0] * invR, s_gt = tot[1] * invR, s_pred_c = tot[2] * invR;

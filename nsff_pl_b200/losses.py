@@ -123,9 +123,12 @@ class NeRFWLoss(nn.Module):
         cfg = dict(R=R, has_flow=has_flow, thickness=int(self.thickness_filter.shape[-1]), n_frames=1, max_t=0,
                    lambda_geo_d=self.lambda_geo_d, lambda_geo_f=self.lambda_geo_f, lambda_reg=self.lambda_reg,
                    lambda_ent=self.lambda_ent, cross_entropy_w=0.0)
-        meds = [torch.median(diff["depth_fine"].detach()), torch.median(-const["disps"])]
-        meds.append(torch.median(diff["depth_coarse"].detach()) if diff["depth_coarse"] is not None else meds[0])
-        const["medians"] = torch.stack(meds).float()
+        if R <= 2048:                       # the stats kernel finds the medians itself (rank counting in shared memory)
+            const["medians"] = torch.empty(3, device=rgb.device, dtype=torch.float32)
+        else:
+            meds = [torch.median(diff["depth_fine"].detach()), torch.median(-const["disps"])]
+            meds.append(torch.median(diff["depth_coarse"].detach()) if diff["depth_coarse"] is not None else meds[0])
+            const["medians"] = torch.stack(meds).float()
         if has_flow:
             S = inputs["transient_weights_fine"].shape[1]
             cfg["cross_entropy_w"] = self.lambda_ent / 5 * min(kwargs["epoch"] / 10, 1.0)
@@ -150,7 +153,8 @@ class NeRFWLoss(nn.Module):
         cfg.update(S=int(S), n_reg=int(S * self.z_far), const=const)
         terms = _LossFn.apply(cfg, *[diff.get(k) for k in _DIFF])
         keys = TERM_KEYS if has_flow else TERM_KEYS[:2]
-        ret = {k: terms[TERM_KEYS.index(k)] for k in keys}
+        parts = terms.unbind(0)            # one autograd node (backward: one stack) instead of eleven selects
+        ret = {k: parts[TERM_KEYS.index(k)] for k in keys}
         if has_flow and self.strict_keys:
             nv = const_valid_counts(cfg)          # host synchronisation, like the reference's valid.any()
             for k, n in zip(("flow_fw_l", "flow_bw_l"), nv):

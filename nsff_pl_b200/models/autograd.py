@@ -261,6 +261,7 @@ class CompositeFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, cfg, zs, xyz, n_s, n_t, n_fw, n_bw, raw, raw_fw, raw_bw, xyz_fw, xyz_bw):
+        ctx.set_materialize_grads(False)      # undefined output gradients stay None (NULL for the kernel), no zero fills
         R, S = zs.shape
         if S > MAX_TRAIN_SAMPLES:
             # nsff_composite_backward keeps a ray's samples in registers (32 lanes x 8 chunks): say so before the forward
