@@ -540,13 +540,23 @@ __device__ __forceinline__ void add2(float a0, float a1, float b0, float b1, flo
 }
 
 // 16 accumulator columns of one row: + bias, (ReLU,) round to bf16, pack pairs -> 8 words = one K = 16 step of the next
-// layer's A operand
-__device__ __forceinline__ void bias_act_pack(const uint32_t (&v)[16], const float4 (&b)[4], bool relu, uint32_t (&w)[8]) {
+// layer's A operand.  kBits (training forward): also the 16 ReLU bits (bit j = pre-activation j is not negative: one
+// funnel shift per column collects the sign bits - the backward's mask; an exact zero counts as active, its gradient
+// contribution meets a zero activation in the weight gradient either way).
+template <bool kBits = false>
+__device__ __forceinline__ void bias_act_pack(const uint32_t (&v)[16], const float4 (&b)[4], bool relu, uint32_t (&w)[8],
+                                              uint32_t* bits = nullptr) {
   float f[16];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     add2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), b[i].x, b[i].y, f[4 * i], f[4 * i + 1]);
     add2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]), b[i].z, b[i].w, f[4 * i + 2], f[4 * i + 3]);
+  }
+  if constexpr (kBits) {
+    uint32_t neg = 0;
+#pragma unroll
+    for (int j = 15; j >= 0; --j) neg = __funnelshift_l(__float_as_uint(f[j]), neg, 1);      // (neg << 1) | sign(f[j])
+    *bits = ~neg & 0xFFFFu;
   }
   if (relu) {
 #pragma unroll
@@ -901,6 +911,9 @@ __global__ void __launch_bounds__(kSave ? kThreadsSave : kThreads, 1) field_forw
       const uint8_t* mask_tb = nullptr;
       if constexpr (kBwd)
         mask_tb = P.mask_base + (size_t)tile * kSaveBitsPerTile + (size_t)row * 4 + (part & 1) * 2 + (part >> 1) * 512;
+      uint8_t* bits_tb = nullptr;                      // training forward: where this thread's ReLU bits of a tile go
+      if constexpr (kSave && !kBwd)
+        bits_tb = P.save_base + (size_t)tile * kSaveBitsPerTile + (size_t)row * 4 + (part & 1) * 2 + (part >> 1) * 512;
       // ---------------- epilogues, one per sub-step ----------------
       for (int s = 0; s < n_subs; ++s, ++gsub) {
         const SubStep& ss = P.subs[s];
@@ -961,12 +974,12 @@ __global__ void __launch_bounds__(kSave ? kThreadsSave : kThreads, 1) field_forw
           } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) lds_v4(s_bias + (uint32_t)((64 + part * 16 + i * 4) * 4), b1[i]);
-            bias_act_pack(v0, b, relu, w0);
+            bias_act_pack<kSave>(v0, b, relu, w0, &mb0);        // (kSave: mb0 / mb1 receive the ReLU bits)
           }
           // K-step `part` of hidden chunk slice0: 16 bf16 = 8 columns, in place (columns this warp has drained)
           tmem_st8(t_acc + (uint32_t)(part * 16), w0[0], w0[1], w0[2], w0[3], w0[4], w0[5], w0[6], w0[7]);
           if constexpr (kBwd) mask_pack(v1, mb1, w1);
-          else bias_act_pack(v1, b1, relu, w1);
+          else bias_act_pack<kSave>(v1, b1, relu, w1, &mb1);
           tmem_st8(t_acc + (uint32_t)(8 + part * 16), w1[0], w1[1], w1[2], w1[3], w1[4], w1[5], w1[6], w1[7]);
           // both chunks of this 128-channel half are written: publish it to the MMA issuer
           tmem_st_wait();
@@ -978,7 +991,7 @@ __global__ void __launch_bounds__(kSave ? kThreadsSave : kThreads, 1) field_forw
             // training mode: the bf16 rows just written are also the backward's tile image (128B-swizzled chunk
             // [tile][chunk][128 rows x 128 B]).  This warp owns one aligned 32-byte sector of its row per chunk: it goes
             // into the staging buffer (same layout), from where the store issuer ships whole chunks; and 16 ReLU bits
-            // per chunk (recomputed from the packed bf16 values: positive <=> non-zero after ReLU) go straight to global.
+            // per chunk (collected by bias_act_pack) go straight to global.
             if (ss.save_off != kNoSave) {
               const uint32_t buf = save_cnt & 1u;
               mbar_wait(bar(BAR_SAVE_EMPTY + buf), ((save_cnt >> 1) & 1u) ^ 1u);
@@ -1001,23 +1014,11 @@ __global__ void __launch_bounds__(kSave ? kThreadsSave : kThreads, 1) field_forw
               __syncwarp();
               if (lane == 0) mbar_arrive(bar(BAR_SAVE_FULL + buf));
               NSFF_TL((gsub << 8) | 9);                        // epi: rows staged
-              if (relu && tile < P.n_tiles) {
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                  const uint32_t* w = c ? w1 : w0;
-                  const int cg = (int)(2 * half) + c;
-                  // bit 2i / 2i+1 = low / high bf16 of word i is non-zero: per word one SIMD compare, collect the low-half
-                  // flags in bits 0-7 and the high-half flags in bits 16-23, then interleave the two bytes
-                  uint32_t acc2 = 0;
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) acc2 |= (__vcmpne2(w[i] & 0x7FFF7FFFu, 0u) & 0x00010001u) << i;
-                  acc2 = (acc2 | (acc2 << 4)) & 0x0F0F0F0Fu;
-                  acc2 = (acc2 | (acc2 << 2)) & 0x33333333u;
-                  acc2 = (acc2 | (acc2 << 1)) & 0x55555555u;
-                  const uint32_t pos16 = (acc2 & 0xFFFFu) | (acc2 >> 15);
-                  *reinterpret_cast<uint16_t*>(P.save_base + ss.bits_off + (size_t)tile * kSaveBitsPerTile +
-                                               ((size_t)(2 * cg + (part >> 1)) * 128 + row) * 4 + (part & 1) * 2) =
-                      (uint16_t)pos16;
+              if constexpr (!kBwd) {
+                if (relu && tile < P.n_tiles) {
+                  uint8_t* bp = bits_tb + ss.mask_off;                               // word plane of chunk slice0
+                  *reinterpret_cast<uint16_t*>(bp) = (uint16_t)mb0;
+                  *reinterpret_cast<uint16_t*>(bp + 1024) = (uint16_t)mb1;         // chunk slice0 + 1: two word planes on
                 }
               }
             }
@@ -1520,7 +1521,10 @@ static int build_program(const nsff_field_desc& d, const PackLayout& L, int out_
       else if (lid >= L_T1 && lid <= L_T8) save_off = SL->t_h[lid - L_T1], bits_off = SL->t_hb[lid - L_T1];
       else if (lid == L_TFIN) save_off = SL->t_feat;
     }
-    return pb.push(L.layer[lid], epi, save_off, bits_off);
+    SubStep* sub = pb.push(L.layer[lid], epi, save_off, bits_off);
+    if (sub && bits_off != kNoSave && epi == EPI_RELU_HID)
+      for (int h = 0; h < 2; ++h) sub[h].mask_off = bits_off + (uint64_t)sub[h].slice0 * 1024u;     // bit-plane offset of chunk slice0
+    return sub;
   };
   P.need_dir = 0;
   P.need_t = 0;
