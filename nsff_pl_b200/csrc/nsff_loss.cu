@@ -2,8 +2,8 @@
 //   loss_stats_kernel   one block: the global statistics the per-ray terms need - scale of the shift/scale-invariant depth
 //                       loss (losses.py:8-29: s = mean|d - median|, and the sums its gradient needs), the means of the
 //                       detached disocclusion weights (losses.py:131-145), the number of rays with a valid 2D-3D flow
-//                       target (losses.py:118-127).  For R <= kMedianMaxR it also finds the three medians (rank counting
-//                       in shared memory: exact lower medians, as torch.median); above that the caller supplies them.
+//                       target (losses.py:118-127).  For R <= kMedianMaxR it also finds the three medians (bitonic
+//                       sort in shared memory: exact lower medians, as torch.median); above that the caller supplies them.
 //   loss_kernel<false>  one warp per ray: every per-ray term, block-reduced, one atomicAdd per term and block.
 //   loss_kernel<true>   same traversal, writes d(sum_k g_k * term_k) / d(input) for every differentiable input.
 //   loss_finish_kernel  divides the sums by their denominators (R, or the valid-ray counts).
@@ -47,22 +47,25 @@ __device__ __forceinline__ void ndc2world_pullback(const float* p, Cam c, const 
 
 constexpr int kMedianMaxR = 2048;
 
-// lower median (sorted[(n - 1) / 2], torch.median's convention) of n <= kMedianMaxR values by rank counting: element i is
-// the answer iff #less <= k < #less + #equal.  One block; `vals` is shared memory.
+// lower median (sorted[(n - 1) / 2], torch.median's convention) of n <= kMedianMaxR values: bitonic sort in shared memory
+// (padded with +inf to a power of two; 55 compare-exchange stages for 1024 values, ~3 us).  One block.
 __device__ void block_median(const float* __restrict__ src, float sign, int n, float* vals, float* out) {
-  for (int i = threadIdx.x; i < n; i += blockDim.x) vals[i] = sign * src[i];
+  int m = 1;
+  while (m < n) m <<= 1;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) vals[i] = i < n ? sign * src[i] : INFINITY;
   __syncthreads();
-  const int k = (n - 1) / 2;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float v = vals[i];
-    int less = 0, equal = 0;
-    for (int j = 0; j < n; ++j) {
-      const float w = vals[j];
-      less += w < v ? 1 : 0;
-      equal += w == v ? 1 : 0;
+  for (int k = 2; k <= m; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const int p = i ^ j;
+        if (p > i) {
+          const float a = vals[i], b = vals[p];
+          if ((a > b) == ((i & k) == 0)) vals[i] = b, vals[p] = a;
+        }
+      }
+      __syncthreads();
     }
-    if (less <= k && k < less + equal) *out = v;      // (ties: every candidate writes the same value)
-  }
+  if (threadIdx.x == 0) *out = vals[(n - 1) / 2];
   __syncthreads();
 }
 

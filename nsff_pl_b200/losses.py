@@ -123,7 +123,7 @@ class NeRFWLoss(nn.Module):
         cfg = dict(R=R, has_flow=has_flow, thickness=int(self.thickness_filter.shape[-1]), n_frames=1, max_t=0,
                    lambda_geo_d=self.lambda_geo_d, lambda_geo_f=self.lambda_geo_f, lambda_reg=self.lambda_reg,
                    lambda_ent=self.lambda_ent, cross_entropy_w=0.0)
-        if R <= 2048:                       # the stats kernel finds the medians itself (rank counting in shared memory)
+        if R <= 2048:                       # the stats kernel finds the medians itself (bitonic sort in shared memory)
             const["medians"] = torch.empty(3, device=rgb.device, dtype=torch.float32)
         else:
             meds = [torch.median(diff["depth_fine"].detach()), torch.median(-const["disps"])]
