@@ -18,34 +18,57 @@ __device__ __forceinline__ void ndc2world_d(const float* p, float fx, float fy, 
   o[2] = rz;
 }
 
-__global__ void interp_splat_kernel(const nsff_interpolate_args a, float* __restrict__ buf) {
-  const int64_t B = a.R * a.S;
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 2 * B) return;
-  const int dir = idx >= B;
-  const int64_t p = dir ? idx - B : idx;
-  const int64_t r = p / a.S;
-  const int s = (int)(p - r * a.S);
-  const float* xyz = a.xyzs + p * 3;
-  const float* fl = (dir ? a.flow_bw : a.flow_fw) + p * (dir ? a.ld_tp1 : a.ld_t);
-  const float scale = dir ? 1.f - a.dt : a.dt;
-  float w0[3], w1[3];
-  ndc2world_d(xyz, a.fx, a.fy, a.cx, a.cy, w0);
-  const float moved[3] = {xyz[0] + fl[0], xyz[1] + fl[1], xyz[2] + fl[2]};
-  ndc2world_d(moved, a.fx, a.fy, a.cx, a.cy, w1);
-  float q[3];
+// One block = 32 consecutive pixels of an image row x 8 sample planes of one direction.  The inputs are ray-major
+// ((R,S,..): a ray's 8 consecutive samples are contiguous), the splat buffer is plane-major: the block loads and projects
+// with thread = (ray, plane) - contiguous 96 / 448-byte segments per ray - hands the projected samples over through
+// shared memory and splats with warp = (plane, 32 neighbouring pixels), so that the reductions of a warp land on ~66
+// neighbouring pixels of ONE plane: their 32-byte sectors are hit 2-4 times while they are still in the L2 (the 1.8 GB
+// buffer of a 512x288x192 frame does not fit: with one thread per (ray, sample) in ray-major order every reduction
+// cost a DRAM round trip - 8.0 ms per frame).
+constexpr int kSplatRays = 32, kSplatPlanes = 8;
+
+__global__ void __launch_bounds__(kSplatRays * kSplatPlanes) interp_splat_kernel(const nsff_interpolate_args a,
+                                                                                   float* __restrict__ buf) {
+  __shared__ float sm[6][kSplatPlanes][kSplatRays + 1];       // ox, oy, rgb * 3, alpha  (NaN ox: nothing to splat)
+  const int dir = blockIdx.z;
+  const int t = threadIdx.x;
+  {
+    const int i = t >> 3, j = t & 7;                            // load phase: ray i, plane j
+    const int64_t r = (int64_t)blockIdx.x * kSplatRays + i;
+    const int sidx = blockIdx.y * kSplatPlanes + j;
+    float ox = __int_as_float(0x7fc00000), oy = 0.f, val[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < a.R && sidx < a.S) {
+      const int64_t p = r * a.S + sidx;
+      const float* xyz = a.xyzs + p * 3;
+      const float* fl = (dir ? a.flow_bw : a.flow_fw) + p * (dir ? a.ld_tp1 : a.ld_t);
+      const float scale = dir ? 1.f - a.dt : a.dt;
+      float w0[3], w1[3];
+      ndc2world_d(xyz, a.fx, a.fy, a.cx, a.cy, w0);
+      const float moved[3] = {xyz[0] + fl[0], xyz[1] + fl[1], xyz[2] + fl[2]};
+      ndc2world_d(moved, a.fx, a.fy, a.cx, a.cy, w1);
+      float q[3];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) q[c] = w0[c] + scale * (w1[c] - w0[c]);
-  const float* P = a.P;
-  const float u = P[0] * q[0] + P[1] * q[1] + P[2] * q[2] + P[3];
-  const float v = P[4] * q[0] + P[5] * q[1] + P[6] * q[2] + P[7];
-  const float d = P[8] * q[0] + P[9] * q[1] + P[10] * q[2] + P[11];
-  const float ox = u / d, oy = v / d;          // target pixel = source pixel + (uv - grid)   (rendering.py:405-410)
+      for (int c = 0; c < 3; ++c) q[c] = w0[c] + scale * (w1[c] - w0[c]);
+      const float* P = a.P;
+      const float u = P[0] * q[0] + P[1] * q[1] + P[2] * q[2] + P[3];
+      const float v = P[4] * q[0] + P[5] * q[1] + P[6] * q[2] + P[7];
+      const float d = P[8] * q[0] + P[9] * q[1] + P[10] * q[2] + P[11];
+      ox = u / d, oy = v / d;                    // target pixel = source pixel + (uv - grid)   (rendering.py:405-410)
+      const float* rgb = (dir ? a.rgb_tp1 : a.rgb_t) + p * (dir ? a.ld_tp1 : a.ld_t);
+      val[0] = rgb[0], val[1] = rgb[1], val[2] = rgb[2], val[3] = (dir ? a.alpha_tp1 : a.alpha_t)[p];
+    }
+    sm[0][j][i] = ox, sm[1][j][i] = oy;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) sm[2 + c][j][i] = val[c];
+  }
+  __syncthreads();
+  const int j = t >> 5, i = t & 31;                             // splat phase: plane j, ray i
+  const int sidx = blockIdx.y * kSplatPlanes + j;
+  const float ox = sm[0][j][i], oy = sm[1][j][i];
+  if (!(ox == ox) || sidx >= a.S) return;                       // (a NaN projection splats nowhere, as in the reference)
+  const float val[4] = {sm[2][j][i], sm[3][j][i], sm[4][j][i], sm[5][j][i]};
   const float x0 = floorf(ox), y0 = floorf(oy);
-  const float* rgb = (dir ? a.rgb_tp1 : a.rgb_t) + p * (dir ? a.ld_tp1 : a.ld_t);
-  const float alpha = (dir ? a.alpha_tp1 : a.alpha_t)[p];
-  const float val[4] = {rgb[0], rgb[1], rgb[2], alpha};
-  float* plane = buf + ((int64_t)dir * a.S + s) * a.R * kSplatStride;
+  float* plane = buf + ((int64_t)dir * a.S + sidx) * a.R * kSplatStride;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const float xi = x0 + (float)(k & 1), yi = y0 + (float)(k >> 1);
@@ -105,8 +128,9 @@ extern "C" int nsff_interpolate(const nsff_interpolate_args* args, float* scratc
     return NSFF_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   NSFF_CUDA_TRY(cudaMemsetAsync(scratch, 0, nsff_interpolate_scratch_floats(a.R, a.S) * sizeof(float), st));
-  const int64_t n = 2 * a.R * a.S;
-  interp_splat_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, st>>>(a, scratch);
+  const dim3 grid((unsigned)cdiv64(a.R, kSplatRays), (unsigned)cdiv64(a.S, kSplatPlanes), 2);
+  if (grid.y > 65535u) return NSFF_EUNSUPPORTED;
+  interp_splat_kernel<<<grid, kSplatRays * kSplatPlanes, 0, st>>>(a, scratch);
   int rc = after_launch();
   if (rc != NSFF_OK) return rc;
   interp_composite_kernel<<<(unsigned)cdiv64(a.R, 128), 128, 0, st>>>(a, scratch, rgb, depth);
