@@ -208,3 +208,55 @@ def test_bf16_gradients_are_within_the_reference_autocast_envelope(installed):
             if ours > 2.5 * envelope + 2e-2:
                 bad.append(f"{n}: ours {ours:.3e} > 2.5 x envelope {envelope:.3e} + 2e-2")
     assert not bad, "\n".join(bad)
+
+
+def test_training_step_replays_from_a_cuda_graph(installed):
+    """forward, fused NeRFWLoss, backward, the re-pack of the bf16 weight images and a capturable Adam are
+    stream-ordered device work - the whole step can be captured once and replayed.  The replayed steps must train (the
+    loss of the captured step, re-evaluated at every replay, falls) and leave finite parameters."""
+    import ref_harness as H
+    from nsff_pl_b200.losses import NeRFWLoss
+    models, emb, _, _ = build_fields(W=256, seed=61, precision="bf16", n_frames=8)
+    for m in models.values():
+        m.requires_grad_(True)
+    emb["t"].weight.requires_grad_(True)
+    params = [p for m in models.values() for p in m.parameters()] + [emb["t"].weight]
+    opt = torch.optim.Adam(params, lr=1e-3, fused=True, capturable=True)
+    R, S = 64, 32
+    rays, ts = synthetic_rays(R, n_frames=8, seed=62)
+    rays, ts = rays.cuda(), ts.cuda()
+    batch = H.to_device(H.make_batch(rays.cpu(), ts.cpu(), img_wh=(64, 36), seed=63), "cuda")
+    Ks, Ps = H.make_cameras(8, (64, 36), 0)
+    loss_fn = NeRFWLoss()
+    loss_fn.register_buffer("Ks", Ks)
+    loss_fn.register_buffer("Ps", Ps)
+    loss_fn.max_t = 7
+    loss_fn = loss_fn.cuda()
+    kw = dict(N_samples=S, perturb=0, noise_std=0, N_importance=0, test_time=False, output_transient_flow=["fw", "bw", "disocc"])
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        res = installed(models, emb, rays, ts, 7, **kw)
+        loss = sum(loss_fn(res, batch, epoch=3, output_transient=True, output_transient_flow=["fw", "bw", "disocc"]).values())
+        loss.backward()
+        opt.step()
+        return loss.detach()
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):                       # warm-up on the capture stream (fresh AccumulateGrad nodes, optimizer state)
+            step()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            loss = step()
+        losses = []
+        for _ in range(6):
+            g.replay()
+            losses.append(float(loss))
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    assert all(l == l and abs(l) < 1e6 for l in losses), losses
+    assert losses[-1] < losses[0], losses
+    assert all(torch.isfinite(p).all() for p in params)
