@@ -208,9 +208,12 @@ NSFF_API size_t nsff_field_bwd_tc_pack_bytes(const nsff_field_desc* desc /*host*
 NSFF_API int nsff_field_bwd_tc_pack(const nsff_field_desc* desc /*host*/, const nsff_field_params* params /*host*/,
                                     void* pack, void* stream);
 /*     `saved` (optional) = the buffer nsff_field_forward_save filled for the same (desc, B, out_mask): the hidden
- *     activations of every layer as tile images + ReLU bit planes, written by the forward kernel itself (its shared
- *     memory hidden chunks are those images).  With it nothing is recomputed; without it (NULL) the layers are
- *     re-evaluated by the GEMM kernel first.
+ *     activations of every layer as tile images + ReLU bit planes, written by the forward kernel itself.  With it
+ *     nothing is recomputed AND the dgrad GEMMs of all layers run as ONE chained launch per call (dZ of a layer stays in
+ *     tensor memory as the A operand of the next), followed by the weight-gradient GEMMs eight to a launch;
+ *     `scratch` then holds the dZ image of every layer (nsff_field_bwd_tc_scratch_bytes(.., with_saved = 1)).
+ *     Without it (NULL), or with an appearance code, or with NSFF_BWD_CHAIN=0 in the environment, the layers are
+ *     re-evaluated / differentiated one GEMM launch at a time.
  */
 NSFF_API size_t nsff_field_save_bytes(const nsff_field_desc* desc /*host*/, int64_t B, int out_mask);
 NSFF_API int nsff_field_forward_save(const nsff_field_desc* desc /*host*/, const void* pack,
