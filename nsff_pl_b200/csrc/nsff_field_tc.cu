@@ -33,6 +33,11 @@
 //   warp  16        : weight + bias producer (one elected lane)
 //   warp  17        : leader CTA: tcgen05.mma issuer (one elected lane walks a flat, host-built list of K-chunk ops);
 //                     peer CTA: relays "my weight half has landed" to the leader's barriers
+//   warp  20        : training kernels only (kSave): ships the staged tile images with cp.async.bulk stores
+//
+// The same kernel, instantiated with kBwd, runs the BACKWARD chain of a tile (launch_backward_chain, called by
+// nsff_field_backward_tc): dZ of a layer is the "hidden activation" kept in tensor memory, W^T blocks are streamed, the
+// epilogue masks with the forward's ReLU bits, two N = 64 accumulators produce the trunk-input gradient rows.
 //
 // Ordering notes.  (1) tcgen05.st -> tcgen05.wait::st -> tcgen05.fence::before_thread_sync -> mbarrier arrive |
 // mbarrier wait -> tcgen05.fence::after_thread_sync -> tcgen05.mma makes the written rows visible to the MMA.

@@ -3,7 +3,8 @@
 The reference gets its backward from torch autograd over ~25 nn.Linear layers and the einops/cumprod composite
 (train.py:178-198 -> rendering.py:83-300).  Here the forward is the same pair of kernels as inference
 (tcgen05 field kernel + composite) and the backward is hand-written:
-    FieldFn      -> nsff_field_backward_tc (bf16 tcgen05 GEMMs) or nsff_field_backward_fp32 (verification):
+    FieldFn      -> nsff_field_backward_tc (bf16 tcgen05: one chained dgrad launch per pass over the activations the
+                    forward saved, weight-gradient GEMMs eight to a launch) or nsff_field_backward_fp32 (verification):
                     recompute + dgrad/wgrad per layer, PE and code gradients
     CompositeFn  -> nsff_composite_backward    (reverse transmittance scans)
 Only cheap glue stays in torch (xyz + flow, embedding-table gathers), so their gradients come for free.
