@@ -44,7 +44,10 @@ def _program(tool, *args):
     return subs, ops
 
 
-@pytest.mark.parametrize("cfg", [(1, 0, 1), (0, 1, 1), (1, 1, 1), (0, 0, 1)], ids=["main", "warp", "main+pos", "warp-no-pos"])
+@pytest.mark.parametrize("cfg", [(1, 0, 1), (0, 1, 1), (1, 1, 1), (0, 0, 1), ("fwd", 15, 1), ("fwd", 15, 0, 1), ("fwd", 10, 1),
+                                 ("fwd", 1, 1), ("fwd", 19, 1)],
+                         ids=["main", "warp", "main+pos", "warp-no-pos", "fwd-inference", "fwd-train", "fwd-warp", "fwd-static",
+                              "fwd-sigma-only"])
 def test_every_hidden_publish_is_waited_for_before_the_next_one(tool, cfg):
     subs, ops = _program(tool, *cfg)
     assert ops and subs
